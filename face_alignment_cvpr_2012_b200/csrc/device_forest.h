@@ -1,0 +1,73 @@
+// Device image of the forests: flat 32-byte slot records (one L2 sector each), leaf tables with
+// the reference's per-leaf arithmetic folded in at load time.
+//
+// Replaces the pointer-linked TreeNode<S> (reference include/TreeNode.hpp:138-146: embedded Leaf +
+// Split + two heap pointers) for Tree<S>::evaluateMT (include/Tree.hpp:174-191).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "model.h"
+
+namespace crf {
+
+constexpr int kRowStride = 128;  // u32 words per integral row (CRF_ROW_STRIDE)
+constexpr int kPatch = 31;       // ForestParam::getPatchSize() for face_size 125 (include/Constants.hpp:26-30)
+constexpr int kHalfPatch = 15;   // patch_size / 2 (src/face_utils.cpp:281-282)
+constexpr int kParts = 10;
+constexpr int kMaxList = 128;    // composed-forest capacity per face (pathological compositions, see engine)
+
+// One slot = one tree node.  Children of an internal node are adjacent: left = child, right = child + 1
+// (left is serialised first: include/TreeNode.hpp:161-162).  Slots of a tree are laid out breadth-first
+// so the hot top levels share cache lines.
+struct alignas(32) DevSlot {
+  uint16_t a1, c1;   // rect1: a = y*kRowStride + x (word offset of the top-left corner), c = h*kRowStride
+  uint16_t a2, c2;   // rect2
+  uint8_t w1, w2;    // rect widths
+  uint8_t ch;        // feature channel == plane index
+  uint8_t is_leaf;
+  int16_t thr;       // ThresholdSplit::threshold clamped to [-256, 255] (|mean1 - mean2| <= 255)
+  uint16_t pad0;
+  uint32_t m1, m2;   // floor(2^31 / area) + 1: mean = umulhi(sum << 1, m) == sum / area for sum <= 255*area
+  int32_t child;     // internal: slot of the left child; leaf: forest-global leaf index
+  uint32_t pad1;
+};
+static_assert(sizeof(DevSlot) == 32, "slot must be one 32-byte sector");
+
+// MPLeaf (include/MPSample.hpp:137-159) with the vote predicate of src/face_utils.cpp:285-290 folded
+// into `mask` (bit i: part i votes) for the options of the context.
+struct DevMpLeaf {
+  int16_t off[kParts][2];
+  float weight;  // forground
+};
+
+struct PackedForest {
+  std::vector<DevSlot> slots;
+  std::vector<int32_t> roots;        // slot of the root of tree t (forest-major for the jungle)
+  std::vector<int32_t> forest_base;  // jungle: first tree of pose forest f in `roots`
+  std::vector<int32_t> forest_ntrees;
+  std::vector<int32_t> leaf_base;    // first forest-global leaf index of tree t
+  std::vector<int32_t> leaf_oid;     // Boost object id (pre-order node index) of leaf l inside its tree
+  // head pose
+  std::vector<float> hp_m;           // expected label of the leaf (src/face_utils.cpp:224-228), -1 when fg <= min_fg
+  // multi part
+  std::vector<DevMpLeaf> mp_leaf;
+  std::vector<uint16_t> mp_mask;
+  int max_depth = 0;
+};
+
+struct PackOptions {
+  float hp_min_foreground = 0.5f;
+  int ffd_min_samples = 2;
+  float ffd_min_foreground = 0.5f;
+  float ffd_min_pf = 0.25f;
+  float ffd_max_variance = 25.f;
+};
+
+int pack_forests(const std::vector<const FlatForest*>& forests, ForestKind kind, const PackOptions& opt, PackedForest& out, std::string& err);
+
+// Exact division helper shared by host checks and the device code.
+inline uint32_t magic_for_area(uint32_t area) { return (uint32_t)((1ull << 31) / area) + 1u; }
+
+}  // namespace crf

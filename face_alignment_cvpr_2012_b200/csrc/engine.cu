@@ -1,0 +1,954 @@
+// Per-GPU context, work buffers and the C ABI (include/crf_b200.h) of the CRF inference path.
+// Orchestrates what FaceForest::analyzeFace does for one face (reference src/FaceForest.cpp:183-258),
+// for whole batches of faces at a time.  There is no CPU fallback: every stage is a CUDA kernel.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "model.h"
+
+struct crf_model { crf::Model m; };
+
+namespace crf {
+
+thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(CRF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need) {
+    if (need <= bytes) return CRF_OK;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    size_t want = need + need / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, need); want = need; }
+    if (e != cudaSuccess) { p = nullptr; return fail(CRF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    bytes = want;
+    return CRF_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static int patches_1d(int len, int stride) { return len > kPatch ? (len - kPatch + stride - 1) / stride : 0; }
+
+// createKernel / initGaborKernels (include/FeatureChannelFactory.hpp:186-251), built in f64 with libm.
+static void build_gabor_bank(std::vector<float2> coef[5], int widths[5]) {
+  const double sigma = 1.0 / 2.0 * M_PI, dF = std::sqrt(2.0);
+  for (int nu = 0; nu <= 4; nu++) {
+    const double k = (M_PI / 2) / std::pow(dF, (double)nu);
+    double width = std::round((sigma / k) * 6 + 1);
+    if (std::fmod(width, 2.0) == 0.0) width++;
+    const int w = (int)width, off = (int)((width - 1) / 2);
+    widths[nu] = w;
+    coef[nu].assign((size_t)7 * w * w, make_float2(0.f, 0.f));
+    for (int mu = 0; mu < 7; mu++) {
+      const double phi = M_PI * mu / 8;
+      for (int i = 0; i < w; i++)
+        for (int j = 0; j < w; j++) {
+          const int x = i - off, y = j - off;
+          const double t1 = (std::pow(k, 2) / std::pow(sigma, 2)) *
+                            std::exp(-(std::pow((double)x, 2) + std::pow((double)y, 2)) * std::pow(k, 2) / (2 * std::pow(sigma, 2)));
+          const double t2 = std::cos(k * std::cos(phi) * x + k * std::sin(phi) * y) - std::exp(-(std::pow(sigma, 2) / 2));
+          const double t3 = std::sin(k * std::cos(phi) * x + k * std::sin(phi) * y);
+          coef[nu][(size_t)mu * w * w + (size_t)j * w + i] = make_float2((float)(t1 * t2), (float)(t1 * t3));
+        }
+    }
+  }
+}
+
+struct StageTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  size_t next = 0;
+  float ms[CRF_NUM_STAGES] = {0};
+  int launches[CRF_NUM_STAGES] = {0};
+  cudaEvent_t get() {
+    if (next == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[next++];
+  }
+  void collect() {
+    for (auto& s : spans) { float t = 0; if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) ms[s.stage] += t; }
+    spans.clear(); next = 0;
+  }
+  void destroy() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+};
+
+}  // namespace crf
+
+using namespace crf;
+
+struct crf_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  crf_options_t opt{};
+  int hp_ntrees = 0, mp_ntrees_cfg = 0, num_channels = 38;
+  PackedForest hp, mp;  // host copies (object-id maps for the stage API)
+  // device model
+  Buf d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5];
+  int gabor_width[5] = {0, 0, 0, 0, 0};
+  ComposeTables ct{};
+  // work buffers
+  Buf d_imgs[2], d_fd, d_scaled, d_stacks, d_mag, d_minmax, d_hp_leaf, d_ffd_leaf, d_face_roots, d_face_ntrees, d_votes, d_vote_counts, d_faces,
+      d_u8planes, d_counters, d_misc;
+  crf_counters_t cnt{};
+  bool counting = false;
+  StageTimer timer;
+  // geometry of the current launch
+  size_t scaled_fs = 0, stack_fs = 0, plane_stride = 0, mag_fs = 0, mag_ps = 0, hp_leaf_fs = 0, ffd_leaf_fs = 0, vote_cap = 0, u8_fs = 0;
+};
+
+namespace crf {
+
+struct Span {
+  crf_ctx* c; int stage; cudaEvent_t a = nullptr;
+  Span(crf_ctx* ctx, int st) : c(ctx), stage(st) {
+    if (c->timer.on) { a = c->timer.get(); cudaEventRecord(a, c->stream); }
+  }
+  ~Span() {
+    if (c->timer.on) { cudaEvent_t b = c->timer.get(); cudaEventRecord(b, c->stream); c->timer.spans.push_back({stage, a, b}); }
+  }
+};
+static inline void count_launch(crf_ctx* c, int stage, int n = 1) { c->cnt.kernel_launches += n; c->timer.launches[stage] += n; }
+
+#define KCHECK()                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                                      \
+    if (e_ != cudaSuccess) return fail(CRF_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class T>
+static int upload(Buf& b, const std::vector<T>& v, cudaStream_t s) {
+  int rc = b.reserve(std::max<size_t>(v.size() * sizeof(T), 16));
+  if (rc) return rc;
+  if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  return CRF_OK;
+}
+
+// Geometry + buffer sizing for a launch over `n` faces whose tallest scaled face is Hmax.
+struct Plan {
+  int n = 0, Hmax = 0, nplanes = 38;
+  int hp_stride = 4, ffd_stride = 3;
+  int tree_cap = 20;
+  bool need_gabor = true, want_u8 = false, need_hp = true, need_ffd = true;
+};
+
+static int ensure(crf_ctx* c, const Plan& p) {
+  const size_t n = (size_t)std::max(p.n, 1);
+  const int H = p.Hmax;
+  c->scaled_fs = (size_t)H * 128;
+  c->plane_stride = (size_t)(H + 1) * kRowStride;
+  c->stack_fs = c->plane_stride * p.nplanes;
+  c->mag_ps = (size_t)H * 128;
+  c->mag_fs = c->mag_ps * 35;
+  const size_t np_hp = (size_t)patches_1d(125, p.hp_stride) * patches_1d(H, p.hp_stride);
+  const size_t np_ffd = (size_t)patches_1d(125, p.ffd_stride) * patches_1d(H, p.ffd_stride);
+  c->hp_leaf_fs = np_hp * std::max(c->hp_ntrees, 1);
+  c->ffd_leaf_fs = np_ffd * p.tree_cap;
+  c->vote_cap = std::max<size_t>(c->ffd_leaf_fs, 1);
+  c->u8_fs = (size_t)p.nplanes * 125 * H;
+  int rc;
+  if ((rc = c->d_scaled.reserve(n * c->scaled_fs))) return rc;
+  if ((rc = c->d_stacks.reserve(n * c->stack_fs * 4))) return rc;
+  if (p.need_gabor) {
+    if ((rc = c->d_mag.reserve(n * c->mag_fs * 4))) return rc;
+    if ((rc = c->d_minmax.reserve(n * 35 * 2 * 4))) return rc;
+  }
+  if (p.need_hp && (rc = c->d_hp_leaf.reserve(std::max<size_t>(n * c->hp_leaf_fs * 4, 16)))) return rc;
+  if ((rc = c->d_face_roots.reserve(n * kMaxList * 4))) return rc;
+  if ((rc = c->d_face_ntrees.reserve(n * 4))) return rc;
+  if (p.need_ffd) {
+    if ((rc = c->d_ffd_leaf.reserve(std::max<size_t>(n * c->ffd_leaf_fs * 4, 16)))) return rc;
+    if ((rc = c->d_votes.reserve(n * kParts * c->vote_cap * sizeof(DevVote)))) return rc;
+    if ((rc = c->d_vote_counts.reserve(n * kParts * 4))) return rc;
+  }
+  if (p.want_u8 && (rc = c->d_u8planes.reserve(n * c->u8_fs))) return rc;
+  return CRF_OK;
+}
+
+// src/FaceForest.cpp:199-204 (scale, scaled size) + the argument checks of the path.
+static int make_desc(const crf_ctx* c, int rows, int cols, size_t step, size_t img_off, const crf_rect_t& b, FaceDesc& d) {
+  if (b.x < 0 || b.y < 0 || b.width <= 0 || b.height <= 0 || b.x + b.width > cols || b.y + b.height > rows)
+    return fail(CRF_ERR_ARG, "bbox outside image");
+  const float scale = static_cast<float>(125) / static_cast<float>(b.width);
+  const int sw = (int)(b.width * scale), sh = (int)(b.height * scale);
+  if (sw <= kPatch || sh <= kPatch) return fail(CRF_ERR_ARG, "scaled face smaller than a patch");
+  if (sw > 125) return fail(CRF_ERR_ARG, "scaled face wider than face_size");
+  if (sh > CRF_MAX_SCALED_H) return fail(CRF_ERR_ARG, "scaled face taller than CRF_MAX_SCALED_H (f32 integral exactness limit)");
+  d.img_off = img_off; d.img_step = step;
+  d.bx = b.x; d.by = b.y; d.bw = b.width; d.bh = b.height;
+  d.W = sw; d.H = sh; d.scale = scale; d.pad = 0;
+  d.scale_x = 1. / ((double)sw / b.width);
+  d.scale_y = 1. / ((double)sh / b.height);
+  (void)c;
+  return CRF_OK;
+}
+
+// ---- stage launchers (all on c->stream; fd/faces point at the first face of the launch) ----------
+static int launch_resize(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, const uint8_t* d_imgs) {
+  Span s(c, CRF_STAGE_RESIZE);
+  k_gray_resize<<<dim3(Hmax, n), 128, 0, c->stream>>>(fd, d_imgs, c->d_scaled.as<uint8_t>(), c->scaled_fs);
+  KCHECK(); count_launch(c, CRF_STAGE_RESIZE);
+  return CRF_OK;
+}
+
+static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool minmax_planes, bool want_u8) {
+  uint8_t* u8 = want_u8 ? c->d_u8planes.as<uint8_t>() : nullptr;
+  {
+    Span s(c, CRF_STAGE_PLAIN);
+    PlainPlanes pp{};
+    int nw;
+    if (!minmax_planes) { nw = 3; pp.which[0] = 0; pp.plane[0] = 0; pp.which[1] = 1; pp.plane[1] = 36; pp.which[2] = 2; pp.plane[2] = 37; }
+    else { nw = 2; pp.which[0] = 3; pp.plane[0] = 0; pp.which[1] = 4; pp.plane[1] = 1; }
+    k_plain_channels<<<dim3(nw, n), 128, 0, c->stream>>>(fd, c->d_scaled.as<uint8_t>(), c->scaled_fs, c->d_stacks.as<uint32_t>(), c->stack_fs,
+                                                         c->plane_stride, u8, c->u8_fs, pp);
+    KCHECK(); count_launch(c, CRF_STAGE_PLAIN);
+  }
+  if (minmax_planes) return CRF_OK;
+  Span s(c, CRF_STAGE_GABOR);
+  k_init_minmax<<<(n * 70 + 255) / 256, 256, 0, c->stream>>>(c->d_minmax.as<uint32_t>(), n * 70);
+  KCHECK();
+  const dim3 grid((Hmax + 15) / 16, 7, n);
+  const uint8_t* sc = c->d_scaled.as<uint8_t>();
+  float* mag = c->d_mag.as<float>();
+  uint32_t* mm = c->d_minmax.as<uint32_t>();
+  // heaviest scale first
+  k_gabor_mag<25><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[4].as<float2>(), 4, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
+  k_gabor_mag<19><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[3].as<float2>(), 3, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
+  k_gabor_mag<13><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[2].as<float2>(), 2, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
+  k_gabor_mag<9><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[1].as<float2>(), 1, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
+  k_gabor_mag<7><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[0].as<float2>(), 0, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
+  k_gabor_quant_integral<<<dim3(35, n), 128, 0, c->stream>>>(fd, mag, c->mag_fs, c->mag_ps, mm, c->d_stacks.as<uint32_t>(), c->stack_fs, c->plane_stride, 1,
+                                                             u8, c->u8_fs);
+  KCHECK(); count_launch(c, CRF_STAGE_GABOR, 7);
+  return CRF_OK;
+}
+
+static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool hp, int stride, const int32_t* roots, int ntrees, int smem_trees) {
+  const int stage = hp ? CRF_STAGE_HP_TRAVERSE : CRF_STAGE_FFD_TRAVERSE;
+  Span s(c, stage);
+  TraverseArgs a{};
+  a.fd = fd; a.stacks = c->d_stacks.as<uint32_t>(); a.stack_face_stride = c->stack_fs; a.plane_stride = c->plane_stride;
+  a.stride = stride;
+  if (hp) {
+    a.slots = c->d_hp_slots.as<DevSlot>(); a.roots = roots; a.ntrees = ntrees;
+    a.leaf_out = c->d_hp_leaf.as<int32_t>(); a.leaf_face_stride = c->hp_leaf_fs;
+    a.cnt_tests = CNT_HP_TESTS; a.cnt_trav = CNT_HP_TRAV;
+  } else {
+    a.slots = c->d_mp_slots.as<DevSlot>();
+    a.face_roots = c->d_face_roots.as<int32_t>(); a.face_ntrees = c->d_face_ntrees.as<int32_t>();
+    a.leaf_out = c->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->ffd_leaf_fs;
+    a.cnt_tests = CNT_FFD_TESTS; a.cnt_trav = CNT_FFD_TRAV;
+  }
+  a.counters = c->counting ? c->d_counters.as<unsigned long long>() : nullptr;
+  const int nx = patches_1d(125, stride), ny = patches_1d(Hmax, stride);
+  const int tiles = ((nx + 31) / 32) * ny;
+  if (tiles <= 0) return CRF_OK;
+  const size_t smem = (size_t)32 * smem_trees * 4;
+  constexpr int NW = 5;
+  if (c->counting) k_traverse<NW, true><<<dim3(tiles, n), NW * 32, smem, c->stream>>>(a);
+  else k_traverse<NW, false><<<dim3(tiles, n), NW * 32, smem, c->stream>>>(a);
+  KCHECK(); count_launch(c, stage);
+  return CRF_OK;
+}
+
+static int launch_hp_reduce(crf_ctx* c, const FaceDesc* fd, int n, int stride, bool compose, int list_cap, crf_face_t* faces) {
+  Span s(c, CRF_STAGE_HP_REDUCE);
+  ComposeTables ct = c->ct;
+  ct.list_cap = list_cap;
+  k_hp_reduce_compose<<<(n + 7) / 8, 256, 0, c->stream>>>(fd, n, c->d_hp_leaf.as<int32_t>(), c->hp_leaf_fs, c->hp_ntrees, stride, c->d_hp_m.as<float>(), ct,
+                                                          compose ? 1 : 0, faces, c->d_face_roots.as<int32_t>(), c->d_face_ntrees.as<int32_t>());
+  KCHECK(); count_launch(c, CRF_STAGE_HP_REDUCE);
+  return CRF_OK;
+}
+
+static int launch_votes_meanshift(crf_ctx* c, const FaceDesc* fd, int n, int stride, crf_face_t* faces) {
+  {
+    Span s(c, CRF_STAGE_VOTES);
+    k_votes<<<n, 256, 0, c->stream>>>(fd, c->d_ffd_leaf.as<int32_t>(), c->ffd_leaf_fs, c->d_face_ntrees.as<int32_t>(), stride, c->d_mp_mask.as<uint16_t>(),
+                                      c->d_mp_leaf.as<DevMpLeaf>(), c->d_votes.as<DevVote>(), c->vote_cap, c->d_vote_counts.as<int32_t>());
+    KCHECK(); count_launch(c, CRF_STAGE_VOTES);
+  }
+  Span s(c, CRF_STAGE_MEANSHIFT);
+  MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
+  k_meanshift<<<(n * kParts + 63) / 64, 64, 0, c->stream>>>(fd, n, c->d_votes.as<DevVote>(), c->vote_cap, c->d_vote_counts.as<int32_t>(), mo, faces,
+                                                            c->counting ? c->d_counters.as<unsigned long long>() : nullptr);
+  KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
+  return CRF_OK;
+}
+
+// The whole path for faces [0, n) of a launch: fd, faces are device pointers to the first of them.
+static int run_faces(crf_ctx* c, const FaceDesc* d_fd, int n, int Hmax, const uint8_t* d_imgs, crf_face_t* d_faces, bool headpose_only, int tree_cap,
+                     cudaEvent_t imgs_consumed) {
+  int rc;
+  if ((rc = launch_resize(c, d_fd, n, Hmax, d_imgs))) return rc;
+  if (imgs_consumed) CU(cudaEventRecord(imgs_consumed, c->stream));
+  if ((rc = launch_channels(c, d_fd, n, Hmax, false, false))) return rc;
+  if ((rc = launch_traverse(c, d_fd, n, Hmax, true, c->opt.hp_stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees))) return rc;
+  if ((rc = launch_hp_reduce(c, d_fd, n, c->opt.hp_stride, !headpose_only, tree_cap, d_faces))) return rc;
+  if (headpose_only) return CRF_OK;
+  if ((rc = launch_traverse(c, d_fd, n, Hmax, false, c->opt.ffd_stride, nullptr, 0, tree_cap))) return rc;
+  if ((rc = launch_votes_meanshift(c, d_fd, n, c->opt.ffd_stride, d_faces))) return rc;
+  return CRF_OK;
+}
+
+static int default_chunk(const crf_ctx* c) { return c->opt.max_chunk > 0 ? c->opt.max_chunk : 256; }
+
+static int pull_counters(crf_ctx* c) {
+  if (!c->counting) return CRF_OK;
+  unsigned long long h[CNT_NUM];
+  CU(cudaMemcpyAsync(h, c->d_counters.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->cnt.hp_node_tests += h[CNT_HP_TESTS]; c->cnt.ffd_node_tests += h[CNT_FFD_TESTS];
+  c->cnt.hp_traversals += h[CNT_HP_TRAV]; c->cnt.ffd_traversals += h[CNT_FFD_TRAV];
+  c->cnt.votes += h[CNT_VOTES]; c->cnt.vote_passes += h[CNT_VOTE_PASSES];
+  CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof h, c->stream));
+  return CRF_OK;
+}
+
+// Faces whose composition asked for more trees than the batched launch holds (flags bit 1; only reachable
+// when areaUnderCurve's Riemann sum overshoots, i.e. a near-zero head-pose variance) are re-run one at a
+// time with the widest list, so that the result still equals the reference-shaped oracle.
+static int rerun_wide(crf_ctx* c, const FaceDesc* d_fd_all, const std::vector<FaceDesc>& descs, const uint8_t* d_imgs, crf_face_t* d_faces_all,
+                      const std::vector<int>& which) {
+  for (int i : which) {
+    Plan p; p.n = 1; p.Hmax = descs[i].H; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = kMaxList;
+    int rc = ensure(c, p);
+    if (rc) return rc;
+    if ((rc = run_faces(c, d_fd_all + i, 1, p.Hmax, d_imgs, d_faces_all + i, false, kMaxList, nullptr))) return rc;
+  }
+  return CRF_OK;
+}
+
+// Host-resident inputs.  image(i) = pointer to frame i; faces are processed in chunks, frames of a chunk
+// are copied on a second stream into one of two device buffers so the copy of chunk k+1 overlaps chunk k.
+static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, int rows, int cols, size_t step, const crf_rect_t* boxes,
+                        const int* image_of_box, int n, crf_face_t* out, bool headpose_only) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (n < 0 || (n > 0 && (!images || !boxes || !out))) return fail(CRF_ERR_ARG, "null argument");
+  if (n == 0) return CRF_OK;
+  if (step < (size_t)cols * 3) return fail(CRF_ERR_ARG, "step smaller than a row");
+  CU(cudaSetDevice(c->device));
+  const size_t img_bytes = (size_t)rows * step;
+  // chunks of consecutive faces; a chunk's frames are the distinct frames its faces name
+  const int chunk = default_chunk(c);
+  std::vector<FaceDesc> descs((size_t)n);
+  struct Chunk { int f0, f1, Hmax; std::vector<int> frames; };
+  std::vector<Chunk> chunks;
+  for (int f0 = 0; f0 < n; f0 += chunk) {
+    Chunk ch; ch.f0 = f0; ch.f1 = std::min(n, f0 + chunk); ch.Hmax = 0;
+    for (int i = f0; i < ch.f1; i++) {
+      const int im = image_of_box ? image_of_box[i] : i;
+      if (im < 0 || im >= n_images) return fail(CRF_ERR_ARG, "image index out of range");
+      int slot = -1;
+      for (size_t k = ch.frames.size(); k-- > 0;) if (ch.frames[k] == im) { slot = (int)k; break; }
+      if (slot < 0) { slot = (int)ch.frames.size(); ch.frames.push_back(im); }
+      int rc = make_desc(c, rows, cols, step, (size_t)slot * img_bytes, boxes[i], descs[i]);
+      if (rc) return rc;
+      ch.Hmax = std::max(ch.Hmax, descs[i].H);
+    }
+    chunks.push_back(std::move(ch));
+  }
+  int rc;
+  if ((rc = c->d_fd.reserve((size_t)n * sizeof(FaceDesc)))) return rc;
+  if ((rc = c->d_faces.reserve((size_t)n * sizeof(crf_face_t)))) return rc;
+  CU(cudaMemcpyAsync(c->d_fd.p, descs.data(), (size_t)n * sizeof(FaceDesc), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->d_faces.p, 0, (size_t)n * sizeof(crf_face_t), c->stream));
+  c->cnt.h2d_bytes += (size_t)n * sizeof(FaceDesc);
+  size_t max_frames = 0; int Hmax_all = 0, max_faces = 0;
+  for (auto& ch : chunks) { max_frames = std::max(max_frames, ch.frames.size()); Hmax_all = std::max(Hmax_all, ch.Hmax); max_faces = std::max(max_faces, ch.f1 - ch.f0); }
+  for (int b = 0; b < 2; b++) if ((rc = c->d_imgs[b].reserve(max_frames * img_bytes))) return rc;
+  Plan p; p.n = max_faces; p.Hmax = Hmax_all; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
+  p.need_ffd = !headpose_only;
+  if ((rc = ensure(c, p))) return rc;
+  // the allocation above must not race with earlier work still using the buffers
+  auto copy_chunk = [&](size_t k) -> int {
+    const Chunk& ch = chunks[k];
+    const int b = (int)(k & 1);
+    if (k >= 2) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+    // consecutive frames that are also consecutive in host memory go in one copy
+    size_t i = 0;
+    while (i < ch.frames.size()) {
+      size_t j = i + 1;
+      while (j < ch.frames.size() && images[ch.frames[j]] == images[ch.frames[j - 1]] + img_bytes) j++;
+      CU(cudaMemcpyAsync(c->d_imgs[b].as<uint8_t>() + i * img_bytes, images[ch.frames[i]], (j - i) * img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+      i = j;
+    }
+    c->cnt.h2d_bytes += ch.frames.size() * img_bytes;
+    CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    return CRF_OK;
+  };
+  if ((rc = copy_chunk(0))) return rc;
+  for (size_t k = 0; k < chunks.size(); k++) {
+    const Chunk& ch = chunks[k];
+    const int b = (int)(k & 1);
+    if (k + 1 < chunks.size() && (rc = copy_chunk(k + 1))) return rc;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    Plan q = p; q.n = ch.f1 - ch.f0; q.Hmax = ch.Hmax;
+    if ((rc = ensure(c, q))) return rc;  // only recomputes strides (capacity already there)
+    if ((rc = run_faces(c, c->d_fd.as<FaceDesc>() + ch.f0, ch.f1 - ch.f0, ch.Hmax, c->d_imgs[b].as<uint8_t>(), c->d_faces.as<crf_face_t>() + ch.f0,
+                        headpose_only, c->mp_ntrees_cfg, c->ev_consumed[b])))
+      return rc;
+    // pathological compositions of this chunk (needs the chunk's frames, so check before they are overwritten)
+    if (!headpose_only) {
+      // flags live in the results; a cheap strided copy of the whole records of the chunk
+      std::vector<crf_face_t> tmp((size_t)(ch.f1 - ch.f0));
+      CU(cudaMemcpyAsync(tmp.data(), c->d_faces.as<crf_face_t>() + ch.f0, tmp.size() * sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      c->cnt.d2h_bytes += tmp.size() * sizeof(crf_face_t);
+      std::vector<int> wide;
+      for (size_t i = 0; i < tmp.size(); i++) if (tmp[i].flags & 2) wide.push_back(ch.f0 + (int)i);
+      if (!wide.empty()) {
+        if ((rc = rerun_wide(c, c->d_fd.as<FaceDesc>(), descs, c->d_imgs[b].as<uint8_t>(), c->d_faces.as<crf_face_t>(), wide))) return rc;
+        for (int i : wide)
+          CU(cudaMemcpyAsync(&tmp[(size_t)(i - ch.f0)], c->d_faces.as<crf_face_t>() + i, sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaEventRecord(c->ev_consumed[b], c->stream));
+      }
+      std::memcpy(out + ch.f0, tmp.data(), tmp.size() * sizeof(crf_face_t));
+    }
+  }
+  if (headpose_only) {
+    CU(cudaMemcpyAsync(out, c->d_faces.p, (size_t)n * sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->stream));
+    c->cnt.d2h_bytes += (size_t)n * sizeof(crf_face_t);
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->cnt.faces += n;
+  c->timer.collect();
+  return pull_counters(c);
+}
+
+}  // namespace crf
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* crf_last_error(void) { return g_last_error.c_str(); }
+const char* crf_version(void) { return "crf_b200 0.1 (sm_100a)"; }
+
+void crf_options_default(crf_options_t* o) {
+  if (!o) return;
+  o->hp_stride = 4; o->hp_min_foreground = 0.5f;                       // include/FaceForest.hpp:33-43
+  o->ffd_stride = 3; o->ffd_min_samples = 2; o->ffd_min_foreground = 0.5f; o->ffd_min_pf = 0.25f; o->ffd_max_variance = 25.f;  // :45-58
+  o->ms_kernel_size = 10; o->ms_max_iterations = 7; o->ms_stopping_criteria = 0.05f;  // include/MeanShift.hpp:16-25
+  o->max_chunk = 0; o->max_scaled_h = 0;
+}
+
+int crf_model_load(const char* hp_dir, int hp_ntrees, const char* ffd_dir, int ffd_ntrees, crf_model** out) {
+  if (!out || !hp_dir || !ffd_dir) return fail(CRF_ERR_ARG, "null argument");
+  *out = nullptr;
+  std::unique_ptr<crf_model> m(new crf_model());
+  std::string err;
+  int rc = load_model_dirs(hp_dir, hp_ntrees, ffd_dir, ffd_ntrees, m->m, err);
+  if (rc) { std::fprintf(stderr, "(!) %s\n", err.c_str()); return fail(rc, err); }
+  *out = m.release();
+  return CRF_OK;
+}
+
+int crf_model_save_packed(const crf_model* m, const char* path) {
+  if (!m || !path) return fail(CRF_ERR_ARG, "null argument");
+  std::string err;
+  int rc = save_model_packed(m->m, path, err);
+  return rc ? fail(rc, err) : CRF_OK;
+}
+
+int crf_model_load_packed(const char* path, crf_model** out) {
+  if (!out || !path) return fail(CRF_ERR_ARG, "null argument");
+  *out = nullptr;
+  std::unique_ptr<crf_model> m(new crf_model());
+  std::string err;
+  int rc = load_model_packed(path, m->m, err);
+  if (rc) return fail(rc, err);
+  *out = m.release();
+  return CRF_OK;
+}
+
+int crf_model_info(const crf_model* m, crf_model_info_t* info) {
+  if (!m || !info) return fail(CRF_ERR_ARG, "null argument");
+  std::memset(info, 0, sizeof *info);
+  info->hp_trees = (int)m->m.hp.trees.size();
+  for (auto& t : m->m.hp.trees) { info->hp_nodes += (int)t.nodes.size(); info->hp_leaves += (int)t.hp_leaves.size(); info->hp_max_depth = std::max(info->hp_max_depth, t.max_depth); }
+  info->mp_forests = (int)m->m.jungle.size();
+  for (auto& f : m->m.jungle)
+    for (auto& t : f.trees) { info->mp_trees++; info->mp_nodes += (int)t.nodes.size(); info->mp_leaves += (int)t.mp_leaves.size(); info->mp_max_depth = std::max(info->mp_max_depth, t.max_depth); }
+  info->patch_size = m->m.patch_size; info->face_size = m->m.face_size; info->num_channels = m->m.num_channels;
+  info->hp_ntrees_cfg = m->m.hp_ntrees_cfg; info->mp_ntrees_cfg = m->m.mp_ntrees_cfg;
+  return CRF_OK;
+}
+
+int crf_model_tree_dump(const crf_model* m, int which, int tree, int32_t* out, int cap_nodes) {
+  if (!m) return fail(CRF_ERR_ARG, "null argument");
+  if (which >= (int)m->m.jungle.size()) return fail(CRF_ERR_ARG, "forest index out of range");
+  const FlatForest& f = which < 0 ? m->m.hp : m->m.jungle[which];
+  if (tree < 0 || tree >= (int)f.trees.size()) return fail(CRF_ERR_ARG, "tree index out of range");
+  const FlatTree& t = f.trees[tree];
+  const int n = (int)t.nodes.size();
+  for (int i = 0; i < n && i < cap_nodes && out; i++) {
+    const FlatNode& nd = t.nodes[i];
+    int32_t* o = out + (size_t)i * 16;
+    const bool leaf = nd.leaf >= 0;
+    o[0] = leaf; o[1] = nd.depth; o[2] = nd.channel;
+    for (int k = 0; k < 4; k++) { o[3 + k] = nd.r1[k]; o[7 + k] = nd.r2[k]; }
+    o[11] = nd.threshold_raw; o[12] = nd.left; o[13] = nd.right;
+    o[14] = !leaf ? 0 : (which < 0 ? t.hp_leaves[nd.leaf].nsamples : t.mp_leaves[nd.leaf].samples);
+    o[15] = i;
+  }
+  return n;
+}
+
+void crf_model_free(crf_model* m) { delete m; }
+
+int crf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void crf_ctx_destroy(crf_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  Buf* all[] = {&c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
+                &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_scaled, &c->d_stacks, &c->d_mag, &c->d_minmax,
+                &c->d_hp_leaf, &c->d_ffd_leaf, &c->d_face_roots, &c->d_face_ntrees, &c->d_votes, &c->d_vote_counts, &c->d_faces, &c->d_u8planes, &c->d_counters,
+                &c->d_misc};
+  for (Buf* b : all) b->release();
+  c->timer.destroy();
+  for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf_ctx** out) {
+  if (!m || !out) return fail(CRF_ERR_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(CRF_ERR_CUDA, "no CUDA device: this library has no CPU fallback"); }
+  if (device < 0 || device >= ndev) return fail(CRF_ERR_ARG, "device index out of range");
+  if (m->m.jungle.size() != CRF_NUM_POSE_FORESTS) return fail(CRF_ERR_UNSUPPORTED, "the facial-feature jungle must hold 5 pose forests (src/FaceForest.cpp:216-222)");
+  CU(cudaSetDevice(device));
+  crf_ctx* c = new crf_ctx();
+  struct Guard { crf_ctx* c; ~Guard() { if (c) crf_ctx_destroy(c); } } guard{c};
+  c->device = device;
+  if (opt) c->opt = *opt; else crf_options_default(&c->opt);
+  if (c->opt.hp_stride < 1 || c->opt.ffd_stride < 1) return fail(CRF_ERR_ARG, "strides must be >= 1");
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+  }
+  PackOptions po;
+  po.hp_min_foreground = c->opt.hp_min_foreground; po.ffd_min_samples = c->opt.ffd_min_samples; po.ffd_min_foreground = c->opt.ffd_min_foreground;
+  po.ffd_min_pf = c->opt.ffd_min_pf; po.ffd_max_variance = c->opt.ffd_max_variance;
+  std::string err;
+  int rc = pack_forests({&m->m.hp}, KIND_HEADPOSE, po, c->hp, err);
+  if (rc) return fail(rc, err);
+  std::vector<const FlatForest*> jf;
+  for (auto& f : m->m.jungle) jf.push_back(&f);
+  rc = pack_forests(jf, KIND_MULTIPART, po, c->mp, err);
+  if (rc) return fail(rc, err);
+  c->hp_ntrees = (int)c->hp.roots.size();
+  c->mp_ntrees_cfg = m->m.mp_ntrees_cfg;
+  c->num_channels = m->m.num_channels;
+  if (c->hp_ntrees > kMaxList || c->mp_ntrees_cfg > kMaxList || c->mp_ntrees_cfg < 1) return fail(CRF_ERR_UNSUPPORTED, "forest size outside 1..128 trees");
+  if ((rc = upload(c->d_hp_slots, c->hp.slots, c->stream)) || (rc = upload(c->d_hp_roots, c->hp.roots, c->stream)) || (rc = upload(c->d_hp_m, c->hp.hp_m, c->stream)) ||
+      (rc = upload(c->d_mp_slots, c->mp.slots, c->stream)) || (rc = upload(c->d_mp_roots, c->mp.roots, c->stream)) ||
+      (rc = upload(c->d_mp_mask, c->mp.mp_mask, c->stream)) || (rc = upload(c->d_mp_leaf, c->mp.mp_leaf, c->stream)))
+    return rc;
+  // Riemann abscissae of areaUnderCurve (src/face_utils.cpp:304-323) for the bins of src/FaceForest.cpp:216-222
+  {
+    float poseT[6];
+    poseT[0] = -2.5; poseT[1] = -0.35; poseT[2] = -0.20; poseT[3] = -poseT[2]; poseT[4] = -poseT[1]; poseT[5] = -poseT[0];
+    std::vector<double> xs;
+    for (int j = 0; j < 5; j++) {
+      c->ct.bin_begin[j] = (int)xs.size();
+      const double step = 0.01;
+      for (double x = poseT[j]; x < poseT[j + 1]; x += step) xs.push_back(x);
+    }
+    c->ct.bin_begin[5] = (int)xs.size();
+    if ((rc = upload(c->d_xs, xs, c->stream))) return rc;
+    c->ct.xs = c->d_xs.as<double>();
+    c->ct.jungle_roots = c->d_mp_roots.as<int32_t>();
+    for (int i = 0; i < 5; i++) { c->ct.forest_base[i] = c->mp.forest_base[i]; c->ct.forest_ntrees[i] = c->mp.forest_ntrees[i]; }
+    c->ct.ntrees_cfg = c->mp_ntrees_cfg;
+    c->ct.list_cap = c->mp_ntrees_cfg;
+  }
+  {
+    std::vector<float2> coef[5];
+    build_gabor_bank(coef, c->gabor_width);
+    const int expect[5] = {7, 9, 13, 19, 25};
+    for (int i = 0; i < 5; i++) {
+      if (c->gabor_width[i] != expect[i]) return fail(CRF_ERR_STATE, "unexpected Gabor kernel width");
+      if ((rc = upload(c->d_coef[i], coef[i], c->stream))) return rc;
+    }
+  }
+  if ((rc = c->d_counters.reserve(sizeof(unsigned long long) * CNT_NUM))) return rc;
+  CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * CNT_NUM, c->stream));
+  if ((rc = c->d_misc.reserve(4096))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  guard.c = nullptr;
+  *out = c;
+  return CRF_OK;
+}
+
+int crf_ctx_set_profiling(crf_ctx* c, int on) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  c->timer.on = on & 1;
+  c->counting = (on & 2) != 0;
+  return CRF_OK;
+}
+
+int crf_ctx_stage_ms(crf_ctx* c, float ms[CRF_NUM_STAGES], int launches[CRF_NUM_STAGES]) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  for (int i = 0; i < CRF_NUM_STAGES; i++) { if (ms) ms[i] = c->timer.ms[i]; if (launches) launches[i] = c->timer.launches[i]; }
+  return CRF_OK;
+}
+
+int crf_ctx_counters(crf_ctx* c, crf_counters_t* out) {
+  if (!c || !out) return fail(CRF_ERR_ARG, "null argument");
+  *out = c->cnt;
+  return CRF_OK;
+}
+
+int crf_ctx_reset_counters(crf_ctx* c) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  c->cnt = crf_counters_t{};
+  for (int i = 0; i < CRF_NUM_STAGES; i++) { c->timer.ms[i] = 0; c->timer.launches[i] = 0; }
+  return CRF_OK;
+}
+
+void* crf_ctx_stream(crf_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int crf_host_alloc(void** p, size_t bytes) {
+  if (!p) return fail(CRF_ERR_ARG, "null argument");
+  CU(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+  return CRF_OK;
+}
+void crf_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int crf_analyze_faces(crf_ctx* c, const uint8_t* bgr, int rows, int cols, size_t step, const crf_rect_t* boxes, int n, crf_face_t* out) {
+  std::vector<int> zero((size_t)std::max(n, 0), 0);
+  const uint8_t* imgs[1] = {bgr};
+  return analyze_host(c, imgs, 1, rows, cols, step, boxes, zero.data(), n, out, false);
+}
+
+int crf_analyze_batch(crf_ctx* c, const uint8_t* const* images, int n_images, int rows, int cols, size_t step, const crf_rect_t* boxes,
+                      const int* image_of_box, int n, crf_face_t* out) {
+  if (!image_of_box && n > 0) return fail(CRF_ERR_ARG, "null argument");
+  return analyze_host(c, images, n_images, rows, cols, step, boxes, image_of_box, n, out, false);
+}
+
+static int crops_host(crf_ctx* c, const uint8_t* bgr_batch, int n, int rows, int cols, crf_face_t* out, bool hp_only) {
+  if (n < 0 || (n > 0 && !bgr_batch)) return fail(CRF_ERR_ARG, "null argument");
+  std::vector<const uint8_t*> imgs((size_t)std::max(n, 0));
+  std::vector<crf_rect_t> boxes((size_t)std::max(n, 0), crf_rect_t{0, 0, cols, rows});
+  for (int i = 0; i < n; i++) imgs[i] = bgr_batch + (size_t)i * rows * cols * 3;
+  return analyze_host(c, imgs.data(), n, rows, cols, (size_t)cols * 3, boxes.data(), nullptr, n, out, hp_only);
+}
+
+int crf_analyze_crops(crf_ctx* c, const uint8_t* bgr_batch, int n, int rows, int cols, crf_face_t* out) { return crops_host(c, bgr_batch, n, rows, cols, out, false); }
+int crf_headpose_crops(crf_ctx* c, const uint8_t* bgr_batch, int n, int rows, int cols, crf_face_t* out) { return crops_host(c, bgr_batch, n, rows, cols, out, true); }
+
+int crf_analyze_crops_device(crf_ctx* c, const uint8_t* d_bgr_batch, int n, int rows, int cols, crf_face_t* d_out, int headpose_only) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (n < 0 || (n > 0 && (!d_bgr_batch || !d_out))) return fail(CRF_ERR_ARG, "null argument");
+  if (n == 0) return CRF_OK;
+  CU(cudaSetDevice(c->device));
+  std::vector<FaceDesc> descs((size_t)n);
+  const size_t img_bytes = (size_t)rows * cols * 3;
+  int Hmax = 0;
+  for (int i = 0; i < n; i++) {
+    int rc = make_desc(c, rows, cols, (size_t)cols * 3, (size_t)i * img_bytes, crf_rect_t{0, 0, cols, rows}, descs[i]);
+    if (rc) return rc;
+    Hmax = std::max(Hmax, descs[i].H);
+  }
+  int rc;
+  if ((rc = c->d_fd.reserve((size_t)n * sizeof(FaceDesc)))) return rc;
+  CU(cudaMemcpyAsync(c->d_fd.p, descs.data(), (size_t)n * sizeof(FaceDesc), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(crf_face_t), c->stream));
+  const int chunk = default_chunk(c);
+  Plan p; p.n = std::min(n, chunk); p.Hmax = Hmax; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
+  p.need_ffd = !headpose_only;
+  if ((rc = ensure(c, p))) return rc;
+  for (int f0 = 0; f0 < n; f0 += chunk) {
+    const int m = std::min(chunk, n - f0);
+    if ((rc = run_faces(c, c->d_fd.as<FaceDesc>() + f0, m, Hmax, d_bgr_batch, d_out + f0, headpose_only != 0, c->mp_ntrees_cfg, nullptr))) return rc;
+  }
+  if (!headpose_only) {
+    // pathological compositions: fetch the flags, re-run those faces with the widest list
+    std::vector<crf_face_t> tmp((size_t)n);
+    CU(cudaMemcpyAsync(tmp.data(), d_out, (size_t)n * sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<int> wide;
+    for (int i = 0; i < n; i++) if (tmp[(size_t)i].flags & 2) wide.push_back(i);
+    if (!wide.empty() && (rc = rerun_wide(c, c->d_fd.as<FaceDesc>(), descs, d_bgr_batch, d_out, wide))) return rc;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->cnt.faces += n;
+  c->timer.collect();
+  return pull_counters(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage-level entry points
+// ---------------------------------------------------------------------------------------------
+int crf_stage_gray_resize(crf_ctx* c, const uint8_t* bgr, int rows, int cols, size_t step, crf_rect_t box, uint8_t* scaled, int* W, int* H) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!bgr || !scaled) return fail(CRF_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  FaceDesc d;
+  int rc = make_desc(c, rows, cols, step, 0, box, d);
+  if (rc) return rc;
+  Plan p; p.n = 1; p.Hmax = d.H; p.need_gabor = false; p.need_hp = false; p.need_ffd = false;
+  if ((rc = ensure(c, p)) || (rc = c->d_fd.reserve(sizeof d)) || (rc = c->d_imgs[0].reserve((size_t)rows * step))) return rc;
+  CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_imgs[0].p, bgr, (size_t)rows * step, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = launch_resize(c, c->d_fd.as<FaceDesc>(), 1, d.H, c->d_imgs[0].as<uint8_t>()))) return rc;
+  CU(cudaMemcpy2DAsync(scaled, d.W, c->d_scaled.p, 128, d.W, d.H, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (W) *W = d.W;
+  if (H) *H = d.H;
+  return CRF_OK;
+}
+
+static int stage_upload_scaled(crf_ctx* c, const uint8_t* scaled, int W, int H, int nplanes, bool gabor, bool want_u8, bool hp, bool ffd, int tree_cap,
+                               int hp_stride, int ffd_stride) {
+  if (W <= kPatch || W > 125 || H <= kPatch || H > CRF_MAX_SCALED_H) return fail(CRF_ERR_ARG, "plane size outside (31,125] x (31,521]");
+  FaceDesc d{};
+  d.W = W; d.H = H; d.bw = W; d.bh = H; d.scale = 125.f / W; d.scale_x = d.scale_y = 1.0;
+  Plan p; p.n = 1; p.Hmax = H; p.nplanes = nplanes; p.need_gabor = gabor; p.want_u8 = want_u8; p.need_hp = hp; p.need_ffd = ffd; p.tree_cap = tree_cap;
+  p.hp_stride = hp_stride; p.ffd_stride = ffd_stride;
+  int rc;
+  if ((rc = ensure(c, p)) || (rc = c->d_fd.reserve(sizeof d))) return rc;
+  CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->stream));
+  if (scaled) CU(cudaMemcpy2DAsync(c->d_scaled.p, 128, scaled, W, W, H, cudaMemcpyHostToDevice, c->stream));
+  return CRF_OK;
+}
+
+static int stage_download_planes(crf_ctx* c, int nplanes, int W, int H, uint8_t* planes_u8, uint32_t* integrals) {
+  if (planes_u8) CU(cudaMemcpyAsync(planes_u8, c->d_u8planes.p, (size_t)nplanes * W * H, cudaMemcpyDeviceToHost, c->stream));
+  if (integrals)
+    for (int pl = 0; pl < nplanes; pl++)
+      CU(cudaMemcpy2DAsync(integrals + (size_t)pl * (H + 1) * (W + 1), (size_t)(W + 1) * 4, c->d_stacks.as<uint32_t>() + (size_t)pl * c->plane_stride,
+                           (size_t)kRowStride * 4, (size_t)(W + 1) * 4, H + 1, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return CRF_OK;
+}
+
+int crf_stage_channels(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!scaled) return fail(CRF_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = stage_upload_scaled(c, scaled, W, H, 38, true, true, false, false, 1, 4, 3);
+  if (rc) return rc;
+  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, false, true))) return rc;
+  return stage_download_planes(c, 38, W, H, planes_u8, integrals);
+}
+
+int crf_stage_minmax(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!scaled) return fail(CRF_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = stage_upload_scaled(c, scaled, W, H, 38, false, true, false, false, 1, 4, 3);
+  if (rc) return rc;
+  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, true, true))) return rc;
+  return stage_download_planes(c, 2, W, H, planes_u8, integrals);
+}
+
+// planes -> integral stack of one synthetic face
+static int stage_planes_to_stack(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int H, bool hp, bool ffd, int tree_cap, int hp_stride, int ffd_stride) {
+  if (!planes_u8) return fail(CRF_ERR_ARG, "null argument");
+  if (C < 1 || C > 64) return fail(CRF_ERR_ARG, "plane count outside 1..64");
+  int rc = stage_upload_scaled(c, nullptr, W, H, C, false, true, hp, ffd, tree_cap, hp_stride, ffd_stride);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->d_u8planes.p, planes_u8, (size_t)C * W * H, cudaMemcpyHostToDevice, c->stream));
+  k_integral_from_u8<<<dim3(C, 1), 128, 0, c->stream>>>(c->d_u8planes.as<uint8_t>(), W, H, c->d_stacks.as<uint32_t>(), c->stack_fs, c->plane_stride);
+  KCHECK(); count_launch(c, CRF_STAGE_PLAIN);
+  return CRF_OK;
+}
+
+static int max_channel_used(const PackedForest& f) {
+  int m = 0;
+  for (const DevSlot& s : f.slots) if (!s.is_leaf) m = std::max(m, (int)s.ch);
+  return m;
+}
+
+static int stage_set_list(crf_ctx* c, const int* tree_forest, const int* tree_index, int ntrees) {
+  if (!tree_forest || !tree_index || ntrees < 0 || ntrees > kMaxList) return fail(CRF_ERR_ARG, "bad composed forest");
+  std::vector<int32_t> list((size_t)kMaxList, 0);
+  for (int i = 0; i < ntrees; i++) {
+    if (tree_forest[i] < 0 || tree_forest[i] >= CRF_NUM_POSE_FORESTS || tree_index[i] < 0 || tree_index[i] >= c->mp.forest_ntrees[tree_forest[i]])
+      return fail(CRF_ERR_ARG, "bad composed forest");
+    list[i] = c->mp.roots[c->mp.forest_base[tree_forest[i]] + tree_index[i]];
+  }
+  CU(cudaMemcpyAsync(c->d_face_roots.p, list.data(), kMaxList * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_face_ntrees.p, &ntrees, 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // `list` and `ntrees` are stack/local host memory
+  return CRF_OK;
+}
+
+int crf_stage_eval_forest(crf_ctx* c, int which, const int* tree_forest, const int* tree_index, int ntrees, const uint8_t* planes_u8, int C, int W, int H,
+                          int stride, int32_t* leaf_ids) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!leaf_ids || stride < 1) return fail(CRF_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  const bool hp = which < 0;
+  const PackedForest& pf = hp ? c->hp : c->mp;
+  if (max_channel_used(pf) >= C) return fail(CRF_ERR_ARG, "forest reads a channel the planes do not provide");
+  const int nt = hp ? c->hp_ntrees : ntrees;
+  int rc = stage_planes_to_stack(c, planes_u8, C, W, H, hp, !hp, std::max(nt, 1), stride, stride);
+  if (rc) return rc;
+  if (!hp && (rc = stage_set_list(c, tree_forest, tree_index, ntrees))) return rc;
+  if ((rc = launch_traverse(c, c->d_fd.as<FaceDesc>(), 1, H, hp, stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, std::max(nt, 1)))) return rc;
+  const size_t n = (size_t)patches_1d(W, stride) * patches_1d(H, stride) * nt;
+  std::vector<int32_t> raw(n);
+  if (n) CU(cudaMemcpyAsync(raw.data(), hp ? c->d_hp_leaf.p : c->d_ffd_leaf.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < n; i++) leaf_ids[i] = pf.leaf_oid[(size_t)raw[i]];
+  c->timer.collect();
+  return pull_counters(c);
+}
+
+static void fill_list_out(crf_ctx* c, const std::vector<int32_t>& list, int n, int* tree_forest, int* tree_index) {
+  for (int i = 0; i < n; i++) {
+    const auto it = std::upper_bound(c->mp.roots.begin(), c->mp.roots.end(), list[i]);  // roots ascend with the tree number
+    const int t = (int)(it - c->mp.roots.begin()) - 1;
+    int f = 0;
+    while (f + 1 < CRF_NUM_POSE_FORESTS && c->mp.forest_base[f + 1] <= t) f++;
+    if (tree_forest) tree_forest[i] = f;
+    if (tree_index) tree_index[i] = t - c->mp.forest_base[f];
+  }
+}
+
+static int stage_fetch_compose(crf_ctx* c, float* headpose, float* variance, int* tree_counts, int* dominant, int* tree_forest, int* tree_index, int* ntrees, int* flags) {
+  crf_face_t face;
+  std::vector<int32_t> list((size_t)kMaxList);
+  int nt = 0;
+  CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(list.data(), c->d_face_roots.p, kMaxList * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&nt, c->d_face_ntrees.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (headpose) *headpose = face.headpose;
+  if (variance) *variance = face.variance;
+  if (tree_counts) std::memcpy(tree_counts, face.tree_counts, sizeof face.tree_counts);
+  if (dominant) *dominant = face.dominant;
+  if (flags) *flags = face.flags & 1;
+  if (ntrees) *ntrees = nt;
+  fill_list_out(c, list, nt, tree_forest, tree_index);
+  return CRF_OK;
+}
+
+int crf_stage_headpose(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int H, int stride, float* headpose, float* variance,
+                       int tree_counts[CRF_NUM_POSE_FORESTS], int* dominant, int* tree_forest, int* tree_index, int* ntrees, int* flags) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (stride < 1) return fail(CRF_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  if (max_channel_used(c->hp) >= C) return fail(CRF_ERR_ARG, "forest reads a channel the planes do not provide");
+  int rc = stage_planes_to_stack(c, planes_u8, C, W, H, true, false, 1, stride, stride);
+  if (rc) return rc;
+  if ((rc = c->d_faces.reserve(sizeof(crf_face_t)))) return rc;
+  CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->stream));
+  if ((rc = launch_traverse(c, c->d_fd.as<FaceDesc>(), 1, H, true, stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees))) return rc;
+  if ((rc = launch_hp_reduce(c, c->d_fd.as<FaceDesc>(), 1, stride, true, kMaxList, c->d_faces.as<crf_face_t>()))) return rc;
+  rc = stage_fetch_compose(c, headpose, variance, tree_counts, dominant, tree_forest, tree_index, ntrees, flags);
+  c->timer.collect();
+  return rc ? rc : pull_counters(c);
+}
+
+int crf_stage_compose(crf_ctx* c, float headpose, float variance, int tree_counts[CRF_NUM_POSE_FORESTS], int* dominant, int* tree_forest, int* tree_index,
+                      int* ntrees, int* flags) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  CU(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = c->d_faces.reserve(sizeof(crf_face_t))) || (rc = c->d_face_roots.reserve(kMaxList * 4)) || (rc = c->d_face_ntrees.reserve(4))) return rc;
+  CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->stream));
+  ComposeTables ct = c->ct;
+  ct.list_cap = kMaxList;
+  k_compose_only<<<1, 32, 0, c->stream>>>(headpose, variance, ct, c->d_faces.as<crf_face_t>(), c->d_face_roots.as<int32_t>(), c->d_face_ntrees.as<int32_t>());
+  KCHECK(); count_launch(c, CRF_STAGE_HP_REDUCE);
+  return stage_fetch_compose(c, nullptr, nullptr, tree_counts, dominant, tree_forest, tree_index, ntrees, flags);
+}
+
+int crf_stage_votes_meanshift(crf_ctx* c, const int* tree_forest, const int* tree_index, int ntrees, const uint8_t* planes_u8, int C, int W, int H, int stride,
+                              int n_votes[CRF_NUM_PARTS], float* votes_xyw, int vote_cap, float mean_xy[CRF_NUM_PARTS][2], int rounded_xy[CRF_NUM_PARTS][2],
+                              int iters[CRF_NUM_PARTS]) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (stride < 1) return fail(CRF_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  if (max_channel_used(c->mp) >= C) return fail(CRF_ERR_ARG, "forest reads a channel the planes do not provide");
+  int rc = stage_planes_to_stack(c, planes_u8, C, W, H, false, true, std::max(ntrees, 1), stride, stride);
+  if (rc) return rc;
+  if ((rc = stage_set_list(c, tree_forest, tree_index, ntrees))) return rc;
+  if ((rc = c->d_faces.reserve(sizeof(crf_face_t)))) return rc;
+  CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->stream));
+  if ((rc = launch_traverse(c, c->d_fd.as<FaceDesc>(), 1, H, false, stride, nullptr, 0, std::max(ntrees, 1)))) return rc;
+  const int saved = c->opt.ffd_stride;
+  if ((rc = launch_votes_meanshift(c, c->d_fd.as<FaceDesc>(), 1, stride, c->d_faces.as<crf_face_t>()))) return rc;
+  (void)saved;
+  crf_face_t face;
+  CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int p = 0; p < kParts; p++) {
+    if (n_votes) n_votes[p] = face.n_votes[p];
+    if (mean_xy) { mean_xy[p][0] = face.ffd_f[p][0]; mean_xy[p][1] = face.ffd_f[p][1]; }
+    if (rounded_xy) { rounded_xy[p][0] = face.ffd_scaled[p][0]; rounded_xy[p][1] = face.ffd_scaled[p][1]; }
+    if (iters) iters[p] = face.ms_iters[p];
+    if (votes_xyw && vote_cap > 0) {
+      const int n = std::min(face.n_votes[p], vote_cap);
+      std::vector<DevVote> v((size_t)n);
+      if (n) CU(cudaMemcpy(v.data(), c->d_votes.as<DevVote>() + (size_t)p * c->vote_cap, (size_t)n * sizeof(DevVote), cudaMemcpyDeviceToHost));
+      for (int k = 0; k < n; k++) {
+        float* o = votes_xyw + ((size_t)p * vote_cap + k) * 3;
+        o[0] = v[k].x; o[1] = v[k].y; o[2] = v[k].w;
+      }
+    }
+  }
+  c->timer.collect();
+  return pull_counters(c);
+}
+
+int crf_stage_meanshift(crf_ctx* c, const float* votes_xyw, int n, float mean_xy[2], int rounded_xy[2], int* iters) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (n < 0 || (n > 0 && !votes_xyw)) return fail(CRF_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  std::vector<DevVote> v((size_t)n);
+  for (int i = 0; i < n; i++) { v[i].x = (short)votes_xyw[3 * i]; v[i].y = (short)votes_xyw[3 * i + 1]; v[i].w = votes_xyw[3 * i + 2]; }
+  int rc;
+  if ((rc = c->d_votes.reserve(std::max<size_t>((size_t)n * sizeof(DevVote), 16)))) return rc;
+  if (n) CU(cudaMemcpyAsync(c->d_votes.p, v.data(), (size_t)n * sizeof(DevVote), cudaMemcpyHostToDevice, c->stream));
+  MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
+  float* d_mean = c->d_misc.as<float>();
+  int* d_rnd = reinterpret_cast<int*>(d_mean + 2);
+  int* d_it = d_rnd + 2;
+  k_meanshift_one<<<1, 1, 0, c->stream>>>(c->d_votes.as<DevVote>(), n, mo, d_mean, d_rnd, d_it);
+  KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
+  struct { float m[2]; int r[2]; int it; } h;
+  CU(cudaMemcpyAsync(&h, d_mean, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (mean_xy) { mean_xy[0] = h.m[0]; mean_xy[1] = h.m[1]; }
+  if (rounded_xy) { rounded_xy[0] = h.r[0]; rounded_xy[1] = h.r[1]; }
+  if (iters) *iters = h.it;
+  return CRF_OK;
+}
+
+}  // extern "C"

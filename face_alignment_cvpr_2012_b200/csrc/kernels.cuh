@@ -1,0 +1,623 @@
+// sm_100a kernels of the CRF inference path.  Compiled with -fmad=false: every float/double
+// operation below rounds separately unless it is an explicit __fmaf_rn, which is what the
+// canonical arithmetic (restated by oracle/crf_oracle.cc) requires.
+//
+// No tensor cores on purpose: nothing on this path is a dense contraction that tolerates reduced
+// precision (the Gabor bank must stay f32-exact in raster order; the forests are integer gathers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/crf_b200.h"
+#include "device_forest.h"
+
+namespace crf {
+
+// Per-face work descriptor, filled on the host (src/FaceForest.cpp:199-204 size arithmetic).
+struct FaceDesc {
+  unsigned long long img_off;  // byte offset of the BGR frame inside the device image buffer
+  unsigned long long img_step; // bytes per frame row
+  int bx, by, bw, bh;          // face box inside the frame
+  int W, H;                    // size after cv::resize (W in {124, 125})
+  float scale;                 // face_size / bw (f32)
+  int pad;
+  double scale_x, scale_y;     // 1 / ((double)W / bw), 1 / ((double)H / bh)   (cv::resize)
+};
+
+enum { CNT_HP_TESTS = 0, CNT_FFD_TESTS, CNT_HP_TRAV, CNT_FFD_TRAV, CNT_VOTES, CNT_VOTE_PASSES, CNT_NUM };
+
+__device__ __forceinline__ int border101(int p, int len) {  // BORDER_REFLECT_101
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2 + a3: cvtColor(BGR2GRAY) on the ROI and cv::resize(INTER_LINEAR) to W x H
+// (src/FaceForest.cpp:196-204).  One thread per destination pixel.
+// scaled: [face][Hcap][128] u8.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int gray_at(const uint8_t* __restrict__ roi, unsigned long long step, int y, int x) {
+  const uint8_t* p = roi + (size_t)y * step + (size_t)x * 3;
+  return (p[2] * 9798 + p[1] * 19235 + p[0] * 3735 + 16384) >> 15;
+}
+
+__global__ void __launch_bounds__(128) k_gray_resize(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ imgs,
+                                                     uint8_t* __restrict__ scaled, size_t scaled_face_stride) {
+  const FaceDesc d = fd[blockIdx.y];
+  const int dy = blockIdx.x, dx = threadIdx.x;
+  if (dy >= d.H) return;
+  uint8_t* out = scaled + blockIdx.y * scaled_face_stride + (size_t)dy * 128;
+  if (dx >= d.W) { out[dx] = 0; return; }
+  const uint8_t* roi = imgs + d.img_off + (size_t)d.by * d.img_step + (size_t)d.bx * 3;
+  float fx = (float)((dx + 0.5) * d.scale_x - 0.5);
+  int sx = (int)floorf(fx);
+  fx -= sx;
+  if (sx < 0) { fx = 0; sx = 0; }
+  if (sx >= d.bw - 1) { fx = 0; sx = d.bw - 1; }
+  const int a0 = __float2int_rn((1.f - fx) * 2048.f), a1 = __float2int_rn(fx * 2048.f);
+  float fy = (float)((dy + 0.5) * d.scale_y - 0.5);
+  int sy = (int)floorf(fy);
+  fy -= sy;
+  const int b0 = __float2int_rn((1.f - fy) * 2048.f), b1 = __float2int_rn(fy * 2048.f);
+  const int sy0 = min(max(sy, 0), d.bh - 1), sy1 = min(max(sy + 1, 0), d.bh - 1);
+  const int sx1 = min(sx + 1, d.bw - 1);
+  const int row0 = gray_at(roi, d.img_step, sy0, sx) * a0 + gray_at(roi, d.img_step, sy0, sx1) * a1;
+  const int row1 = gray_at(roi, d.img_step, sy1, sx) * a0 + gray_at(roi, d.img_step, sy1, sx1) * a1;
+  const int v = (((b0 * (row0 >> 4)) >> 16) + ((b1 * (row1 >> 4)) >> 16) + 2) >> 2;
+  out[dx] = (uint8_t)min(max(v, 0), 255);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv::integral (FeatureChannelFactory.hpp:51 etc.) of one W x H plane whose pixels
+// come from `pix(r, c)`.  128 threads.  Column sums run down the rows in registers (no
+// communication), then each 32-row band is scanned horizontally by warps and written with
+// fully coalesced 512-byte rows.  u32 on the device (exact; f32 in the reference is exact < 2^24).
+// out: (H+1) rows x kRowStride words.  u8out (optional): dense H x W copy of the 8-bit plane.
+// ---------------------------------------------------------------------------------------------
+template <class PixFn>
+__device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, uint32_t* __restrict__ out, uint8_t* __restrict__ u8out) {
+  __shared__ __align__(16) uint32_t band[32][kRowStride];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  out[tid] = 0;  // row 0
+  uint32_t run = 0;
+  for (int r0 = 0; r0 < H; r0 += 32) {
+    const int nr = min(32, H - r0);
+    for (int r = 0; r < nr; r++) {
+      uint32_t p = 0;
+      if (tid < W) {
+        p = pix(r0 + r, tid);
+        if (u8out) u8out[(size_t)(r0 + r) * W + tid] = (uint8_t)p;
+      }
+      run += p;
+      band[r][tid] = run;
+    }
+    __syncthreads();
+    for (int r = warp; r < nr; r += 4) {
+      uint4 v = *reinterpret_cast<uint4*>(&band[r][lane * 4]);
+      v.y += v.x; v.z += v.y; v.w += v.z;
+      uint32_t incl = v.w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      const uint32_t excl = incl - v.w;
+      v.x += excl; v.y += excl; v.z += excl; v.w += excl;
+      *reinterpret_cast<uint4*>(&band[r][lane * 4]) = v;
+    }
+    __syncthreads();
+    for (int r = 0; r < nr; r++)  // I[y+1][x+1] = sum; column 0 stays zero
+      out[(size_t)(r0 + r + 1) * kRowStride + tid] = tid == 0 ? 0u : band[r][tid - 1];
+    __syncthreads();
+  }
+}
+
+// a5 + a7 (+ a7b): FC_GRAY, FC_SOBEL (d/dy then d/dx, 8U-saturated), FC_MIN_MAX
+// (include/FeatureChannelFactory.hpp:46-57, :120-165).  grid = (nwhich, faces), 128 threads.
+// which: 0 gray, 1 Sobel dy, 2 Sobel dx, 3 erode, 4 dilate.  plane_of[which] = output plane index.
+struct PlainPlanes { int which[5]; int plane[5]; };
+
+__global__ void __launch_bounds__(128) k_plain_channels(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
+                                                        uint32_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride,
+                                                        uint8_t* __restrict__ u8planes, size_t u8_face_stride, PlainPlanes pp) {
+  const FaceDesc d = fd[blockIdx.y];
+  const int W = d.W, H = d.H;
+  const uint8_t* __restrict__ g = scaled + blockIdx.y * scaled_face_stride;
+  const int which = pp.which[blockIdx.x], plane = pp.plane[blockIdx.x];
+  uint32_t* out = stacks + blockIdx.y * stack_face_stride + (size_t)plane * plane_stride;
+  uint8_t* u8o = u8planes ? u8planes + blockIdx.y * u8_face_stride + (size_t)plane * W * H : nullptr;
+  auto G = [&](int y, int x) -> int { return g[(size_t)y * 128 + x]; };
+  if (which == 0) {
+    integral_plane([&](int r, int c) -> uint32_t { return G(r, c); }, W, H, out, u8o);
+  } else if (which == 1 || which == 2) {
+    const bool is_dx = which == 2;
+    integral_plane([&](int r, int c) -> uint32_t {
+      const int ym = border101(r - 1, H), yp = border101(r + 1, H), xm = border101(c - 1, W), xp = border101(c + 1, W);
+      int v;
+      if (is_dx) v = (G(ym, xp) + 2 * G(r, xp) + G(yp, xp)) - (G(ym, xm) + 2 * G(r, xm) + G(yp, xm));
+      else v = (G(yp, xm) + 2 * G(yp, c) + G(yp, xp)) - (G(ym, xm) + 2 * G(ym, c) + G(ym, xp));
+      return (uint32_t)min(max(v, 0), 255);
+    }, W, H, out, u8o);
+  } else {
+    const bool is_max = which == 4;
+    integral_plane([&](int r, int c) -> uint32_t {
+      int lo = 255, hi = 0;
+      for (int j = -1; j <= 1; j++)
+        for (int i = -1; i <= 1; i++) {
+          const int yy = r + j, xx = c + i;
+          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+          const int v = G(yy, xx);
+          lo = min(lo, v); hi = max(hi, v);
+        }
+      return (uint32_t)(is_max ? hi : lo);
+    }, W, H, out, u8o);
+  }
+}
+
+// Integral of caller-supplied dense u8 planes [C][H][W] (stage API: synthetic channels).
+__global__ void __launch_bounds__(128) k_integral_from_u8(const uint8_t* __restrict__ planes, int W, int H,
+                                                          uint32_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride) {
+  const uint8_t* __restrict__ p = planes + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * W * H;
+  uint32_t* out = stacks + blockIdx.y * stack_face_stride + (size_t)blockIdx.x * plane_stride;
+  integral_plane([&](int r, int c) -> uint32_t { return p[(size_t)r * W + c]; }, W, H, out, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a6, first half: the 35 complex Gabor responses (include/FeatureChannelFactory.hpp:253-270).
+// cv::filter2D = correlation, anchor centre, REFLECT_101, u8 -> f32; canonical accumulation =
+// raster order over the kernel, product and sum rounded separately.  Then
+// magnitude = sqrt(im*im + re*re).  One CTA = one 16-row band of one (face, orientation) at scale
+// NU (kernel size K); each thread owns 1 x 4 output strips, the band and its halo live in shared
+// memory as f32, coefficients are broadcast LDS.64.  Per-plane min/max via integer atomics
+// (magnitudes are >= 0, so float order == unsigned order).
+// mag: [face][35][Hcap][128] f32.  minmax: [face][35][2] u32 (initialised to {0x7f800000, 0}).
+// grid = (bands, 7, faces), 256 threads.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+struct GaborGeom {
+  static constexpr int R = K / 2;
+  static constexpr int NF4 = (K + 3 + 3) / 4;      // float4 loads covering 4 + K - 1 pixels
+  static constexpr int PITCH = 124 + 4 * NF4;      // floats per tile row
+  static constexpr int BAND = 16;
+  static constexpr int TH = BAND + K - 1;
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) k_gabor_mag(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
+                                                   const float2* __restrict__ coef /* this scale: [7][K*K] (re, im) raster order */, int nu,
+                                                   float* __restrict__ mag, size_t mag_face_stride, size_t mag_plane_stride,
+                                                   uint32_t* __restrict__ minmax) {
+  using G = GaborGeom<K>;
+  __shared__ __align__(16) float tile[G::TH][G::PITCH];
+  __shared__ float2 cf[K * K];
+  const FaceDesc d = fd[blockIdx.z];
+  const int W = d.W, H = d.H;
+  const int r0 = blockIdx.x * G::BAND;
+  if (r0 >= H) return;
+  const int mu = blockIdx.y, plane = nu * 7 + mu;
+  const int tid = threadIdx.x;
+  const uint8_t* __restrict__ g = scaled + blockIdx.z * scaled_face_stride;
+  for (int i = tid; i < K * K; i += 256) cf[i] = coef[mu * K * K + i];
+  for (int i = tid; i < G::TH * G::PITCH; i += 256) {
+    const int ty = i / G::PITCH, tx = i - ty * G::PITCH;
+    const int sy = border101(r0 + ty - G::R, H), sx = border101(tx - G::R, W);
+    tile[ty][tx] = (float)g[(size_t)sy * 128 + sx];
+  }
+  __syncthreads();
+  const int x0 = (tid & 31) * 4;
+  float vmin = __int_as_float(0x7f800000), vmax = 0.f;
+  float* mplane = mag + blockIdx.z * mag_face_stride + (size_t)plane * mag_plane_stride;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    const int r = (tid >> 5) + 8 * pass;
+    float re[4] = {0.f, 0.f, 0.f, 0.f}, im[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {
+      float px[4 * G::NF4];
+      const float4* row = reinterpret_cast<const float4*>(&tile[r + j][x0]);
+#pragma unroll
+      for (int q = 0; q < G::NF4; q++) {
+        const float4 v = row[q];
+        px[4 * q] = v.x; px[4 * q + 1] = v.y; px[4 * q + 2] = v.z; px[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < K; i++) {
+        const float2 c = cf[j * K + i];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+          re[o] = __fadd_rn(re[o], __fmul_rn(px[o + i], c.x));
+          im[o] = __fadd_rn(im[o], __fmul_rn(px[o + i], c.y));
+        }
+      }
+    }
+    if (r0 + r < H) {
+      float m[4];
+#pragma unroll
+      for (int o = 0; o < 4; o++) {
+        m[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[o], im[o]), __fmul_rn(re[o], re[o])));
+        if (x0 + o < W) { vmin = fminf(vmin, m[o]); vmax = fmaxf(vmax, m[o]); }
+      }
+      *reinterpret_cast<float4*>(&mplane[(size_t)(r0 + r) * 128 + x0]) = make_float4(m[0], m[1], m[2], m[3]);
+    }
+  }
+  uint32_t umin = __float_as_uint(vmin), umax = __float_as_uint(vmax);
+  umin = __reduce_min_sync(0xffffffffu, umin);
+  umax = __reduce_max_sync(0xffffffffu, umax);
+  if ((tid & 31) == 0) {
+    uint32_t* mm = minmax + ((size_t)blockIdx.z * 35 + plane) * 2;
+    atomicMin(&mm[0], umin);
+    atomicMax(&mm[1], umax);
+  }
+}
+
+// a6, second half: cv::normalize(NORM_MINMAX, 0, 1) as one single-rounded FMA, convertTo(8U, x255)
+// with round-half-even, then cv::integral (FeatureChannelFactory.hpp:271-283).
+// grid = (35, faces), 128 threads.  Gabor planes are 1..35 of the stack.
+__global__ void __launch_bounds__(128) k_gabor_quant_integral(const FaceDesc* __restrict__ fd, const float* __restrict__ mag, size_t mag_face_stride,
+                                                              size_t mag_plane_stride, const uint32_t* __restrict__ minmax,
+                                                              uint32_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride, int first_plane,
+                                                              uint8_t* __restrict__ u8planes, size_t u8_face_stride) {
+  const FaceDesc d = fd[blockIdx.y];
+  const int gp = blockIdx.x;
+  const float* __restrict__ m = mag + blockIdx.y * mag_face_stride + (size_t)gp * mag_plane_stride;
+  const uint32_t* mm = minmax + ((size_t)blockIdx.y * 35 + gp) * 2;
+  const double smin = (double)__uint_as_float(mm[0]), smax = (double)__uint_as_float(mm[1]);
+  const double dscale = (smax - smin) > 2.220446049250313e-16 ? 1. / (smax - smin) : 0.;
+  const double dshift = 0.0 - smin * dscale;
+  const float a = (float)dscale, b = (float)dshift;
+  const int plane = first_plane + gp;
+  uint32_t* out = stacks + blockIdx.y * stack_face_stride + (size_t)plane * plane_stride;
+  uint8_t* u8o = u8planes ? u8planes + blockIdx.y * u8_face_stride + (size_t)plane * d.W * d.H : nullptr;
+  integral_plane([&](int r, int c) -> uint32_t {
+    const float v = __fmaf_rn(m[(size_t)r * 128 + c], a, b);
+    const int iv = __float2int_rn(__fmul_rn(v, 255.f));
+    return (uint32_t)min(max(iv, 0), 255);
+  }, d.W, d.H, out, u8o);
+}
+
+__global__ void k_init_minmax(uint32_t* mm, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mm[i] = (i & 1) ? 0u : 0x7f800000u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9 + a10: Forest<S>::evaluateMT over the dense patch grid (HOT LOOPS A and B; src/face_utils.cpp:
+// 198-216, :256-274; include/Tree.hpp:174-191; src/ImageSample.cpp:48-63).
+// One CTA = one row of 32 x-adjacent patches of one face; its warps take the trees in turn, a lane
+// is one patch.  Lanes of a warp sit on the same node near the root, so the slot fetch is a broadcast
+// and each of the 8 corner loads is one coalesced 128-byte row segment; deeper down the lanes
+// diverge and the loads degrade into sector gathers served by L1/L2 (the stacks of the faces in
+// flight are L2-resident).
+// leaf_out: [face][patch (x outer, y inner)][tree] = forest-global leaf index.
+// grid = (tiles, faces); tile -> (iy, ixb).  NW warps per CTA.
+// ---------------------------------------------------------------------------------------------
+struct TraverseArgs {
+  const FaceDesc* fd;
+  const uint32_t* stacks;
+  size_t stack_face_stride, plane_stride;
+  const DevSlot* slots;
+  const int32_t* roots;        // shared tree list (head pose) or nullptr
+  const int32_t* face_roots;   // [face][kMaxList] composed lists (FFD) or nullptr
+  const int32_t* face_ntrees;  // [face] or nullptr
+  int ntrees;                  // used when face_ntrees == nullptr
+  int stride;
+  int32_t* leaf_out;
+  size_t leaf_face_stride;
+  unsigned long long* counters;  // nullptr = no counting
+  int cnt_tests, cnt_trav;
+};
+
+template <int NW, bool COUNT>
+__global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
+  extern __shared__ int32_t s_leaf[];  // [32][nt]
+  const int f = blockIdx.y;
+  const FaceDesc d = a.fd[f];
+  const int nx = (d.W - kPatch + a.stride - 1) / a.stride, ny = (d.H - kPatch + a.stride - 1) / a.stride;
+  const int nxb = (nx + 31) >> 5;
+  const int tile = blockIdx.x;
+  if (nx <= 0 || ny <= 0 || tile >= nxb * ny) return;
+  const int iy = tile / nxb, ixb = tile - iy * nxb;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ix = ixb * 32 + lane;
+  const bool active = ix < nx;
+  const int nt = a.face_ntrees ? a.face_ntrees[f] : a.ntrees;
+  const int32_t* roots = a.face_roots ? a.face_roots + (size_t)f * kMaxList : a.roots;
+  const uint32_t* __restrict__ origin = a.stacks + f * a.stack_face_stride + (size_t)(iy * a.stride) * kRowStride + (active ? ix : 0) * a.stride;
+  const DevSlot* __restrict__ slots = a.slots;
+  unsigned tests = 0;
+  for (int t = warp; t < nt; t += NW) {
+    int cur = roots[t];
+    int leaf = -1;
+    if (active) {
+      for (;;) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(slots + cur));
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(slots + cur) + 1);
+        // q0.x = a1 | c1<<16 ; q0.y = a2 | c2<<16 ; q0.z = w1 | w2<<8 | ch<<16 | leaf<<24 ; q0.w = thr (low 16)
+        // q1.x = m1 ; q1.y = m2 ; q1.z = child
+        if (q0.z >> 24) { leaf = (int)q1.z; break; }
+        const uint32_t* __restrict__ p = origin + (size_t)((q0.z >> 16) & 0xff) * a.plane_stride;
+        const uint32_t a1 = q0.x & 0xffff, c1 = q0.x >> 16, a2 = q0.y & 0xffff, c2 = q0.y >> 16, w1 = q0.z & 0xff, w2 = (q0.z >> 8) & 0xff;
+        const uint32_t A1 = __ldg(p + a1), B1 = __ldg(p + a1 + w1), C1 = __ldg(p + a1 + c1), D1 = __ldg(p + a1 + c1 + w1);
+        const uint32_t A2 = __ldg(p + a2), B2 = __ldg(p + a2 + w2), C2 = __ldg(p + a2 + c2), D2 = __ldg(p + a2 + c2 + w2);
+        const uint32_t s1 = D1 - B1 - C1 + A1, s2 = D2 - B2 - C2 + A2;
+        const int m1 = (int)__umulhi(s1 << 1, q1.x), m2 = (int)__umulhi(s2 << 1, q1.y);
+        const int thr = (int)(short)(q0.w & 0xffff);
+        cur = (int)q1.z + ((m1 - m2) > thr ? 1 : 0);  // go left iff mean1 - mean2 <= threshold
+        if (COUNT) tests++;
+      }
+    }
+    s_leaf[lane * nt + t] = leaf;
+  }
+  __syncthreads();
+  // rows of nt contiguous ints per patch
+  const int npatch_tile = min(32, nx - ixb * 32);
+  int32_t* out = a.leaf_out + f * a.leaf_face_stride;
+  for (int i = threadIdx.x; i < npatch_tile * nt; i += NW * 32) {
+    const int l = i / nt, t = i - l * nt;
+    out[((size_t)(ixb * 32 + l) * ny + iy) * nt + t] = s_leaf[i];
+  }
+  if (COUNT) {
+    tests = __reduce_add_sync(0xffffffffu, tests);
+    if (lane == 0 && tests) atomicAdd(&a.counters[a.cnt_tests], (unsigned long long)tests);
+    if (threadIdx.x == 0) atomicAdd(&a.counters[a.cnt_trav], (unsigned long long)npatch_tile * nt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8 (reduce) + a11: head-pose mean/variance in the reference's sequential f32 order
+// (src/face_utils.cpp:219-241), areaUnderCurve and forest composition (src/face_utils.cpp:304-323,
+// src/FaceForest.cpp:215-250).  One warp per face: lanes fetch 32 leaves,
+// then every lane folds them in index order (same instruction stream, so no divergence).
+// ---------------------------------------------------------------------------------------------
+struct ComposeTables {
+  const double* xs;        // concatenated Riemann abscissae of the 5 bins (x += 0.01 in double from (double)poseT[j])
+  int bin_begin[6];
+  const int32_t* jungle_roots;
+  int forest_base[CRF_NUM_POSE_FORESTS];
+  int forest_ntrees[CRF_NUM_POSE_FORESTS];
+  int ntrees_cfg;
+  int list_cap;            // trees a face may evaluate in this launch (<= kMaxList)
+};
+
+__device__ __forceinline__ void compose_face(float headpose, float variance, const ComposeTables& ct, int lane,
+                                             crf_face_t* face, int32_t* list, int32_t* ntrees_out) {
+  // areaUnderCurve(x1, x2, mean, std): lanes evaluate exp() of their abscissae, lane 0 folds in order.
+  const double mean = (double)headpose, sd = sqrt((double)variance);
+  __shared__ double s_e[8][32];
+  double* e = s_e[(threadIdx.x >> 5) & 7];
+  float area[CRF_NUM_POSE_FORESTS];
+  for (int j = 0; j < CRF_NUM_POSE_FORESTS; j++) {
+    double sum = 0;
+    for (int b = ct.bin_begin[j]; b < ct.bin_begin[j + 1]; b += 32) {
+      const int i = b + lane;
+      double v = 0;
+      if (i < ct.bin_begin[j + 1]) {
+        const double t = (ct.xs[i] - mean) / sd;
+        v = exp(-0.5 * (t * t)) * 0.01;
+      }
+      e[lane] = v;
+      __syncwarp();
+      const int n = min(32, ct.bin_begin[j + 1] - b);
+      for (int k = 0; k < n; k++) sum += e[k];
+      __syncwarp();
+    }
+    area[j] = (float)(sum * 1.0 / (sd * sqrt(2 * 3.14159265358979323846)));
+  }
+  if (lane != 0) return;
+  float max_area = 0;
+  int dominant = 0;
+  for (int j = 0; j < CRF_NUM_POSE_FORESTS; j++)
+    if (max_area < area[j]) { max_area = area[j]; dominant = j; }
+  int n = 0, flags = 0;
+  for (int i = 0; i < CRF_NUM_POSE_FORESTS; i++) {
+    const float prod = area[i] * ct.ntrees_cfg;
+    const double fl = floor((double)prod);
+    int cnt_req = (fl != fl || fl < -2147483648.0 || fl > 2147483647.0) ? INT_MIN : (int)fl;  // x86 cvttsd2si semantics
+    if (cnt_req > ct.forest_ntrees[i]) { cnt_req = ct.forest_ntrees[i]; flags |= 1; }
+    int cnt = 0;
+    for (int j = 0; j < cnt_req; j++) {
+      if (n < ct.list_cap) { list[n++] = ct.jungle_roots[ct.forest_base[i] + j]; cnt++; }
+      else flags |= 2;  // more trees than this launch holds: the engine re-runs the face with a wider list
+    }
+    face->tree_counts[i] = cnt;
+  }
+  for (int i = n; i < ct.ntrees_cfg; i++) {
+    if (i >= ct.forest_ntrees[dominant]) { flags |= 1; break; }
+    if (n < ct.list_cap) list[n++] = ct.jungle_roots[ct.forest_base[dominant] + i];
+    else flags |= 2;
+  }
+  face->dominant = dominant;
+  face->flags = flags;
+  *ntrees_out = n;
+}
+
+__global__ void __launch_bounds__(256) k_hp_reduce_compose(const FaceDesc* __restrict__ fd, int nfaces, const int32_t* __restrict__ leaf_ids, size_t leaf_face_stride,
+                                                           int ntrees, int stride, const float* __restrict__ hp_m, ComposeTables ct, int do_compose,
+                                                           crf_face_t* __restrict__ faces, int32_t* __restrict__ face_roots, int32_t* __restrict__ face_ntrees) {
+  __shared__ float s_m[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = blockIdx.x * 8 + warp;
+  if (f >= nfaces) return;
+  const FaceDesc d = fd[f];
+  const int nx = (d.W - kPatch + stride - 1) / stride, ny = (d.H - kPatch + stride - 1) / stride;
+  const int n = max(nx, 0) * max(ny, 0) * ntrees;
+  const int32_t* __restrict__ ids = leaf_ids + f * leaf_face_stride;
+  float cnt = 0, sum = 0, sum_sq = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int i = b + lane;
+    s_m[warp][lane] = i < n ? __ldg(hp_m + ids[i]) : -1.f;
+    __syncwarp();
+#pragma unroll 8
+    for (int k = 0; k < 32; k++) {
+      const float m = s_m[warp][k];
+      if (m >= 0.f || m != m) {  // fg > min_foreground_probability (folded into the table at load time)
+        sum += m;
+        sum_sq += m * m;
+        cnt += 1.f;
+      }
+    }
+    __syncwarp();
+  }
+  float mean = sum / cnt;
+  float var = (sum_sq / cnt) - (mean * mean);
+  mean -= 2;
+  var *= 0.05f;  // NORM_HEADPOSE_VARIANCE_FACTOR (include/Constants.hpp:67)
+  crf_face_t* face = faces + f;
+  if (lane == 0) {
+    face->headpose = mean;
+    face->variance = var;
+    face->scaled_w = d.W; face->scaled_h = d.H; face->scale = d.scale;
+  }
+  if (do_compose) compose_face(mean, var, ct, lane, face, face_roots + (size_t)f * kMaxList, face_ntrees + f);
+}
+
+// Composition alone (stage API).
+__global__ void k_compose_only(float headpose, float variance, ComposeTables ct, crf_face_t* face, int32_t* list, int32_t* ntrees) {
+  compose_face(headpose, variance, ct, threadIdx.x & 31, face, list, ntrees);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a12 (emission): ordered vote lists (src/face_utils.cpp:277-301).  Votes of part i keep
+// the reference's order (leaf index = patch-major, tree-minor) because MeanShift sums them in f32.
+// One CTA per face walks the leaves in chunks of 256 and compacts per part with warp ballots.
+// votes: [face][part][vote_cap] {x, y, weight}.
+// ---------------------------------------------------------------------------------------------
+struct __align__(8) DevVote { short x, y; float w; };
+
+__global__ void __launch_bounds__(256) k_votes(const FaceDesc* __restrict__ fd, const int32_t* __restrict__ leaf_ids, size_t leaf_face_stride,
+                                               const int32_t* __restrict__ face_ntrees, int stride,
+                                               const uint16_t* __restrict__ mp_mask, const DevMpLeaf* __restrict__ mp_leaf,
+                                               DevVote* __restrict__ votes, size_t vote_cap, int32_t* __restrict__ vote_counts /* [face][10] */) {
+  __shared__ int s_cnt[8][kParts];
+  __shared__ int s_run[kParts];
+  const int f = blockIdx.x;
+  const FaceDesc d = fd[f];
+  const int nt = face_ntrees[f];
+  const int nx = (d.W - kPatch + stride - 1) / stride, ny = (d.H - kPatch + stride - 1) / stride;
+  const int n = max(nx, 0) * max(ny, 0) * nt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t* __restrict__ ids = leaf_ids + f * leaf_face_stride;
+  DevVote* __restrict__ fv = votes + (size_t)f * kParts * vote_cap;
+  if (threadIdx.x < kParts) s_run[threadIdx.x] = 0;
+  __syncthreads();
+  for (int b = 0; b < n; b += 256) {
+    const int k = b + threadIdx.x;
+    int leaf = -1;
+    unsigned mask = 0;
+    if (k < n) { leaf = ids[k]; mask = __ldg(mp_mask + leaf); }
+    unsigned bal[kParts];
+#pragma unroll
+    for (int p = 0; p < kParts; p++) {
+      bal[p] = __ballot_sync(0xffffffffu, (mask >> p) & 1u);
+      if (lane == 0) s_cnt[warp][p] = __popc(bal[p]);
+    }
+    __syncthreads();
+    if (mask) {
+      const int patch = k / nt;
+      const int ix = patch / ny, iy = patch - ix * ny;
+      const int cx = ix * stride + kHalfPatch, cy = iy * stride + kHalfPatch;
+      const DevMpLeaf L = mp_leaf[leaf];
+#pragma unroll
+      for (int p = 0; p < kParts; p++) {
+        if ((mask >> p) & 1u) {
+          int pos = s_run[p] + __popc(bal[p] & ((1u << lane) - 1u));
+          for (int w = 0; w < warp; w++) pos += s_cnt[w][p];
+          DevVote v;
+          v.x = (short)(L.off[p][0] + cx);
+          v.y = (short)(L.off[p][1] + cy);
+          v.w = L.weight;
+          fv[(size_t)p * vote_cap + pos] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < kParts) {
+      int tot = 0;
+      for (int w = 0; w < 8; w++) tot += s_cnt[w][threadIdx.x];
+      s_run[threadIdx.x] += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < kParts) vote_counts[f * kParts + threadIdx.x] = s_run[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// a14: MeanShift::shift (include/MeanShift.hpp:52-135) + the final rescale of
+// FaceForest::analyzeFace (src/FaceForest.cpp:256-257).  The f32 sums are order-dependent, so one
+// thread owns one (face, part) chain and walks its votes in order.
+// ---------------------------------------------------------------------------------------------
+struct MeanShiftOpt { int kernel; int max_iterations; float stopping; };
+
+__device__ __forceinline__ void meanshift_chain(const DevVote* __restrict__ v, int n, MeanShiftOpt o, float* mean_xy, int* rounded, int* iters_out,
+                                                unsigned long long* passes) {
+  float mx = 0.f, my = 0.f;
+  {
+    float sum_w = 0;
+    for (int i = 0; i < n; i++) {
+      const DevVote q = v[i];
+      mx += q.x * q.w;
+      my += q.y * q.w;
+      sum_w += q.w;
+    }
+    if (sum_w > 0) { mx /= sum_w; my /= sum_w; }
+  }
+  const float lamda = (float)o.kernel;
+  bool conv = false;
+  int it = 0;
+  for (int i = 0; i < o.max_iterations && !conv; i++) {
+    float sx = 0.f, sy = 0.f, sum_w = 0;
+    for (int k = 0; k < n; k++) {
+      const DevVote q = v[k];
+      const float dx = mx - (float)q.x, dy = my - (float)q.y;
+      float dist = (float)sqrt((double)dx * dx + (double)dy * dy);  // cv::norm(Point2f) accumulates in double
+      dist = (float)exp((double)(-dist / lamda));                  // expf: double exp rounded once == correctly rounded f32
+      const float w = q.w * dist;
+      sx += q.x * w;
+      sy += q.y * w;
+      sum_w += w;
+    }
+    if (sum_w > 0) { sx /= sum_w; sy /= sum_w; }
+    const float ex = sx - mx, ey = sy - my;
+    if (sqrt((double)ex * ex + (double)ey * ey) < o.stopping) conv = true;
+    mx = sx; my = sy;
+    it++;
+  }
+  mean_xy[0] = mx; mean_xy[1] = my;
+  rounded[0] = __float2int_rn(mx);  // Point_<int> = Point_<float>: cvRound
+  rounded[1] = __float2int_rn(my);
+  *iters_out = it;
+  if (passes) *passes = (unsigned long long)n * (1 + it);
+}
+
+__global__ void __launch_bounds__(64) k_meanshift(const FaceDesc* __restrict__ fd, int nfaces, const DevVote* __restrict__ votes, size_t vote_cap,
+                                                  const int32_t* __restrict__ vote_counts, MeanShiftOpt o, crf_face_t* __restrict__ faces,
+                                                  unsigned long long* counters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nfaces * kParts) return;
+  const int f = i / kParts, p = i - f * kParts;
+  const int n = vote_counts[i];
+  float mean[2];
+  int rnd[2], it;
+  unsigned long long passes = 0;
+  meanshift_chain(votes + ((size_t)f * kParts + p) * vote_cap, n, o, mean, rnd, &it, counters ? &passes : nullptr);
+  crf_face_t* face = faces + f;
+  face->ffd_f[p][0] = mean[0]; face->ffd_f[p][1] = mean[1];
+  face->ffd_scaled[p][0] = rnd[0]; face->ffd_scaled[p][1] = rnd[1];
+  const float inv = 1.0f / fd[f].scale;  // Point_<int> *= float: saturate_cast<int>(x * b)
+  face->ffd[p][0] = __float2int_rn(rnd[0] * inv);
+  face->ffd[p][1] = __float2int_rn(rnd[1] * inv);
+  face->ms_iters[p] = it;
+  face->n_votes[p] = n;
+  if (counters) {
+    atomicAdd(&counters[CNT_VOTES], (unsigned long long)n);
+    atomicAdd(&counters[CNT_VOTE_PASSES], passes);
+  }
+}
+
+// MeanShift on a caller-supplied list (stage API).
+__global__ void k_meanshift_one(const DevVote* v, int n, MeanShiftOpt o, float* mean, int* rounded, int* iters) {
+  meanshift_chain(v, n, o, mean, rounded, iters, nullptr);
+}
+
+}  // namespace crf

@@ -1,0 +1,110 @@
+// Packs host-side FlatForests into the device image (device_forest.h).
+#include <deque>
+
+#include "../../include/crf_b200.h"
+#include "device_forest.h"
+
+namespace crf {
+
+int pack_forests(const std::vector<const FlatForest*>& forests, ForestKind kind, const PackOptions& opt, PackedForest& out, std::string& err) {
+  out = PackedForest();
+  for (const FlatForest* f : forests) {
+    out.forest_base.push_back((int32_t)out.roots.size());
+    out.forest_ntrees.push_back((int32_t)f->trees.size());
+    for (const FlatTree& t : f->trees) {
+      if (t.nodes.empty()) { err = "empty tree"; return CRF_ERR_FORMAT; }
+      const int32_t leaf_base = (int32_t)out.leaf_oid.size();
+      out.leaf_base.push_back(leaf_base);
+      out.max_depth = t.max_depth > out.max_depth ? t.max_depth : out.max_depth;
+      // leaves keep the tree's pre-order leaf numbering
+      const size_t nleaves = kind == KIND_HEADPOSE ? t.hp_leaves.size() : t.mp_leaves.size();
+      out.leaf_oid.resize(leaf_base + nleaves);
+      if (kind == KIND_HEADPOSE) {
+        out.hp_m.resize(leaf_base + nleaves);
+        for (size_t l = 0; l < nleaves; l++) {
+          const HpLeaf& L = t.hp_leaves[l];
+          out.leaf_oid[leaf_base + l] = L.object_id;
+          // src/face_utils.cpp:222-228, same float operation order
+          float m = -1.f;
+          if (L.foreground > opt.hp_min_foreground) {
+            m = 0;
+            for (int j = 0; j < 5; j++) m += L.labels[j] * j;
+            m /= (L.nsamples * L.foreground);
+            if (!(m >= 0.f)) m = __builtin_nanf("");  // cannot happen for finished trees; keeps the NaN path visible
+          }
+          out.hp_m[leaf_base + l] = m;
+        }
+      } else {
+        out.mp_leaf.resize(leaf_base + nleaves);
+        out.mp_mask.resize(leaf_base + nleaves);
+        for (size_t l = 0; l < nleaves; l++) {
+          const MpLeaf& L = t.mp_leaves[l];
+          out.leaf_oid[leaf_base + l] = L.object_id;
+          DevMpLeaf d{};
+          uint16_t mask = 0;
+          for (int i = 0; i < kParts; i++) {
+            if (L.offset[i][0] < -32768 || L.offset[i][0] > 32767 || L.offset[i][1] < -32768 || L.offset[i][1] > 32767) {
+              err = "leaf offset does not fit int16"; return CRF_ERR_UNSUPPORTED;
+            }
+            d.off[i][0] = (int16_t)L.offset[i][0];
+            d.off[i][1] = (int16_t)L.offset[i][1];
+            // src/face_utils.cpp:284-290
+            float min_pf = opt.ffd_min_pf;
+            if (i == 0 || i == 7) min_pf *= 1.5;
+            if (L.foreground > opt.ffd_min_foreground && L.prob_foreground[i] > min_pf && L.variance[i] < opt.ffd_max_variance &&
+                L.samples > opt.ffd_min_samples)
+              mask |= (uint16_t)(1u << i);
+          }
+          d.weight = L.foreground;
+          out.mp_leaf[leaf_base + l] = d;
+          out.mp_mask[leaf_base + l] = mask;
+        }
+      }
+      // breadth-first slot assignment
+      const int32_t base = (int32_t)out.slots.size();
+      out.roots.push_back(base);
+      std::vector<int32_t> slot_of(t.nodes.size(), -1);
+      std::deque<int32_t> q;
+      out.slots.emplace_back();
+      slot_of[0] = base;
+      q.push_back(0);
+      while (!q.empty()) {
+        const int32_t ni = q.front();
+        q.pop_front();
+        const FlatNode& n = t.nodes[ni];
+        DevSlot s{};
+        if (n.leaf >= 0) {
+          s.is_leaf = 1;
+          s.child = leaf_base + n.leaf;
+        } else {
+          if (n.left < 0 || n.right < 0 || n.left >= (int32_t)t.nodes.size() || n.right >= (int32_t)t.nodes.size()) { err = "dangling child"; return CRF_ERR_FORMAT; }
+          const int32_t pair = (int32_t)out.slots.size();
+          out.slots.emplace_back();
+          out.slots.emplace_back();
+          slot_of[n.left] = pair;
+          slot_of[n.right] = pair + 1;
+          q.push_back(n.left);
+          q.push_back(n.right);
+          const uint32_t area1 = (uint32_t)n.r1[2] * n.r1[3], area2 = (uint32_t)n.r2[2] * n.r2[3];
+          if (area1 == 0 || area2 == 0) { err = "empty rectangle"; return CRF_ERR_UNSUPPORTED; }
+          if (n.r1[0] + n.r1[2] > kPatch || n.r1[1] + n.r1[3] > kPatch || n.r2[0] + n.r2[2] > kPatch || n.r2[1] + n.r2[3] > kPatch) { err = "rectangle leaves the patch"; return CRF_ERR_UNSUPPORTED; }
+          s.a1 = (uint16_t)(n.r1[1] * kRowStride + n.r1[0]);
+          s.c1 = (uint16_t)(n.r1[3] * kRowStride);
+          s.w1 = n.r1[2];
+          s.a2 = (uint16_t)(n.r2[1] * kRowStride + n.r2[0]);
+          s.c2 = (uint16_t)(n.r2[3] * kRowStride);
+          s.w2 = n.r2[2];
+          s.ch = n.channel;
+          s.thr = n.threshold;
+          s.m1 = magic_for_area(area1);
+          s.m2 = magic_for_area(area2);
+          s.child = pair;
+        }
+        out.slots[slot_of[ni]] = s;
+      }
+    }
+  }
+  return CRF_OK;
+}
+
+}  // namespace crf

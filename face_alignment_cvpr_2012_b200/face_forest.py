@@ -1,0 +1,358 @@
+"""Host-side mirror of the reference's C++ interface for the inference path, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the reference (citations: /root/reference):
+FaceForest / FaceForestOptions / Face (include/FaceForest.hpp:21-159), Forest<S>::load / evaluateMT
+(include/Forest.hpp:81-129), ImageSample (include/ImageSample.hpp:146-199), MeanShift::shift
+(include/MeanShift.hpp:41-50).  cv::Mat becomes a numpy uint8 array, cv::Rect a 4-tuple (x, y, w, h),
+cv::Point a length-2 int array.  Everything computes on the GPU through libcrf_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+from . import capi
+from .capi import FACE_DTYPE, CrfError, Options, Rect
+
+
+@dataclass
+class ForestParam:
+    """include/Constants.hpp:24-60 — the fields the inference path reads."""
+    tree_path: str = ""
+    ntrees: int = 0
+    max_depth: int = 0
+    face_size: int = 125
+    patch_size_ratio: float = 0.25
+    features: list = field(default_factory=lambda: [0, 1, 2])
+
+    def getPatchSize(self) -> int:
+        return int(round(self.face_size * self.patch_size_ratio))
+
+
+def loadConfigFile(path: str) -> ForestParam:
+    """src/face_utils.cpp:50-140: label line then value line, 11 entries."""
+    p = ForestParam()
+    try:
+        lines = Path(path).read_text().split("\n")
+    except OSError:
+        raise FileNotFoundError(f"file not found {path}")
+    vals = [lines[i].strip() for i in range(1, len(lines), 2)]
+    p.max_depth = int(vals[0]); p.ntrees = int(vals[3]); p.tree_path = vals[4]
+    p.face_size = int(vals[8]); p.patch_size_ratio = float(vals[9]); p.features = [int(v) for v in vals[10].split()]
+    return p
+
+
+@dataclass
+class HeadPoseEstimatorOption:  # include/FaceForest.hpp:33-43
+    num_head_pose_labels: int = 5
+    step_size: int = 4
+    min_foreground_probability: float = 0.5
+
+
+@dataclass
+class MultiPartEstimatorOption:  # include/FaceForest.hpp:45-58
+    num_parts: int = 10
+    step_size: int = 3
+    min_samples: int = 2
+    min_forground: float = 0.5
+    min_pf: float = 0.25
+    max_variance: float = 25.0
+
+
+@dataclass
+class MeanShiftOption:  # include/MeanShift.hpp:16-25
+    kernel_size: int = 10
+    max_iterations: int = 7
+    stopping_criteria: float = 0.05
+
+
+@dataclass
+class FaceForestOptions:  # include/FaceForest.hpp:60-68 (face-detector fields omitted: boxes are given)
+    head_pose_forest_param: ForestParam = field(default_factory=ForestParam)
+    mp_forest_param: ForestParam = field(default_factory=ForestParam)
+    pose_option: HeadPoseEstimatorOption = field(default_factory=HeadPoseEstimatorOption)
+    multi_part_option: MultiPartEstimatorOption = field(default_factory=MultiPartEstimatorOption)
+    mean_shift_option: MeanShiftOption = field(default_factory=MeanShiftOption)
+    packed_model: str = ""   # "next" row f1: pre-packed binary image instead of the two tree directories
+    device: int = 0
+    max_chunk: int = 0
+
+
+@dataclass
+class Face:  # include/FaceForest.hpp:70-75
+    headpose: float = 0.0
+    bbox: tuple = (0, 0, 0, 0)
+    ffd_cordinates: np.ndarray = field(default_factory=lambda: np.zeros((10, 2), np.int32))
+    record: np.void | None = None  # the full crf_face_t (pre-rounding means, composition, vote counts)
+
+
+class Model:
+    """What FaceForest's constructor loads (src/FaceForest.cpp:15-58): the head-pose forest + the jungle."""
+
+    def __init__(self, hp_dir: str | None = None, ffd_dir: str | None = None, hp_ntrees: int = 15, ffd_ntrees: int = 20, packed: str | None = None):
+        L = capi.lib()
+        h = C.c_void_p()
+        if packed:
+            capi.check(L.crf_model_load_packed(str(packed).encode(), C.byref(h)))
+        else:
+            capi.check(L.crf_model_load(str(hp_dir).encode(), hp_ntrees, str(ffd_dir).encode(), ffd_ntrees, C.byref(h)))
+        self.h = h
+        info = capi.ModelInfo()
+        capi.check(L.crf_model_info(self.h, C.byref(info)))
+        self.info = {n: getattr(info, n) for n, _ in info._fields_}
+
+    def save_packed(self, path: str) -> None:
+        capi.check(capi.lib().crf_model_save_packed(self.h, str(path).encode()))
+
+    def tree_dump(self, which: int, tree: int) -> np.ndarray:
+        L = capi.lib()
+        n = L.crf_model_tree_dump(self.h, which, tree, None, 0)
+        if n < 0:
+            capi.check(n)
+        out = np.zeros((n, 16), np.int32)
+        L.crf_model_tree_dump(self.h, which, tree, capi.ptr(out, C.c_int32), n)
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            capi.lib().crf_model_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _options(o: FaceForestOptions | None, hp_stride=None, ffd_stride=None, max_chunk=None) -> Options:
+    opt = Options()
+    capi.lib().crf_options_default(C.byref(opt))
+    if o is not None:
+        opt.hp_stride = o.pose_option.step_size
+        opt.hp_min_foreground = o.pose_option.min_foreground_probability
+        opt.ffd_stride = o.multi_part_option.step_size
+        opt.ffd_min_samples = o.multi_part_option.min_samples
+        opt.ffd_min_foreground = o.multi_part_option.min_forground
+        opt.ffd_min_pf = o.multi_part_option.min_pf
+        opt.ffd_max_variance = o.multi_part_option.max_variance
+        opt.ms_kernel_size = o.mean_shift_option.kernel_size
+        opt.ms_max_iterations = o.mean_shift_option.max_iterations
+        opt.ms_stopping_criteria = o.mean_shift_option.stopping_criteria
+        opt.max_chunk = o.max_chunk
+    if hp_stride is not None:
+        opt.hp_stride = hp_stride
+    if ffd_stride is not None:
+        opt.ffd_stride = ffd_stride
+    if max_chunk is not None:
+        opt.max_chunk = max_chunk
+    return opt
+
+
+class Context:
+    """One GPU's packed forests + work buffers (crf_ctx)."""
+
+    def __init__(self, model: Model, device: int = 0, options: Options | None = None):
+        self.model = model
+        h = C.c_void_p()
+        capi.check(capi.lib().crf_ctx_create(model.h, device, C.byref(options) if options is not None else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            capi.lib().crf_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- profiling / counters
+    def set_profiling(self, stage_events: bool = False, count_work: bool = False) -> None:
+        capi.check(capi.lib().crf_ctx_set_profiling(self.h, (1 if stage_events else 0) | (2 if count_work else 0)))
+
+    def stage_ms(self):
+        ms = np.zeros(capi.NUM_STAGES, np.float32); ln = np.zeros(capi.NUM_STAGES, np.int32)
+        capi.check(capi.lib().crf_ctx_stage_ms(self.h, capi.ptr(ms, C.c_float), capi.ptr(ln, C.c_int32)))
+        return dict(zip(capi.STAGE_NAMES, ms.tolist())), dict(zip(capi.STAGE_NAMES, ln.tolist()))
+
+    def counters(self) -> dict:
+        c = capi.Counters()
+        capi.check(capi.lib().crf_ctx_counters(self.h, C.byref(c)))
+        return {n: int(getattr(c, n)) for n, _ in c._fields_}
+
+    def reset_counters(self) -> None:
+        capi.check(capi.lib().crf_ctx_reset_counters(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(capi.lib().crf_ctx_stream(self.h) or 0)
+
+    # ---- whole path
+    def analyze_crops(self, crops: np.ndarray, headpose_only: bool = False) -> np.ndarray:
+        crops = np.ascontiguousarray(crops, np.uint8)
+        n, rows, cols = crops.shape[:3]
+        out = np.zeros(n, FACE_DTYPE)
+        fn = capi.lib().crf_headpose_crops if headpose_only else capi.lib().crf_analyze_crops
+        capi.check(fn(self.h, crops.ctypes.data, n, rows, cols, out.ctypes.data))
+        return out
+
+    def analyze_crops_ptr(self, host_ptr: int, n: int, rows: int, cols: int, out: np.ndarray, headpose_only: bool = False) -> None:
+        fn = capi.lib().crf_headpose_crops if headpose_only else capi.lib().crf_analyze_crops
+        capi.check(fn(self.h, host_ptr, n, rows, cols, out.ctypes.data))
+
+    def analyze_crops_device(self, d_bgr: int, n: int, rows: int, cols: int, d_out: int, headpose_only: bool = False) -> None:
+        capi.check(capi.lib().crf_analyze_crops_device(self.h, d_bgr, n, rows, cols, d_out, int(headpose_only)))
+
+    def analyze_faces(self, bgr: np.ndarray, boxes) -> np.ndarray:
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        rows, cols = bgr.shape[:2]
+        n = len(boxes)
+        rects = (Rect * max(n, 1))(*[Rect(int(b[0]), int(b[1]), int(b[2]), int(b[3])) for b in boxes])
+        out = np.zeros(n, FACE_DTYPE)
+        capi.check(capi.lib().crf_analyze_faces(self.h, bgr.ctypes.data, rows, cols, cols * 3, rects, n, out.ctypes.data))
+        return out
+
+    def analyze_batch(self, frames: np.ndarray, boxes, image_of_box) -> np.ndarray:
+        """frames: [n_images, rows, cols, 3] u8 (or a list of equal-size frames)."""
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames] if not isinstance(frames, np.ndarray) else np.ascontiguousarray(frames, np.uint8)
+        n_images = len(frames)
+        rows, cols = frames[0].shape[:2]
+        ptrs = (C.c_void_p * n_images)(*[f.ctypes.data for f in frames])
+        n = len(boxes)
+        rects = (Rect * max(n, 1))(*[Rect(int(b[0]), int(b[1]), int(b[2]), int(b[3])) for b in boxes])
+        iob = np.ascontiguousarray(image_of_box, np.int32)
+        out = np.zeros(n, FACE_DTYPE)
+        capi.check(capi.lib().crf_analyze_batch(self.h, ptrs, n_images, rows, cols, cols * 3, rects, capi.ptr(iob, C.c_int32), n, out.ctypes.data))
+        return out
+
+    # ---- stages (parity tests)
+    def stage_gray_resize(self, bgr: np.ndarray, box) -> np.ndarray:
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        rows, cols = bgr.shape[:2]
+        buf = np.zeros(capi.MAX_SCALED_H * 125, np.uint8)
+        W = C.c_int(); H = C.c_int()
+        capi.check(capi.lib().crf_stage_gray_resize(self.h, capi.ptr(bgr, C.c_uint8), rows, cols, cols * 3, Rect(*[int(v) for v in box]),
+                                                    capi.ptr(buf, C.c_uint8), C.byref(W), C.byref(H)))
+        return buf[: W.value * H.value].reshape(H.value, W.value).copy()
+
+    def stage_channels(self, scaled: np.ndarray, minmax: bool = False):
+        scaled = np.ascontiguousarray(scaled, np.uint8)
+        H, W = scaled.shape
+        n = 2 if minmax else 38
+        planes = np.zeros((n, H, W), np.uint8); integ = np.zeros((n, H + 1, W + 1), np.uint32)
+        fn = capi.lib().crf_stage_minmax if minmax else capi.lib().crf_stage_channels
+        capi.check(fn(self.h, capi.ptr(scaled, C.c_uint8), W, H, capi.ptr(planes, C.c_uint8), capi.ptr(integ, C.c_uint32)))
+        return planes, integ
+
+    def stage_eval_forest(self, planes: np.ndarray, stride: int, forest_idx=None, tree_idx=None) -> np.ndarray:
+        planes = np.ascontiguousarray(planes, np.uint8)
+        Cn, H, W = planes.shape
+        ps = self.model.info["patch_size"]
+        npatch = max(0, -(-(W - ps) // stride)) * max(0, -(-(H - ps) // stride))
+        if forest_idx is None:
+            nt = self.model.info["hp_trees"]
+            ids = np.zeros((npatch, nt), np.int32)
+            capi.check(capi.lib().crf_stage_eval_forest(self.h, -1, None, None, 0, capi.ptr(planes, C.c_uint8), Cn, W, H, stride, capi.ptr(ids, C.c_int32)))
+            return ids
+        fi = np.ascontiguousarray(forest_idx, np.int32); ti = np.ascontiguousarray(tree_idx, np.int32)
+        ids = np.zeros((npatch, len(fi)), np.int32)
+        capi.check(capi.lib().crf_stage_eval_forest(self.h, 0, capi.ptr(fi, C.c_int32), capi.ptr(ti, C.c_int32), len(fi), capi.ptr(planes, C.c_uint8),
+                                                    Cn, W, H, stride, capi.ptr(ids, C.c_int32)))
+        return ids
+
+    def _compose_out(self):
+        return (np.zeros(5, np.int32), C.c_int(), np.zeros(128, np.int32), np.zeros(128, np.int32), C.c_int(), C.c_int())
+
+    def stage_headpose(self, planes: np.ndarray, stride: int) -> dict:
+        planes = np.ascontiguousarray(planes, np.uint8)
+        Cn, H, W = planes.shape
+        hp = C.c_float(); var = C.c_float()
+        counts, dom, fi, ti, nt, flags = self._compose_out()
+        capi.check(capi.lib().crf_stage_headpose(self.h, capi.ptr(planes, C.c_uint8), Cn, W, H, stride, C.byref(hp), C.byref(var), capi.ptr(counts, C.c_int32),
+                                                 C.byref(dom), capi.ptr(fi, C.c_int32), capi.ptr(ti, C.c_int32), C.byref(nt), C.byref(flags)))
+        return dict(headpose=np.float32(hp.value), variance=np.float32(var.value), tree_counts=counts, dominant=dom.value,
+                    forest_idx=fi[: nt.value].copy(), tree_idx=ti[: nt.value].copy(), flags=flags.value)
+
+    def stage_compose(self, headpose: float, variance: float) -> dict:
+        counts, dom, fi, ti, nt, flags = self._compose_out()
+        capi.check(capi.lib().crf_stage_compose(self.h, headpose, variance, capi.ptr(counts, C.c_int32), C.byref(dom), capi.ptr(fi, C.c_int32),
+                                                capi.ptr(ti, C.c_int32), C.byref(nt), C.byref(flags)))
+        return dict(tree_counts=counts, dominant=dom.value, forest_idx=fi[: nt.value].copy(), tree_idx=ti[: nt.value].copy(), flags=flags.value)
+
+    def stage_votes_meanshift(self, planes: np.ndarray, stride: int, forest_idx, tree_idx, vote_cap: int = 0) -> dict:
+        planes = np.ascontiguousarray(planes, np.uint8)
+        Cn, H, W = planes.shape
+        fi = np.ascontiguousarray(forest_idx, np.int32); ti = np.ascontiguousarray(tree_idx, np.int32)
+        nv = np.zeros(10, np.int32); votes = np.zeros((10, max(vote_cap, 1), 3), np.float32)
+        mean = np.zeros((10, 2), np.float32); rnd = np.zeros((10, 2), np.int32); it = np.zeros(10, np.int32)
+        capi.check(capi.lib().crf_stage_votes_meanshift(self.h, capi.ptr(fi, C.c_int32), capi.ptr(ti, C.c_int32), len(fi), capi.ptr(planes, C.c_uint8),
+                                                        Cn, W, H, stride, capi.ptr(nv, C.c_int32), capi.ptr(votes, C.c_float) if vote_cap else None, vote_cap,
+                                                        capi.ptr(mean, C.c_float), capi.ptr(rnd, C.c_int32), capi.ptr(it, C.c_int32)))
+        return dict(n_votes=nv, votes=votes if vote_cap else None, mean=mean, rounded=rnd, iters=it)
+
+    def stage_meanshift(self, votes_xyw: np.ndarray):
+        v = np.ascontiguousarray(votes_xyw, np.float32).reshape(-1, 3)
+        mean = np.zeros(2, np.float32); rnd = np.zeros(2, np.int32); it = C.c_int()
+        capi.check(capi.lib().crf_stage_meanshift(self.h, capi.ptr(v, C.c_float), len(v), capi.ptr(mean, C.c_float), capi.ptr(rnd, C.c_int32), C.byref(it)))
+        return mean, rnd, it.value
+
+
+class FaceForest:
+    """FaceForest (include/FaceForest.hpp:77-159, src/FaceForest.cpp).  Face boxes are supplied by the caller."""
+
+    def __init__(self, option: FaceForestOptions | None = None, model: Model | None = None):
+        self.is_inizialized = False
+        self.option = option or FaceForestOptions()
+        try:
+            if model is None:
+                o = self.option
+                if o.packed_model:
+                    model = Model(packed=o.packed_model)
+                else:
+                    model = Model(o.head_pose_forest_param.tree_path, o.mp_forest_param.tree_path, o.head_pose_forest_param.ntrees or 15,
+                                  o.mp_forest_param.ntrees or 20)
+            self.model = model
+            self.ctx = Context(model, self.option.device, _options(self.option))
+        except CrfError as e:  # src/FaceForest.cpp:31-36: ERROR(...) and leave is_inizialized false
+            import sys
+            print(f"(!) Error loading forest: {e}", file=sys.stderr)
+            self.model = None; self.ctx = None
+            return
+        self.is_inizialized = True
+
+    def _to_faces(self, recs: np.ndarray, boxes) -> list:
+        return [Face(float(r["headpose"]), tuple(int(v) for v in b), r["ffd"].copy(), r) for r, b in zip(recs, boxes)]
+
+    def analyzeFace(self, img: np.ndarray, face_bbox, face: Face | None = None, normalize: bool = True) -> Face:
+        """src/FaceForest.cpp:183-258."""
+        if not self.is_inizialized:
+            raise AssertionError("CV_Assert(is_inizialized)")  # src/FaceForest.cpp:191
+        f = self._to_faces(self.ctx.analyze_faces(img, [face_bbox]), [face_bbox])[0]
+        if face is not None:
+            face.headpose, face.bbox, face.ffd_cordinates, face.record = f.headpose, f.bbox, f.ffd_cordinates, f.record
+            return face
+        return f
+
+    def analyzeImage(self, img: np.ndarray, faces_bboxes, faces: list | None = None) -> list:
+        """src/FaceForest.cpp:161-181 with the detectFace() boxes given by the caller."""
+        if not self.is_inizialized:
+            raise AssertionError("CV_Assert(is_inizialized)")  # src/FaceForest.cpp:167
+        out = self._to_faces(self.ctx.analyze_faces(img, list(faces_bboxes)), faces_bboxes)
+        if faces is not None:
+            faces.clear(); faces.extend(out)
+        return out
+
+
+class MeanShift:
+    """include/MeanShift.hpp:27-50."""
+
+    @staticmethod
+    def shift(ctx: Context, votes_xyw: np.ndarray):
+        return ctx.stage_meanshift(votes_xyw)

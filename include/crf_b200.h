@@ -1,0 +1,183 @@
+/* =============================================================================
+ * crf_b200.h — C ABI of the B200-native Conditional Regression Forest inference path.
+ *
+ * Drop-in boundary for the hot path of MatrixPlayer/face_alignment_cvpr_2012
+ * (citations are file:line under the reference tree).  The reference has no FFI layer; its
+ * boundary is the C++ class API called by its mains (src/eval_ffd.cpp:89,
+ * src/eval_headpose.cpp:66, src/demo.cpp:154, src/test_cvpr_2012.cpp:44).  The entry points
+ * below are what a binding of that API needs; include/crf_b200_compat.hpp re-exposes the
+ * reference's class names/signatures on top of them.
+ *
+ * Conventions: plain pointers and sizes; opaque handles; every function returns 0 on success and
+ * a negative crf_status on error (crf_last_error() gives the message, mirroring the reference's
+ * bool + ERROR(...) print); the caller owns all in/out buffers; the library owns device memory
+ * behind a crf_ctx; one crf_ctx belongs to one GPU and is used by one host thread at a time (the
+ * reference's FaceForest is not re-entrant either: src/FaceForest.cpp:239-250).
+ * There is NO CPU fallback: without a CUDA device crf_ctx_create fails.
+ * ============================================================================= */
+#ifndef CRF_B200_H
+#define CRF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRF_NUM_PARTS 10          /* MultiPartEstimatorOption::num_parts   include/FaceForest.hpp:49 */
+#define CRF_NUM_POSE_FORESTS 5    /* poseT hard-codes 5 bins               src/FaceForest.cpp:216-222 */
+#define CRF_NUM_HEADPOSE_CLASSES 5/* NUM_HEADPOSE_CLASSES                  include/Constants.hpp:66   */
+#define CRF_MAX_SCALED_H 521      /* f32 integral exactness limit (sums < 2^24), SURVEY H7           */
+#define CRF_ROW_STRIDE 128        /* u32 words per integral row on the device                         */
+
+typedef enum {
+  CRF_OK = 0,
+  CRF_ERR_ARG = -1,        /* bad argument / box outside image / face too small or too tall        */
+  CRF_ERR_IO = -2,         /* file not found / unreadable          (Tree::load, include/Tree.hpp:202) */
+  CRF_ERR_FORMAT = -3,     /* archive does not parse / unfinished tree (Forest::load_tree :142-152)  */
+  CRF_ERR_CUDA = -4,       /* CUDA runtime error or no device                                        */
+  CRF_ERR_STATE = -5,      /* use before init                       (CV_Assert, src/FaceForest.cpp:167) */
+  CRF_ERR_UNSUPPORTED = -6 /* model outside the packed-format limits (channel > 63, rect > 31, ...)  */
+} crf_status;
+
+typedef struct crf_model crf_model; /* host-side forests: what FaceForest's ctor loads (src/FaceForest.cpp:15-58) */
+typedef struct crf_ctx crf_ctx;     /* per-GPU context: packed forests + work buffers                */
+
+typedef struct { int x, y, width, height; } crf_rect_t; /* cv::Rect  include/opencv_serialization.hpp:65-72 */
+
+/* HeadPoseEstimatorOption + MultiPartEstimatorOption (include/FaceForest.hpp:33-58) and
+ * MeanShiftOption (include/MeanShift.hpp:16-25); crf_options_default() fills the reference defaults. */
+typedef struct {
+  int   hp_stride;             /* step_size = 4 */
+  float hp_min_foreground;     /* min_foreground_probability = 0.5 */
+  int   ffd_stride;            /* step_size = 3 */
+  int   ffd_min_samples;       /* 2 */
+  float ffd_min_foreground;    /* min_forground = 0.5 */
+  float ffd_min_pf;            /* 0.25 (x1.5 for parts 0 and 7, src/face_utils.cpp:286-287) */
+  float ffd_max_variance;      /* 25 */
+  int   ms_kernel_size;        /* 10 */
+  int   ms_max_iterations;     /* 7 */
+  float ms_stopping_criteria;  /* 0.05 */
+  int   max_chunk;             /* faces resident per device chunk; 0 = library default */
+  int   max_scaled_h;          /* tallest scaled face the context is sized for; 0 = 192 */
+} crf_options_t;
+
+/* Face (include/FaceForest.hpp:70-75) plus the intermediate results the parity tests need. */
+typedef struct {
+  float headpose, variance;          /* src/face_utils.cpp:236-241 */
+  int   tree_counts[CRF_NUM_POSE_FORESTS]; /* trees taken from each pose forest (src/FaceForest.cpp:241-246) */
+  int   dominant;                    /* dominant_headpose (:231-235) */
+  int   scaled_w, scaled_h;          /* size after cv::resize (:204) */
+  float scale;                       /* face_size / bbox.width (:202) */
+  float ffd_f[CRF_NUM_PARTS][2];     /* MeanShift mean before rounding, scaled-face pixels */
+  int   ffd_scaled[CRF_NUM_PARTS][2];/* Point_<int> = Point_<float> (include/MeanShift.hpp:75) */
+  int   ffd[CRF_NUM_PARTS][2];       /* ffd_cordinates after *= 1/scale (src/FaceForest.cpp:256-257): bbox-relative original pixels */
+  int   ms_iters[CRF_NUM_PARTS];     /* MeanShift iterations executed */
+  int   n_votes[CRF_NUM_PARTS];      /* votes per part (src/face_utils.cpp:289-298) */
+  int   flags;                       /* bit0: composition clamped (reference would index out of bounds) */
+} crf_face_t;
+
+typedef struct {
+  int hp_trees, hp_nodes, hp_leaves, hp_max_depth;
+  int mp_forests, mp_trees, mp_nodes, mp_leaves, mp_max_depth;
+  int patch_size, face_size, num_channels;
+  int hp_ntrees_cfg, mp_ntrees_cfg;
+} crf_model_info_t;
+
+/* Work counters of the calls since the last reset (exact, counted on the device). */
+typedef struct {
+  unsigned long long faces;
+  unsigned long long hp_node_tests, ffd_node_tests; /* internal-node tests (one 16-B record + 8 integral samples each) */
+  unsigned long long hp_traversals, ffd_traversals; /* (patch, tree) pairs */
+  unsigned long long votes;                         /* votes emitted */
+  unsigned long long vote_passes;                   /* sum over (face, part) of votes x (1 + MeanShift iterations) */
+  unsigned long long kernel_launches;               /* CUDA kernels launched by this library */
+  unsigned long long h2d_bytes, d2h_bytes;
+} crf_counters_t;
+
+enum { CRF_STAGE_RESIZE = 0, CRF_STAGE_PLAIN, CRF_STAGE_GABOR, CRF_STAGE_HP_TRAVERSE, CRF_STAGE_HP_REDUCE,
+       CRF_STAGE_FFD_TRAVERSE, CRF_STAGE_VOTES, CRF_STAGE_MEANSHIFT, CRF_NUM_STAGES };
+
+const char* crf_last_error(void);
+const char* crf_version(void);
+void crf_options_default(crf_options_t* opt);
+
+/* ---- model: Forest<S>::load / Tree<S>::load (include/Forest.hpp:103-153, include/Tree.hpp:193-237) and the
+ * jungle enumeration of FaceForest::FaceForest (src/FaceForest.cpp:39-55: sub-directories of ffd_dir, sorted). */
+int crf_model_load(const char* hp_dir, int hp_ntrees, const char* ffd_dir, int ffd_ntrees, crf_model** out);
+/* "next" row f1: pre-packed binary image of the same forests (versioned, checksummed). */
+int crf_model_save_packed(const crf_model* m, const char* path);
+int crf_model_load_packed(const char* path, crf_model** out);
+int crf_model_info(const crf_model* m, crf_model_info_t* info);
+/* Pre-order dump of one tree (which = -1 head pose, 0..4 pose forest), 16 ints per node:
+ * [is_leaf, depth, ch, r1x,r1y,r1w,r1h, r2x,r2y,r2w,r2h, thr, left_oid, right_oid, nsamples, object_id] */
+int crf_model_tree_dump(const crf_model* m, int which, int tree, int32_t* out, int cap_nodes);
+void crf_model_free(crf_model* m);
+
+/* ---- context */
+int crf_device_count(void);
+int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf_ctx** out);
+void crf_ctx_destroy(crf_ctx* ctx);
+int crf_ctx_set_profiling(crf_ctx* ctx, int on);                  /* CUDA events around every stage */
+int crf_ctx_stage_ms(crf_ctx* ctx, float ms[CRF_NUM_STAGES], int launches[CRF_NUM_STAGES]); /* accumulated since reset */
+int crf_ctx_counters(crf_ctx* ctx, crf_counters_t* c);
+int crf_ctx_reset_counters(crf_ctx* ctx);
+void* crf_ctx_stream(crf_ctx* ctx);                               /* cudaStream_t the kernels run on */
+/* pinned host memory for callers that want the fast H2D path */
+int crf_host_alloc(void** p, size_t bytes);
+void crf_host_free(void* p);
+
+/* ---- FaceForest::analyzeFace (src/FaceForest.cpp:183-258) for n boxes of one BGR frame
+ * (analyzeImage with the Haar boxes given, :161-181). */
+int crf_analyze_faces(crf_ctx* ctx, const uint8_t* bgr, int rows, int cols, size_t step,
+                      const crf_rect_t* boxes, int n, crf_face_t* out);
+/* n boxes spread over n_images equal-size frames; image_of_box[i] selects the frame of box i. */
+int crf_analyze_batch(crf_ctx* ctx, const uint8_t* const* images, int n_images, int rows, int cols, size_t step,
+                      const crf_rect_t* boxes, const int* image_of_box, int n, crf_face_t* out);
+/* n equal-size crops stored back to back (n x rows x cols x 3), box = whole crop. */
+int crf_analyze_crops(crf_ctx* ctx, const uint8_t* bgr_batch, int n, int rows, int cols, crf_face_t* out);
+/* stop after getHeadPoseVotesMT (src/face_utils.cpp:183-242): fills headpose, variance, scaled_*, scale. */
+int crf_headpose_crops(crf_ctx* ctx, const uint8_t* bgr_batch, int n, int rows, int cols, crf_face_t* out);
+/* same two, inputs and outputs already resident in device memory (d_out: n x crf_face_t); asynchronous
+ * on crf_ctx_stream(); used to measure the kernel path without PCIe. */
+int crf_analyze_crops_device(crf_ctx* ctx, const uint8_t* d_bgr_batch, int n, int rows, int cols, crf_face_t* d_out, int headpose_only);
+
+/* ---- stage-level entry points (device results copied back) used by the parity tests and by the
+ * reference-shaped classes in crf_b200_compat.hpp. */
+/* src/FaceForest.cpp:196-204: cvtColor + ROI + resize.  scaled: caller buffer of at least max_h x 125 bytes, dense rows of *W. */
+int crf_stage_gray_resize(crf_ctx* ctx, const uint8_t* bgr, int rows, int cols, size_t step, crf_rect_t box,
+                          uint8_t* scaled, int* W, int* H);
+/* ImageSample::extractFeatureChannels (src/ImageSample.cpp:77-90) with features {0,1,2}:
+ * planes_u8 [38][H][W] (may be NULL), integrals [38][H+1][W+1] u32 (may be NULL). */
+int crf_stage_channels(crf_ctx* ctx, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals);
+/* FC_MIN_MAX (include/FeatureChannelFactory.hpp:142-165): planes [2][H][W], integrals [2][H+1][W+1]. */
+int crf_stage_minmax(crf_ctx* ctx, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals);
+/* Forest<S>::evaluateMT over the dense grid of getHeadPoseVotesMT / getFacialFeaturesVotesMT.
+ * Channel data comes from caller-supplied u8 planes [C][H][W] (C <= 64) so that synthetic
+ * channels can be used.  which = -1: head-pose forest (tree_forest/tree_index ignored);
+ * which = 0: explicit list of ntrees (forest, tree) pairs of the FFD jungle.
+ * leaf_ids: [patch][tree] in the reference's order (x outer, y inner), value = Boost object id. */
+int crf_stage_eval_forest(crf_ctx* ctx, int which, const int* tree_forest, const int* tree_index, int ntrees,
+                          const uint8_t* planes_u8, int C, int W, int H, int stride, int32_t* leaf_ids);
+/* getHeadPoseVotesMT reduce + areaUnderCurve + composition (src/face_utils.cpp:219-241, :304-323;
+ * src/FaceForest.cpp:215-250) from planes: returns headpose, variance, counts, dominant and the composed list. */
+int crf_stage_headpose(crf_ctx* ctx, const uint8_t* planes_u8, int C, int W, int H, int stride,
+                       float* headpose, float* variance, int tree_counts[CRF_NUM_POSE_FORESTS], int* dominant,
+                       int* tree_forest, int* tree_index, int* ntrees, int* flags);
+/* composition alone from (headpose, variance) */
+int crf_stage_compose(crf_ctx* ctx, float headpose, float variance, int tree_counts[CRF_NUM_POSE_FORESTS], int* dominant,
+                      int* tree_forest, int* tree_index, int* ntrees, int* flags);
+/* getFacialFeaturesVotesMT vote emission + MeanShift::shift x10 (src/face_utils.cpp:277-301,
+ * include/MeanShift.hpp:52-135) for an explicit composed forest.  votes_xyw (optional): [10][vote_cap][3]. */
+int crf_stage_votes_meanshift(crf_ctx* ctx, const int* tree_forest, const int* tree_index, int ntrees,
+                              const uint8_t* planes_u8, int C, int W, int H, int stride,
+                              int n_votes[CRF_NUM_PARTS], float* votes_xyw, int vote_cap,
+                              float mean_xy[CRF_NUM_PARTS][2], int rounded_xy[CRF_NUM_PARTS][2], int iters[CRF_NUM_PARTS]);
+/* MeanShift::shift on a caller-supplied vote list (x, y, weight triples). */
+int crf_stage_meanshift(crf_ctx* ctx, const float* votes_xyw, int n, float mean_xy[2], int rounded_xy[2], int* iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRF_B200_H */

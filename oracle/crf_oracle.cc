@@ -894,6 +894,147 @@ void orc_model_free(void* h) {
   delete m;
 }
 
+// Reads the packed binary forest image written by the product's crf_model_save_packed
+// (face_alignment_cvpr_2012_b200/csrc/model.cc: magic "CRFB200M", version 2, FNV-1a 64 trailer) into
+// the oracle's own pointer-linked trees.  The text archives (282 MB) cannot travel to the GPU box;
+// tests/test_model_loader.py proves here, where /root/reference exists, that this image holds exactly
+// what the oracle's own Boost-archive parser reads from the shipped files.
+}  // extern "C"
+namespace {
+#pragma pack(push, 1)
+struct PkNode { int32_t right; int32_t thr_raw; uint8_t ch, depth; uint8_t r1[4], r2[4]; uint8_t is_leaf; uint8_t pad; };
+struct PkParam { int32_t max_depth, min_patches, ntests, ntrees, nimages, npatches, face_size; float patch_size_ratio; int32_t n_features; int32_t features[8]; };
+struct PkHpLeaf { int32_t nsamples; float foreground; int32_t labels[5]; int32_t object_id; };
+struct PkMpLeaf { int32_t samples; int16_t off[10][2]; float var[10]; float pf[10]; float fg; int32_t oid; };
+#pragma pack(pop)
+struct PkReader {
+  const uint8_t* p; const uint8_t* e; bool ok = true;
+  template <class T> T pod() { T v{}; if (p + sizeof(T) > e) { ok = false; return v; } std::memcpy(&v, p, sizeof(T)); p += sizeof(T); return v; }
+};
+static bool read_packed_forest(PkReader& r, Forest& f, Kind kind) {
+  r.pod<int32_t>();  // kind
+  int32_t nt = r.pod<int32_t>();
+  if (!r.ok || nt < 0 || nt > 4096) return false;
+  for (int t = 0; t < nt; t++) {
+    Tree* tree = new Tree();
+    f.m_trees.push_back(tree);
+    tree->m_num_nodes = r.pod<int32_t>(); tree->i_node = r.pod<int32_t>(); tree->max_depth_seen = r.pod<int32_t>();
+    PkParam pp = r.pod<PkParam>();
+    tree->m_param.max_depth = pp.max_depth; tree->m_param.ntrees = pp.ntrees; tree->m_param.face_size = pp.face_size;
+    tree->m_param.patch_size_ratio = pp.patch_size_ratio;
+    for (int i = 0; i < pp.n_features && i < 8; i++) tree->m_param.features.push_back(pp.features[i]);
+    int32_t nn = r.pod<int32_t>();
+    if (!r.ok || nn < 1) return false;
+    std::vector<PkNode> recs((size_t)nn);
+    for (auto& q : recs) q = r.pod<PkNode>();
+    std::vector<TreeNode*> nodes((size_t)nn);
+    std::vector<TreeNode*> leaves;
+    for (int i = 0; i < nn; i++) {
+      TreeNode* n = new TreeNode();
+      nodes[i] = n;
+      n->object_id = i; n->depth = recs[i].depth; n->is_leaf = recs[i].is_leaf != 0; n->has_split = !n->is_leaf;
+      n->leaf.object_id = i;
+      if (n->is_leaf) leaves.push_back(n);
+      else {
+        Split& s = n->split;
+        s.feature_channel = recs[i].ch; s.threshold = recs[i].thr_raw;
+        s.rect1 = Rect{recs[i].r1[0], recs[i].r1[1], recs[i].r1[2], recs[i].r1[3]};
+        s.rect2 = Rect{recs[i].r2[0], recs[i].r2[1], recs[i].r2[2], recs[i].r2[3]};
+      }
+    }
+    tree->root = nodes[0];
+    tree->n_nodes_parsed = nn; tree->n_leaves_parsed = (int)leaves.size();
+    for (int i = 0; i < nn; i++)
+      if (!nodes[i]->is_leaf) {
+        if (recs[i].right <= i + 1 || recs[i].right >= nn) return false;
+        nodes[i]->left = nodes[i + 1]; nodes[i]->right = nodes[recs[i].right];
+      }
+    int32_t nh = r.pod<int32_t>();
+    if (!r.ok || nh < 0 || nh > nn) return false;
+    for (int i = 0; i < nh; i++) {
+      PkHpLeaf q = r.pod<PkHpLeaf>();
+      if (kind != KIND_HP || i >= (int)leaves.size()) return false;
+      Leaf& L = leaves[i]->leaf;
+      L.hp_nsamples = q.nsamples; L.hp_foreground = q.foreground; L.hp_nlabels = 5;
+      for (int j = 0; j < 5; j++) L.hp_labels[j] = q.labels[j];
+    }
+    int32_t nm = r.pod<int32_t>();
+    if (!r.ok || nm < 0 || nm > nn) return false;
+    for (int i = 0; i < nm; i++) {
+      PkMpLeaf q = r.pod<PkMpLeaf>();
+      if (kind != KIND_MP || i >= (int)leaves.size()) return false;
+      Leaf& L = leaves[i]->leaf;
+      L.mp_samples = q.samples; L.mp_nparts = 10; L.mp_foreground = q.fg;
+      for (int j = 0; j < 10; j++) { L.mp_parts_offset[j].x = q.off[j][0]; L.mp_parts_offset[j].y = q.off[j][1]; L.mp_parts_variance[j] = q.var[j]; L.mp_prob_foreground[j] = q.pf[j]; }
+    }
+    if (!r.ok || (int)leaves.size() != nh + nm) return false;
+  }
+  return r.ok;
+}
+}  // namespace
+extern "C" {
+
+void* orc_model_load_packed(const char* path) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { set_err(std::string("File not found: ") + path); return nullptr; }
+  std::fseek(f, 0, SEEK_END);
+  long sz = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> buf((size_t)std::max(sz, 0L));
+  bool ok = sz > 0 && std::fread(buf.data(), 1, buf.size(), f) == buf.size();
+  std::fclose(f);
+  if (!ok || buf.size() < 20 || std::memcmp(buf.data(), "CRFB200M", 8) != 0) { set_err("not a packed CRF model"); return nullptr; }
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i + 8 < buf.size(); i++) { h ^= buf[i]; h *= 1099511628211ull; }
+  uint64_t want; std::memcpy(&want, buf.data() + buf.size() - 8, 8);
+  if (h != want) { set_err("checksum mismatch"); return nullptr; }
+  PkReader r{buf.data() + 8, buf.data() + buf.size() - 8};
+  if (r.pod<uint32_t>() != 2) { set_err("packed model version mismatch"); return nullptr; }
+  Model* m = new Model();
+  int32_t hp_cfg = r.pod<int32_t>(), mp_cfg = r.pod<int32_t>(), face_size = r.pod<int32_t>();
+  r.pod<int32_t>(); r.pod<int32_t>();  // patch size, channel count (derived)
+  m->hp_param = default_param(hp_cfg, 15); m->mp_param = default_param(mp_cfg, 20);
+  m->hp_param.face_size = m->mp_param.face_size = face_size;
+  bool good = read_packed_forest(r, m->hp_forest, KIND_HP);
+  int32_t nj = good ? r.pod<int32_t>() : 0;
+  for (int i = 0; good && i < nj; i++) { m->mp_jungle.emplace_back(); good = read_packed_forest(r, m->mp_jungle.back(), KIND_MP); }
+  if (!good || !r.ok) { set_err("corrupt packed model"); orc_model_free(m); return nullptr; }
+  if (m->hp_forest.numberOfTrees() > 0) m->hp_param.patch_size_ratio = m->hp_forest.m_trees[0]->m_param.patch_size_ratio;
+  m->mp_param.patch_size_ratio = m->hp_param.patch_size_ratio;
+  m->hp_forest.m_forest_param = m->hp_param;
+  for (auto& jf : m->mp_jungle) jf.m_forest_param = m->mp_param;
+  return m;
+}
+
+// Leaf payload dump for cross-checking loaders: per leaf in pre-order, 36 floats:
+// HP: [oid, nsamples, fg, labels x5, 0...]; MP: [oid, samples, fg, off x20, var x10, pf x10 -> 43] (cap 44)
+int orc_leaf_dump(void* h, int which, int tree, float* out, int cap_leaves) {
+  Model* m = (Model*)h;
+  const Forest& f = which < 0 ? m->hp_forest : m->mp_jungle[which];
+  if (tree < 0 || tree >= f.numberOfTrees()) return -1;
+  std::vector<TreeNode*> st{f.m_trees[tree]->root};
+  int n = 0;
+  while (!st.empty()) {
+    TreeNode* nd = st.back(); st.pop_back();
+    if (nd->is_leaf) {
+      if (n < cap_leaves && out) {
+        float* o = out + (size_t)n * 44;
+        std::memset(o, 0, sizeof(float) * 44);
+        const Leaf& L = nd->leaf;
+        o[0] = (float)nd->object_id;
+        if (which < 0) { o[1] = (float)L.hp_nsamples; o[2] = L.hp_foreground; for (int j = 0; j < 5; j++) o[3 + j] = (float)L.hp_labels[j]; }
+        else {
+          o[1] = (float)L.mp_samples; o[2] = L.mp_foreground;
+          for (int j = 0; j < 10; j++) { o[3 + 2 * j] = (float)L.mp_parts_offset[j].x; o[4 + 2 * j] = (float)L.mp_parts_offset[j].y; o[23 + j] = L.mp_parts_variance[j]; o[33 + j] = L.mp_prob_foreground[j]; }
+        }
+      }
+      n++;
+    } else { st.push_back(nd->right); st.push_back(nd->left); }
+  }
+  return n;
+}
+
+
 // counts: [0]=hp trees [1]=hp nodes [2]=hp leaves [3]=n mp forests [4]=mp trees [5]=mp nodes [6]=mp leaves
 // [7]=hp max depth [8]=mp max depth [9]=patch size [10]=face size
 int orc_model_info(void* h, int* counts) {

@@ -73,6 +73,9 @@ def lib() -> C.CDLL:
     L.orc_model_load.restype = C.c_void_p
     L.orc_model_load.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     L.orc_model_free.argtypes = [C.c_void_p]
+    L.orc_model_load_packed.restype = C.c_void_p
+    L.orc_model_load_packed.argtypes = [C.c_char_p]
+    L.orc_leaf_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_int]
     L.orc_model_info.argtypes = [C.c_void_p, i32p]
     L.orc_tree_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, C.c_int]
     L.orc_bgr2gray.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p]
@@ -120,9 +123,12 @@ class OracleError(RuntimeError):
 class Model:
     """What FaceForest's constructor loads (src/FaceForest.cpp:15-58)."""
 
-    def __init__(self, hp_dir: str | None, ffd_dir: str | None, hp_ntrees: int = 15, ffd_ntrees: int = 20):
+    def __init__(self, hp_dir: str | None = None, ffd_dir: str | None = None, hp_ntrees: int = 15, ffd_ntrees: int = 20, packed: str | None = None):
         L = lib()
-        self.h = L.orc_model_load((hp_dir or "").encode(), hp_ntrees, (ffd_dir or "").encode(), ffd_ntrees)
+        if packed:
+            self.h = L.orc_model_load_packed(str(packed).encode())
+        else:
+            self.h = L.orc_model_load((hp_dir or "").encode(), hp_ntrees, (ffd_dir or "").encode(), ffd_ntrees)
         if not self.h:
             raise OracleError(L.orc_last_error().decode())
         info = np.zeros(11, np.int32)
@@ -140,6 +146,13 @@ class Model:
         n = L.orc_tree_dump(self.h, which, tree, None, 0)
         out = np.zeros((n, 16), np.int32)
         L.orc_tree_dump(self.h, which, tree, _p(out, C.c_int32), n)
+        return out
+
+    def leaf_dump(self, which: int, tree: int) -> np.ndarray:
+        L = lib()
+        n = L.orc_leaf_dump(self.h, which, tree, None, 0)
+        out = np.zeros((n, 44), np.float32)
+        L.orc_leaf_dump(self.h, which, tree, _p(out, C.c_float), n)
         return out
 
     def compose(self, headpose: float, variance: float):
