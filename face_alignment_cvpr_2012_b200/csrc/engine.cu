@@ -105,10 +105,11 @@ struct crf_ctx {
   int gabor_width[5] = {0, 0, 0, 0, 0};
   ComposeTables ct{};
   // work buffers
-  Buf d_imgs[2], d_fd, d_scaled, d_stacks, d_mag, d_minmax, d_hp_leaf, d_ffd_leaf, d_face_roots, d_face_ntrees, d_votes, d_vote_counts, d_faces,
+  Buf d_imgs[2], d_fd, d_scaled, d_stacks, d_mag, d_minmax, d_hp_leaf, d_ffd_leaf, d_face_roots, d_face_ntrees, d_votes, d_vote_counts, d_seg_counts, d_faces,
       d_u8planes, d_counters, d_misc;
   crf_counters_t cnt{};
   bool counting = false;
+  size_t work_budget = (size_t)24 << 30;  // bytes of work buffers a launch may use (min(24 GB, half of the free memory at creation))
   StageTimer timer;
   // geometry of the current launch
   size_t scaled_fs = 0, stack_fs = 0, plane_stride = 0, mag_fs = 0, mag_ps = 0, hp_leaf_fs = 0, ffd_leaf_fs = 0, vote_cap = 0, u8_fs = 0;
@@ -177,6 +178,7 @@ static int ensure(crf_ctx* c, const Plan& p) {
     if ((rc = c->d_ffd_leaf.reserve(std::max<size_t>(n * c->ffd_leaf_fs * 4, 16)))) return rc;
     if ((rc = c->d_votes.reserve(n * kParts * c->vote_cap * sizeof(DevVote)))) return rc;
     if ((rc = c->d_vote_counts.reserve(n * kParts * 4))) return rc;
+    if ((rc = c->d_seg_counts.reserve(n * kVoteSegs * kParts * 4))) return rc;
   }
   if (p.want_u8 && (rc = c->d_u8planes.reserve(n * c->u8_fs))) return rc;
   return CRF_OK;
@@ -272,25 +274,36 @@ static int launch_hp_reduce(crf_ctx* c, const FaceDesc* fd, int n, int stride, b
   Span s(c, CRF_STAGE_HP_REDUCE);
   ComposeTables ct = c->ct;
   ct.list_cap = list_cap;
-  k_hp_reduce_compose<<<(n + 7) / 8, 256, 0, c->stream>>>(fd, n, c->d_hp_leaf.as<int32_t>(), c->hp_leaf_fs, c->hp_ntrees, stride, c->d_hp_m.as<float>(), ct,
+  k_hp_reduce_compose<<<(n + kFoldChains - 1) / kFoldChains, kFoldThreads, 0, c->stream>>>(fd, n, c->d_hp_leaf.as<int32_t>(), c->hp_leaf_fs, c->hp_ntrees, stride, c->d_hp_m.as<float>(), ct,
                                                           compose ? 1 : 0, faces, c->d_face_roots.as<int32_t>(), c->d_face_ntrees.as<int32_t>());
   KCHECK(); count_launch(c, CRF_STAGE_HP_REDUCE);
+  return CRF_OK;
+}
+
+static int launch_meanshift(crf_ctx* c, const FaceDesc* fd, int nchains, crf_face_t* faces) {
+  Span s(c, CRF_STAGE_MEANSHIFT);
+  MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
+  k_meanshift<<<(nchains + kFoldChains - 1) / kFoldChains, kFoldThreads, kMsSmem, c->stream>>>(fd, nchains, c->d_votes.as<DevVote>(), c->vote_cap,
+                                                                                       c->d_vote_counts.as<int32_t>(), mo, faces,
+                                                                                       c->counting ? c->d_counters.as<unsigned long long>() : nullptr);
+  KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
   return CRF_OK;
 }
 
 static int launch_votes_meanshift(crf_ctx* c, const FaceDesc* fd, int n, int stride, crf_face_t* faces) {
   {
     Span s(c, CRF_STAGE_VOTES);
-    k_votes<<<n, 256, 0, c->stream>>>(fd, c->d_ffd_leaf.as<int32_t>(), c->ffd_leaf_fs, c->d_face_ntrees.as<int32_t>(), stride, c->d_mp_mask.as<uint16_t>(),
-                                      c->d_mp_leaf.as<DevMpLeaf>(), c->d_votes.as<DevVote>(), c->vote_cap, c->d_vote_counts.as<int32_t>());
-    KCHECK(); count_launch(c, CRF_STAGE_VOTES);
+    VoteArgs a{};
+    a.fd = fd; a.leaf_ids = c->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->ffd_leaf_fs; a.face_ntrees = c->d_face_ntrees.as<int32_t>(); a.stride = stride;
+    a.mp_mask = c->d_mp_mask.as<uint16_t>(); a.mp_leaf = c->d_mp_leaf.as<DevMpLeaf>(); a.votes = c->d_votes.as<DevVote>(); a.vote_cap = c->vote_cap;
+    a.seg_counts = c->d_seg_counts.as<int32_t>(); a.vote_counts = c->d_vote_counts.as<int32_t>();
+    CU(cudaMemsetAsync(a.vote_counts, 0, (size_t)n * kParts * 4, c->stream));
+    k_votes_count<<<dim3(kVoteSegs / 8, n), 256, 0, c->stream>>>(a);
+    KCHECK();
+    k_votes_emit<<<dim3(kVoteSegs / 8, n), 256, 0, c->stream>>>(a);
+    KCHECK(); count_launch(c, CRF_STAGE_VOTES, 2);
   }
-  Span s(c, CRF_STAGE_MEANSHIFT);
-  MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
-  k_meanshift<<<(n * kParts + 63) / 64, 64, 0, c->stream>>>(fd, n, c->d_votes.as<DevVote>(), c->vote_cap, c->d_vote_counts.as<int32_t>(), mo, faces,
-                                                            c->counting ? c->d_counters.as<unsigned long long>() : nullptr);
-  KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
-  return CRF_OK;
+  return launch_meanshift(c, fd, n * kParts, faces);
 }
 
 // The whole path for faces [0, n) of a launch: fd, faces are device pointers to the first of them.
@@ -308,7 +321,19 @@ static int run_faces(crf_ctx* c, const FaceDesc* d_fd, int n, int Hmax, const ui
   return CRF_OK;
 }
 
-static int default_chunk(const crf_ctx* c) { return c->opt.max_chunk > 0 ? c->opt.max_chunk : 256; }
+// Faces resident per launch: as many as fit a work-buffer budget (the ordered vote lists are sized for the worst
+// case of every leaf voting for every part), at most 1024 unless the caller asks otherwise.  Latency-bound tails
+// (sequential folds) want many faces in flight; nothing else depends on the choice (results are chunk-invariant).
+static int pick_chunk(const crf_ctx* c, int Hmax, bool headpose_only) {
+  const size_t np_hp = (size_t)patches_1d(125, c->opt.hp_stride) * patches_1d(Hmax, c->opt.hp_stride);
+  const size_t np_ffd = headpose_only ? 0 : (size_t)patches_1d(125, c->opt.ffd_stride) * patches_1d(Hmax, c->opt.ffd_stride);
+  const size_t per_face = (size_t)Hmax * 128 + (size_t)(Hmax + 1) * kRowStride * 4 * 38 + (size_t)Hmax * 128 * 4 * 35 + np_hp * c->hp_ntrees * 4 +
+                          np_ffd * c->mp_ntrees_cfg * (4 + kParts * sizeof(DevVote)) + 4096;
+  const size_t budget = c->work_budget;
+  long long chunk = (long long)(budget / per_face);
+  const int cap = c->opt.max_chunk > 0 ? c->opt.max_chunk : 1024;
+  return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(chunk, cap), 32768));
+}
 
 static int pull_counters(crf_ctx* c) {
   if (!c->counting) return CRF_OK;
@@ -346,9 +371,15 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
   if (step < (size_t)cols * 3) return fail(CRF_ERR_ARG, "step smaller than a row");
   CU(cudaSetDevice(c->device));
   const size_t img_bytes = (size_t)rows * step;
-  // chunks of consecutive faces; a chunk's frames are the distinct frames its faces name
-  const int chunk = default_chunk(c);
   std::vector<FaceDesc> descs((size_t)n);
+  int Hmax_first = 0;
+  for (int i = 0; i < n; i++) {
+    int rc = make_desc(c, rows, cols, step, 0, boxes[i], descs[i]);
+    if (rc) return rc;
+    Hmax_first = std::max(Hmax_first, descs[i].H);
+  }
+  // chunks of consecutive faces; a chunk's frames are the distinct frames its faces name
+  const int chunk = pick_chunk(c, Hmax_first, headpose_only);
   struct Chunk { int f0, f1, Hmax; std::vector<int> frames; };
   std::vector<Chunk> chunks;
   for (int f0 = 0; f0 < n; f0 += chunk) {
@@ -359,8 +390,7 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
       int slot = -1;
       for (size_t k = ch.frames.size(); k-- > 0;) if (ch.frames[k] == im) { slot = (int)k; break; }
       if (slot < 0) { slot = (int)ch.frames.size(); ch.frames.push_back(im); }
-      int rc = make_desc(c, rows, cols, step, (size_t)slot * img_bytes, boxes[i], descs[i]);
-      if (rc) return rc;
+      descs[i].img_off = (size_t)slot * img_bytes;
       ch.Hmax = std::max(ch.Hmax, descs[i].H);
     }
     chunks.push_back(std::move(ch));
@@ -528,7 +558,7 @@ void crf_ctx_destroy(crf_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   Buf* all[] = {&c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
                 &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_scaled, &c->d_stacks, &c->d_mag, &c->d_minmax,
-                &c->d_hp_leaf, &c->d_ffd_leaf, &c->d_face_roots, &c->d_face_ntrees, &c->d_votes, &c->d_vote_counts, &c->d_faces, &c->d_u8planes, &c->d_counters,
+                &c->d_hp_leaf, &c->d_ffd_leaf, &c->d_face_roots, &c->d_face_ntrees, &c->d_votes, &c->d_vote_counts, &c->d_seg_counts, &c->d_faces, &c->d_u8planes, &c->d_counters,
                 &c->d_misc};
   for (Buf* b : all) b->release();
   c->timer.destroy();
@@ -602,6 +632,21 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
       if ((rc = upload(c->d_coef[i], coef[i], c->stream))) return rc;
     }
   }
+  {
+    ExpfTable t;
+    for (int i = 0; i < 32; i++) {
+      const double v = std::exp2((double)i / 32.0);
+      unsigned long long u;
+      std::memcpy(&u, &v, 8);
+      t.tab[i] = u - ((unsigned long long)i << 47);
+    }
+    CU(cudaMemcpyToSymbolAsync(c_expf, &t, sizeof t, 0, cudaMemcpyHostToDevice, c->stream));
+  }
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->work_budget = std::min(c->work_budget, free_b / 2);
+  }
+  CU(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
   if ((rc = c->d_counters.reserve(sizeof(unsigned long long) * CNT_NUM))) return rc;
   CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * CNT_NUM, c->stream));
   if ((rc = c->d_misc.reserve(4096))) return rc;
@@ -686,7 +731,7 @@ int crf_analyze_crops_device(crf_ctx* c, const uint8_t* d_bgr_batch, int n, int 
   if ((rc = c->d_fd.reserve((size_t)n * sizeof(FaceDesc)))) return rc;
   CU(cudaMemcpyAsync(c->d_fd.p, descs.data(), (size_t)n * sizeof(FaceDesc), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(crf_face_t), c->stream));
-  const int chunk = default_chunk(c);
+  const int chunk = pick_chunk(c, Hmax, headpose_only != 0);
   Plan p; p.n = std::min(n, chunk); p.Hmax = Hmax; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
   p.need_ffd = !headpose_only;
   if ((rc = ensure(c, p))) return rc;
@@ -934,20 +979,23 @@ int crf_stage_meanshift(crf_ctx* c, const float* votes_xyw, int n, float mean_xy
   std::vector<DevVote> v((size_t)n);
   for (int i = 0; i < n; i++) { v[i].x = (short)votes_xyw[3 * i]; v[i].y = (short)votes_xyw[3 * i + 1]; v[i].w = votes_xyw[3 * i + 2]; }
   int rc;
-  if ((rc = c->d_votes.reserve(std::max<size_t>((size_t)n * sizeof(DevVote), 16)))) return rc;
+  if ((rc = c->d_votes.reserve(std::max<size_t>((size_t)n * sizeof(DevVote), 16))) || (rc = c->d_vote_counts.reserve(kParts * 4)) ||
+      (rc = c->d_faces.reserve(sizeof(crf_face_t))) || (rc = c->d_fd.reserve(sizeof(FaceDesc))))
+    return rc;
+  FaceDesc d{};
+  d.scale = 1.f;
+  CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->stream));
   if (n) CU(cudaMemcpyAsync(c->d_votes.p, v.data(), (size_t)n * sizeof(DevVote), cudaMemcpyHostToDevice, c->stream));
-  MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
-  float* d_mean = c->d_misc.as<float>();
-  int* d_rnd = reinterpret_cast<int*>(d_mean + 2);
-  int* d_it = d_rnd + 2;
-  k_meanshift_one<<<1, 1, 0, c->stream>>>(c->d_votes.as<DevVote>(), n, mo, d_mean, d_rnd, d_it);
-  KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
-  struct { float m[2]; int r[2]; int it; } h;
-  CU(cudaMemcpyAsync(&h, d_mean, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->d_vote_counts.p, &n, 4, cudaMemcpyHostToDevice, c->stream));
+  c->vote_cap = (size_t)std::max(n, 1);
+  if ((rc = launch_meanshift(c, c->d_fd.as<FaceDesc>(), 1, c->d_faces.as<crf_face_t>()))) return rc;
+  crf_face_t face;
+  CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (mean_xy) { mean_xy[0] = h.m[0]; mean_xy[1] = h.m[1]; }
-  if (rounded_xy) { rounded_xy[0] = h.r[0]; rounded_xy[1] = h.r[1]; }
-  if (iters) *iters = h.it;
+  if (mean_xy) { mean_xy[0] = face.ffd_f[0][0]; mean_xy[1] = face.ffd_f[0][1]; }
+  if (rounded_xy) { rounded_xy[0] = face.ffd_scaled[0][0]; rounded_xy[1] = face.ffd_scaled[0][1]; }
+  if (iters) *iters = face.ms_iters[0];
+  c->timer.collect();
   return CRF_OK;
 }
 

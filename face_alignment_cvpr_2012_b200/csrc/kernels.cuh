@@ -1,6 +1,6 @@
 // sm_100a kernels of the CRF inference path.  Compiled with -fmad=false: every float/double
 // operation below rounds separately unless it is an explicit __fmaf_rn, which is what the
-// canonical arithmetic (restated by oracle/crf_oracle.cc) requires.
+// canonical arithmetic requires.
 //
 // No tensor cores on purpose: nothing on this path is a dense contraction that tolerates reduced
 // precision (the Gabor bank must stay f32-exact in raster order; the forests are integer gathers).
@@ -384,8 +384,8 @@ __device__ __forceinline__ void compose_face(float headpose, float variance, con
                                              crf_face_t* face, int32_t* list, int32_t* ntrees_out) {
   // areaUnderCurve(x1, x2, mean, std): lanes evaluate exp() of their abscissae, lane 0 folds in order.
   const double mean = (double)headpose, sd = sqrt((double)variance);
-  __shared__ double s_e[8][32];
-  double* e = s_e[(threadIdx.x >> 5) & 7];
+  __shared__ double s_e[9][32];
+  double* e = s_e[(threadIdx.x >> 5) % 9];
   float area[CRF_NUM_POSE_FORESTS];
   for (int j = 0; j < CRF_NUM_POSE_FORESTS; j++) {
     double sum = 0;
@@ -432,44 +432,97 @@ __device__ __forceinline__ void compose_face(float headpose, float variance, con
   *ntrees_out = n;
 }
 
-__global__ void __launch_bounds__(256) k_hp_reduce_compose(const FaceDesc* __restrict__ fd, int nfaces, const int32_t* __restrict__ leaf_ids, size_t leaf_face_stride,
-                                                           int ntrees, int stride, const float* __restrict__ hp_m, ComposeTables ct, int do_compose,
-                                                           crf_face_t* __restrict__ faces, int32_t* __restrict__ face_roots, int32_t* __restrict__ face_ntrees) {
-  __shared__ float s_m[8][32];
+// Sequential folds are latency-bound chains (one dependent FADD every 4 cycles), so 32 of them share a warp:
+// lane j of warp 0 folds chain j from shared-memory tiles that the other 8 warps fill one tile ahead
+// (double buffer).  Tiles are laid out [element][chain] with a pitch of 33 words: conflict-free for the
+// producers (lanes = elements) and for the fold (lanes = chains).
+constexpr int kFoldChains = 32;
+constexpr int kFoldThreads = 288;  // warp 0 folds, warps 1..8 produce (4 chains each)
+
+constexpr int kHpTile = 128;
+
+__global__ void __launch_bounds__(kFoldThreads) k_hp_reduce_compose(const FaceDesc* __restrict__ fd, int nfaces, const int32_t* __restrict__ leaf_ids, size_t leaf_face_stride,
+                                                                    int ntrees, int stride, const float* __restrict__ hp_m, ComposeTables ct, int do_compose,
+                                                                    crf_face_t* __restrict__ faces, int32_t* __restrict__ face_roots, int32_t* __restrict__ face_ntrees) {
+  __shared__ float s_m[2][kHpTile][33];
+  __shared__ int s_n[kFoldChains];
+  __shared__ float s_mean[kFoldChains], s_var[kFoldChains];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int f = blockIdx.x * 8 + warp;
-  if (f >= nfaces) return;
-  const FaceDesc d = fd[f];
-  const int nx = (d.W - kPatch + stride - 1) / stride, ny = (d.H - kPatch + stride - 1) / stride;
-  const int n = max(nx, 0) * max(ny, 0) * ntrees;
-  const int32_t* __restrict__ ids = leaf_ids + f * leaf_face_stride;
-  float cnt = 0, sum = 0, sum_sq = 0;
-  for (int b = 0; b < n; b += 32) {
-    const int i = b + lane;
-    s_m[warp][lane] = i < n ? __ldg(hp_m + ids[i]) : -1.f;
-    __syncwarp();
-#pragma unroll 8
-    for (int k = 0; k < 32; k++) {
-      const float m = s_m[warp][k];
-      if (m >= 0.f || m != m) {  // fg > min_foreground_probability (folded into the table at load time)
-        sum += m;
-        sum_sq += m * m;
-        cnt += 1.f;
-      }
+  const int f0 = blockIdx.x * kFoldChains;
+  if (threadIdx.x < kFoldChains) {
+    const int f = f0 + threadIdx.x;
+    int n = 0;
+    if (f < nfaces) {
+      const FaceDesc d = fd[f];
+      const int nx = (d.W - kPatch + stride - 1) / stride, ny = (d.H - kPatch + stride - 1) / stride;
+      n = max(nx, 0) * max(ny, 0) * ntrees;
     }
-    __syncwarp();
+    s_n[threadIdx.x] = n;
   }
-  float mean = sum / cnt;
-  float var = (sum_sq / cnt) - (mean * mean);
-  mean -= 2;
-  var *= 0.05f;  // NORM_HEADPOSE_VARIANCE_FACTOR (include/Constants.hpp:67)
-  crf_face_t* face = faces + f;
-  if (lane == 0) {
-    face->headpose = mean;
-    face->variance = var;
-    face->scaled_w = d.W; face->scaled_h = d.H; face->scale = d.scale;
+  __syncthreads();
+  int maxn = 0;
+  for (int j = 0; j < kFoldChains; j++) maxn = max(maxn, s_n[j]);
+  const int ntiles = (maxn + kHpTile - 1) / kHpTile;
+  auto produce = [&](int tile) {
+    float(*buf)[33] = s_m[tile & 1];
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int j = (warp - 1) * 4 + jj;
+      const int n = s_n[j];
+      if (tile * kHpTile >= n) continue;
+      const int32_t* __restrict__ ids = leaf_ids + (size_t)(f0 + j) * leaf_face_stride;
+      int32_t id[kHpTile / 32];
+#pragma unroll
+      for (int h = 0; h < kHpTile / 32; h++) {
+        const int k = tile * kHpTile + h * 32 + lane;
+        id[h] = k < n ? ids[k] : -1;
+      }
+#pragma unroll
+      for (int h = 0; h < kHpTile / 32; h++) buf[h * 32 + lane][j] = id[h] >= 0 ? __ldg(hp_m + id[h]) : -1.f;
+    }
+  };
+  float cnt = 0, sum = 0, sum_sq = 0;
+  if (warp > 0 && ntiles > 0) produce(0);
+  __syncthreads();
+  for (int tile = 0; tile < ntiles; tile++) {
+    if (warp == 0) {
+      const float(*buf)[33] = s_m[tile & 1];
+      const int kmax = min(kHpTile, s_n[lane] - tile * kHpTile);
+#pragma unroll 8
+      for (int k = 0; k < kHpTile; k++) {
+        // fg > min_foreground_probability is folded into the table at load time (-1 = skip).  Adding +0 is exact
+        // (the sums never hold -0), so the fold is branch-free.
+        const float m = buf[k][lane];
+        const bool valid = k < kmax && !(m < 0.f);
+        const float v = valid ? m : 0.f;
+        sum += v;
+        sum_sq += v * v;
+        cnt += valid ? 1.f : 0.f;
+      }
+    } else if (tile + 1 < ntiles) {
+      produce(tile + 1);
+    }
+    __syncthreads();
   }
-  if (do_compose) compose_face(mean, var, ct, lane, face, face_roots + (size_t)f * kMaxList, face_ntrees + f);
+  if (warp == 0) {
+    float mean = sum / cnt;
+    float var = (sum_sq / cnt) - (mean * mean);
+    mean -= 2;
+    var *= 0.05f;  // NORM_HEADPOSE_VARIANCE_FACTOR (include/Constants.hpp:67)
+    s_mean[lane] = mean; s_var[lane] = var;
+    const int f = f0 + lane;
+    if (f < nfaces) {
+      const FaceDesc d = fd[f];
+      crf_face_t* face = faces + f;
+      face->headpose = mean;
+      face->variance = var;
+      face->scaled_w = d.W; face->scaled_h = d.H; face->scale = d.scale;
+    }
+  }
+  __syncthreads();
+  if (do_compose)
+    for (int j = warp; j < kFoldChains && f0 + j < nfaces; j += kFoldThreads / 32)
+      compose_face(s_mean[j], s_var[j], ct, lane, faces + f0 + j, face_roots + (size_t)(f0 + j) * kMaxList, face_ntrees + f0 + j);
 }
 
 // Composition alone (stage API).
@@ -485,139 +538,260 @@ __global__ void k_compose_only(float headpose, float variance, ComposeTables ct,
 // ---------------------------------------------------------------------------------------------
 struct __align__(8) DevVote { short x, y; float w; };
 
-__global__ void __launch_bounds__(256) k_votes(const FaceDesc* __restrict__ fd, const int32_t* __restrict__ leaf_ids, size_t leaf_face_stride,
-                                               const int32_t* __restrict__ face_ntrees, int stride,
-                                               const uint16_t* __restrict__ mp_mask, const DevMpLeaf* __restrict__ mp_leaf,
-                                               DevVote* __restrict__ votes, size_t vote_cap, int32_t* __restrict__ vote_counts /* [face][10] */) {
-  __shared__ int s_cnt[8][kParts];
-  __shared__ int s_run[kParts];
-  const int f = blockIdx.x;
-  const FaceDesc d = fd[f];
-  const int nt = face_ntrees[f];
-  const int nx = (d.W - kPatch + stride - 1) / stride, ny = (d.H - kPatch + stride - 1) / stride;
-  const int n = max(nx, 0) * max(ny, 0) * nt;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int32_t* __restrict__ ids = leaf_ids + f * leaf_face_stride;
-  DevVote* __restrict__ fv = votes + (size_t)f * kParts * vote_cap;
-  if (threadIdx.x < kParts) s_run[threadIdx.x] = 0;
-  __syncthreads();
-  for (int b = 0; b < n; b += 256) {
-    const int k = b + threadIdx.x;
-    int leaf = -1;
-    unsigned mask = 0;
-    if (k < n) { leaf = ids[k]; mask = __ldg(mp_mask + leaf); }
-    unsigned bal[kParts];
+// The leaves of a face are split into kVoteSegs contiguous warp-segments.  Pass 1 counts the votes of every
+// (segment, part); pass 2 derives each segment's base by summing the earlier segments and compacts with warp
+// ballots only (no block barrier): a warp owns a contiguous run of leaves, so order is preserved.
+constexpr int kVoteSegs = 128;
+
+struct VoteArgs {
+  const FaceDesc* fd;
+  const int32_t* leaf_ids; size_t leaf_face_stride;
+  const int32_t* face_ntrees; int stride;
+  const uint16_t* mp_mask; const DevMpLeaf* mp_leaf;
+  DevVote* votes; size_t vote_cap;
+  int32_t* seg_counts;   // [face][kVoteSegs][kParts]
+  int32_t* vote_counts;  // [face][kParts] (zeroed before pass 1)
+};
+
+__device__ __forceinline__ void vote_segment(const VoteArgs& a, int f, int seg, int& n, int& k0, int& k1, int& nt, int& ny) {
+  const FaceDesc d = a.fd[f];
+  nt = a.face_ntrees[f];
+  const int nx = (d.W - kPatch + a.stride - 1) / a.stride;
+  ny = (d.H - kPatch + a.stride - 1) / a.stride;
+  n = max(nx, 0) * max(ny, 0) * nt;
+  const int per = (((n + kVoteSegs - 1) / kVoteSegs) + 31) & ~31;
+  k0 = min(n, seg * per);
+  k1 = min(n, k0 + per);
+}
+
+// grid = (kVoteSegs / 8, faces), 256 threads: one warp per segment.
+__global__ void __launch_bounds__(256) k_votes_count(VoteArgs a) {
+  const int f = blockIdx.y, lane = threadIdx.x & 31, seg = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int n, k0, k1, nt, ny;
+  vote_segment(a, f, seg, n, k0, k1, nt, ny);
+  const int32_t* __restrict__ ids = a.leaf_ids + f * a.leaf_face_stride;
+  int cnt = 0;  // lane p < kParts accumulates part p
+  for (int k = k0 + lane; k - lane < k1; k += 32) {
+    const unsigned mask = k < k1 ? (unsigned)__ldg(a.mp_mask + ids[k]) : 0u;
 #pragma unroll
     for (int p = 0; p < kParts; p++) {
-      bal[p] = __ballot_sync(0xffffffffu, (mask >> p) & 1u);
-      if (lane == 0) s_cnt[warp][p] = __popc(bal[p]);
+      const int c = __popc(__ballot_sync(0xffffffffu, (mask >> p) & 1u));
+      if (lane == p) cnt += c;
     }
-    __syncthreads();
+  }
+  if (lane < kParts) {
+    a.seg_counts[((size_t)f * kVoteSegs + seg) * kParts + lane] = cnt;
+    if (cnt) atomicAdd(&a.vote_counts[f * kParts + lane], cnt);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
+  const int f = blockIdx.y, lane = threadIdx.x & 31, seg = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int n, k0, k1, nt, ny;
+  vote_segment(a, f, seg, n, k0, k1, nt, ny);
+  if (k0 >= k1) return;
+  // base of this segment for every part: sum over the earlier segments (lanes stride over them)
+  int base[kParts];
+  const int32_t* sc = a.seg_counts + (size_t)f * kVoteSegs * kParts;
+#pragma unroll
+  for (int p = 0; p < kParts; p++) {
+    int v = 0;
+    for (int s = lane; s < seg; s += 32) v += sc[s * kParts + p];
+    base[p] = __reduce_add_sync(0xffffffffu, v);
+  }
+  const int32_t* __restrict__ ids = a.leaf_ids + f * a.leaf_face_stride;
+  DevVote* __restrict__ fv = a.votes + (size_t)f * kParts * a.vote_cap;
+  for (int k = k0 + lane; k - lane < k1; k += 32) {
+    int leaf = 0;
+    unsigned mask = 0;
+    if (k < k1) { leaf = ids[k]; mask = __ldg(a.mp_mask + leaf); }
+    unsigned bal[kParts];
+#pragma unroll
+    for (int p = 0; p < kParts; p++) bal[p] = __ballot_sync(0xffffffffu, (mask >> p) & 1u);
     if (mask) {
       const int patch = k / nt;
       const int ix = patch / ny, iy = patch - ix * ny;
-      const int cx = ix * stride + kHalfPatch, cy = iy * stride + kHalfPatch;
-      const DevMpLeaf L = mp_leaf[leaf];
+      const int cx = ix * a.stride + kHalfPatch, cy = iy * a.stride + kHalfPatch;  // patch centre (src/face_utils.cpp:281-282)
+      const DevMpLeaf L = a.mp_leaf[leaf];
 #pragma unroll
       for (int p = 0; p < kParts; p++) {
         if ((mask >> p) & 1u) {
-          int pos = s_run[p] + __popc(bal[p] & ((1u << lane) - 1u));
-          for (int w = 0; w < warp; w++) pos += s_cnt[w][p];
           DevVote v;
           v.x = (short)(L.off[p][0] + cx);
           v.y = (short)(L.off[p][1] + cy);
           v.w = L.weight;
-          fv[(size_t)p * vote_cap + pos] = v;
+          fv[(size_t)p * a.vote_cap + base[p] + __popc(bal[p] & ((1u << lane) - 1u))] = v;
         }
       }
     }
-    __syncthreads();
-    if (threadIdx.x < kParts) {
-      int tot = 0;
-      for (int w = 0; w < 8; w++) tot += s_cnt[w][threadIdx.x];
-      s_run[threadIdx.x] += tot;
-    }
-    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < kParts; p++) base[p] += __popc(bal[p]);
   }
-  if (threadIdx.x < kParts) vote_counts[f * kParts + threadIdx.x] = s_run[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
 // a14: MeanShift::shift (include/MeanShift.hpp:52-135) + the final rescale of
-// FaceForest::analyzeFace (src/FaceForest.cpp:256-257).  The f32 sums are order-dependent, so one
-// thread owns one (face, part) chain and walks its votes in order.
+// FaceForest::analyzeFace (src/FaceForest.cpp:256-257).  The f32 sums are order-dependent, so each
+// (face, part) chain is folded sequentially — 32 chains per CTA, lane j of warp 0 folds chain j while
+// warps 1..8 evaluate the kernel weights of the next tile of votes in parallel (see the fold note above).
 // ---------------------------------------------------------------------------------------------
 struct MeanShiftOpt { int kernel; int max_iterations; float stopping; };
 
-__device__ __forceinline__ void meanshift_chain(const DevVote* __restrict__ v, int n, MeanShiftOpt o, float* mean_xy, int* rounded, int* iters_out,
-                                                unsigned long long* passes) {
-  float mx = 0.f, my = 0.f;
-  {
-    float sum_w = 0;
-    for (int i = 0; i < n; i++) {
-      const DevVote q = v[i];
-      mx += q.x * q.w;
-      my += q.y * q.w;
-      sum_w += q.w;
-    }
-    if (sum_w > 0) { mx /= sum_w; my /= sum_w; }
+// expf as glibc computes it (sysdeps/ieee754/flt-32/e_expf.c: 2^(k/32) table + cubic in double, one final
+// rounding): bit-identical to the host's expf on every input tried (4e7 in [-60, 0]), which a correctly
+// rounded exp() is not.  tab[i] = bits(2^(i/32)) - (i << 47), built on the host with exp2().
+struct ExpfTable { unsigned long long tab[32]; };
+__constant__ ExpfTable c_expf;
+
+__device__ __forceinline__ float expf_glibc(float x, const unsigned long long* __restrict__ tab) {
+  const double N = 32.0;
+  const double InvLn2N = 0x1.71547652b82fep+0 * N;
+  const double C0 = 0x1.c6af84b912394p-5 / N / N / N, C1 = 0x1.ebfce50fac4f3p-3 / N / N, C2 = 0x1.62e42ff0c52d6p-1 / N;
+  const double xd = (double)x;
+  if (!(xd > -103.0)) return xd != xd ? x : 0.f;   // underflow (arguments here are -distance/lambda <= 0)
+  if (xd > 88.0) return __int_as_float(0x7f800000);
+  const double z = InvLn2N * xd;
+  const double kd = rint(z);
+  const long long ki = (long long)kd;
+  const double r = z - kd;
+  const double s = __longlong_as_double((long long)(tab[ki & 31] + ((unsigned long long)ki << 47)));
+  const double zz = fma(C0, r, C1);
+  const double r2 = r * r;
+  double y = fma(C2, r, 1.0);
+  y = fma(zz, r2, y);
+  return (float)(y * s);
+}
+
+__device__ __forceinline__ void vote_terms(const DevVote q, bool first_pass, float mx, float my, float lamda, const unsigned long long* __restrict__ tab,
+                                           float& w, float& wx, float& wy) {
+  if (first_pass) {
+    w = q.w;
+  } else {
+    const float dx = mx - (float)q.x, dy = my - (float)q.y;
+    const float dist = (float)sqrt((double)dx * dx + (double)dy * dy);  // cv::norm(Point2f) accumulates in double
+    w = q.w * expf_glibc(-dist / lamda, tab);
   }
+  wx = q.x * w;
+  wy = q.y * w;
+}
+
+constexpr int kMsTile = 64;
+constexpr size_t kMsSmem = (size_t)2 * 3 * kMsTile * 33 * sizeof(float);  // dynamic shared memory of k_meanshift
+
+__global__ void __launch_bounds__(kFoldThreads) k_meanshift(const FaceDesc* __restrict__ fd, int nchains, const DevVote* __restrict__ votes, size_t vote_cap,
+                                                            const int32_t* __restrict__ vote_counts, MeanShiftOpt o, crf_face_t* __restrict__ faces,
+                                                            unsigned long long* counters) {
+  extern __shared__ __align__(16) float s_dyn[];
+  typedef float Tile[kMsTile][33];
+  Tile* s_w = reinterpret_cast<Tile*>(s_dyn);   // [2]
+  Tile* s_x = s_w + 2;
+  Tile* s_y = s_w + 4;
+  __shared__ int s_n[kFoldChains], s_active[kFoldChains];
+  __shared__ float s_mx[kFoldChains], s_my[kFoldChains];
+  __shared__ unsigned long long s_tab[32];
+  __shared__ int s_maxn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * kFoldChains;
+  if (threadIdx.x < kFoldChains) {
+    const int c = c0 + threadIdx.x;
+    s_n[threadIdx.x] = c < nchains ? vote_counts[c] : 0;
+    s_active[threadIdx.x] = c < nchains;
+    s_mx[threadIdx.x] = 0.f; s_my[threadIdx.x] = 0.f;
+    s_tab[threadIdx.x] = c_expf.tab[threadIdx.x];
+  }
+  __syncthreads();
   const float lamda = (float)o.kernel;
-  bool conv = false;
-  int it = 0;
-  for (int i = 0; i < o.max_iterations && !conv; i++) {
-    float sx = 0.f, sy = 0.f, sum_w = 0;
-    for (int k = 0; k < n; k++) {
-      const DevVote q = v[k];
-      const float dx = mx - (float)q.x, dy = my - (float)q.y;
-      float dist = (float)sqrt((double)dx * dx + (double)dy * dy);  // cv::norm(Point2f) accumulates in double
-      dist = (float)exp((double)(-dist / lamda));                  // expf: double exp rounded once == correctly rounded f32
-      const float w = q.w * dist;
-      sx += q.x * w;
-      sy += q.y * w;
-      sum_w += w;
+  int it = 0;                 // warp 0, lane j: iterations of chain j
+  float mx = 0.f, my = 0.f;   // warp 0, lane j: current mean of chain j
+  for (int pass = 0; pass <= o.max_iterations; pass++) {
+    if (warp == 0) {
+      int m = s_active[lane] ? max(s_n[lane], 1) : 0;   // an empty chain still runs its (empty) passes
+      m = __reduce_max_sync(0xffffffffu, m);
+      if (lane == 0) s_maxn = m;
     }
-    if (sum_w > 0) { sx /= sum_w; sy /= sum_w; }
-    const float ex = sx - mx, ey = sy - my;
-    if (sqrt((double)ex * ex + (double)ey * ey) < o.stopping) conv = true;
-    mx = sx; my = sy;
-    it++;
+    __syncthreads();
+    const int maxn = s_maxn;
+    if (maxn == 0) break;
+    const int ntiles = (maxn + kMsTile - 1) / kMsTile;
+    auto produce = [&](int tile) {
+      const int b = tile & 1;
+      DevVote q[4][kMsTile / 32];
+      bool ok[4][kMsTile / 32];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const int j = (warp - 1) * 4 + jj;
+        const int n = s_active[j] ? s_n[j] : 0;
+#pragma unroll
+        for (int h = 0; h < kMsTile / 32; h++) {
+          const int k = tile * kMsTile + h * 32 + lane;
+          ok[jj][h] = k < n;
+          if (ok[jj][h]) q[jj][h] = votes[(size_t)(c0 + j) * vote_cap + k];
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const int j = (warp - 1) * 4 + jj;
+        const float cmx = s_mx[j], cmy = s_my[j];
+#pragma unroll
+        for (int h = 0; h < kMsTile / 32; h++) {
+          if (!ok[jj][h]) continue;
+          float w, wx, wy;
+          vote_terms(q[jj][h], pass == 0, cmx, cmy, lamda, s_tab, w, wx, wy);
+          s_w[b][h * 32 + lane][j] = w; s_x[b][h * 32 + lane][j] = wx; s_y[b][h * 32 + lane][j] = wy;
+        }
+      }
+    };
+    float sw = 0.f, sx = 0.f, sy = 0.f;
+    if (warp > 0) produce(0);
+    __syncthreads();
+    for (int tile = 0; tile < ntiles; tile++) {
+      if (warp == 0) {
+        const int b = tile & 1;
+        const int kmax = s_active[lane] ? min(kMsTile, s_n[lane] - tile * kMsTile) : 0;
+#pragma unroll 8
+        for (int k = 0; k < kMsTile; k++) {   // branch-free: adding +0 is exact (the sums never hold -0)
+          const bool valid = k < kmax;
+          sx += valid ? s_x[b][k][lane] : 0.f;
+          sy += valid ? s_y[b][k][lane] : 0.f;
+          sw += valid ? s_w[b][k][lane] : 0.f;
+        }
+      } else if (tile + 1 < ntiles) {
+        produce(tile + 1);
+      }
+      __syncthreads();
+    }
+    if (warp == 0 && s_active[lane]) {
+      if (sw > 0) { sx /= sw; sy /= sw; }
+      if (pass == 0) {
+        mx = sx; my = sy;
+        if (o.max_iterations <= 0) s_active[lane] = 0;
+      } else {
+        const float ex = sx - mx, ey = sy - my;
+        const bool conv = sqrt((double)ex * ex + (double)ey * ey) < o.stopping;
+        mx = sx; my = sy;
+        it++;
+        if (conv || it >= o.max_iterations) s_active[lane] = 0;
+      }
+      s_mx[lane] = mx; s_my[lane] = my;
+    }
+    __syncthreads();
   }
-  mean_xy[0] = mx; mean_xy[1] = my;
-  rounded[0] = __float2int_rn(mx);  // Point_<int> = Point_<float>: cvRound
-  rounded[1] = __float2int_rn(my);
-  *iters_out = it;
-  if (passes) *passes = (unsigned long long)n * (1 + it);
-}
-
-__global__ void __launch_bounds__(64) k_meanshift(const FaceDesc* __restrict__ fd, int nfaces, const DevVote* __restrict__ votes, size_t vote_cap,
-                                                  const int32_t* __restrict__ vote_counts, MeanShiftOpt o, crf_face_t* __restrict__ faces,
-                                                  unsigned long long* counters) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nfaces * kParts) return;
-  const int f = i / kParts, p = i - f * kParts;
-  const int n = vote_counts[i];
-  float mean[2];
-  int rnd[2], it;
-  unsigned long long passes = 0;
-  meanshift_chain(votes + ((size_t)f * kParts + p) * vote_cap, n, o, mean, rnd, &it, counters ? &passes : nullptr);
-  crf_face_t* face = faces + f;
-  face->ffd_f[p][0] = mean[0]; face->ffd_f[p][1] = mean[1];
-  face->ffd_scaled[p][0] = rnd[0]; face->ffd_scaled[p][1] = rnd[1];
-  const float inv = 1.0f / fd[f].scale;  // Point_<int> *= float: saturate_cast<int>(x * b)
-  face->ffd[p][0] = __float2int_rn(rnd[0] * inv);
-  face->ffd[p][1] = __float2int_rn(rnd[1] * inv);
-  face->ms_iters[p] = it;
-  face->n_votes[p] = n;
-  if (counters) {
-    atomicAdd(&counters[CNT_VOTES], (unsigned long long)n);
-    atomicAdd(&counters[CNT_VOTE_PASSES], passes);
+  if (warp == 0 && c0 + lane < nchains) {
+    const int c = c0 + lane, f = c / kParts, p = c - f * kParts;
+    const int rx = __float2int_rn(mx), ry = __float2int_rn(my);  // Point_<int> = Point_<float>: cvRound
+    crf_face_t* face = faces + f;
+    face->ffd_f[p][0] = mx; face->ffd_f[p][1] = my;
+    face->ffd_scaled[p][0] = rx; face->ffd_scaled[p][1] = ry;
+    const float inv = 1.0f / fd[f].scale;  // Point_<int> *= float: saturate_cast<int>(x * b)
+    face->ffd[p][0] = __float2int_rn(rx * inv);
+    face->ffd[p][1] = __float2int_rn(ry * inv);
+    face->ms_iters[p] = it;
+    face->n_votes[p] = s_n[lane];
+    if (counters) {
+      atomicAdd(&counters[CNT_VOTES], (unsigned long long)s_n[lane]);
+      atomicAdd(&counters[CNT_VOTE_PASSES], (unsigned long long)s_n[lane] * (1 + it));
+    }
   }
-}
-
-// MeanShift on a caller-supplied list (stage API).
-__global__ void k_meanshift_one(const DevVote* v, int n, MeanShiftOpt o, float* mean, int* rounded, int* iters) {
-  meanshift_chain(v, n, o, mean, rounded, iters, nullptr);
 }
 
 }  // namespace crf

@@ -40,7 +40,8 @@ def loadConfigFile(path: str) -> ForestParam:
     except OSError:
         raise FileNotFoundError(f"file not found {path}")
     vals = [lines[i].strip() for i in range(1, len(lines), 2)]
-    p.max_depth = int(vals[0]); p.ntrees = int(vals[3]); p.tree_path = vals[4]
+    # order of data/config_*.txt: image index, tree path, ntrees, ntests, max depth, min patches, images, patches, face size, ratio, features
+    p.tree_path = vals[1]; p.ntrees = int(vals[2]); p.max_depth = int(vals[4])
     p.face_size = int(vals[8]); p.patch_size_ratio = float(vals[9]); p.features = [int(v) for v in vals[10].split()]
     return p
 

@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library loads, exports every symbol include/crf_b200.h declares, and refuses to run without a GPU."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared():
+    hdr = (ROOT / "include" / "crf_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(crf_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_every_declared_symbol_is_exported(crf):
+    from face_alignment_cvpr_2012_b200 import capi
+    L = C.CDLL(str(capi.LIB_PATH))
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(capi.EXPORTS) == names
+
+
+def test_options_default_are_the_reference_defaults(crf):
+    o = crf.Options()
+    crf.lib().crf_options_default(C.byref(o))
+    assert (o.hp_stride, o.ffd_stride, o.ffd_min_samples, o.ms_kernel_size, o.ms_max_iterations) == (4, 3, 2, 10, 7)
+    assert abs(o.ffd_min_pf - 0.25) < 1e-9 and abs(o.ms_stopping_criteria - 0.05) < 1e-7 and o.ffd_max_variance == 25.0
+
+
+def test_no_cpu_fallback(crf, synth_models):
+    if crf.lib().crf_device_count() > 0:
+        pytest.skip("a GPU is present")
+    gm, _ = synth_models
+    with pytest.raises(crf.CrfError) as e:
+        crf.Context(gm, 0)
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+    ff = crf.FaceForest(model=gm)  # reference behaviour: constructor prints, is_inizialized stays false, use asserts
+    assert not ff.is_inizialized
+    with pytest.raises(AssertionError):
+        ff.analyzeFace(None, (0, 0, 10, 10))
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, link or call it."""
+    bad = re.compile(r"(^\s*(from|import)\s+oracle\b|libcrf_oracle|\borc_[a-z_]+\s*\(|oracle/crf_oracle|oracle\.oracle)", re.M)
+    for p in (ROOT / "face_alignment_cvpr_2012_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".cc", ".h") or p.name == "Makefile":
+            m = bad.search(p.read_text())
+            assert m is None, (p, m.group(0))

@@ -1,0 +1,344 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle on the same inputs, stage by stage and end to end.
+Bit-exact for every integer / byte / index result (scaled pixels, 8-bit planes, integrals, leaf ids, vote lists,
+head pose and its variance, forest composition); MeanShift means within the 0.5 px of the north star (observed
+<= 1e-4: the only non-identical operation is exp())."""
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL_PX = 0.5
+
+
+@pytest.fixture(scope="module")
+def gpu(crf):
+    if crf.lib().crf_device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box (there is no CPU fallback)")
+    return True
+
+
+@pytest.fixture(scope="module")
+def sctx(crf, gpu, synth_models):
+    return crf.Context(synth_models[0], 0)
+
+
+@pytest.fixture(scope="module")
+def rctx(crf, gpu, staged_models):
+    return crf.Context(staged_models[0], 0)
+
+
+def _planes(rng, C=38, H=125, W=125, smooth=True):
+    import cv2
+    p = rng.integers(0, 256, (C, H, W), dtype=np.uint8)
+    if smooth:
+        p = np.stack([cv2.GaussianBlur(q, (0, 0), 2.0) for q in p])
+        p = np.clip((p.astype(np.float32) - 128) * 6 + 128, 0, 255).astype(np.uint8)
+    return p
+
+
+# ------------------------------------------------------------------ stages
+@pytest.mark.parametrize("shape,box", [((250, 250), (61, 72, 130, 130)), ((97, 143), (3, 5, 100, 90)), ((300, 400), (10, 20, 333, 250)),
+                                       ((480, 640), (100, 50, 211, 300)), ((1080, 1920), (700, 200, 507, 611)), ((64, 64), (0, 0, 64, 64))])
+def test_gray_resize(O, sctx, shape, box):
+    rng = np.random.default_rng(shape[0] * 7 + box[2])
+    img = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+    got = sctx.stage_gray_resize(img, box)
+    x, y, w, h = box
+    sw, sh, _ = O.scaled_size(w, h)
+    want = O.resize(O.bgr2gray(img)[y:y + h, x:x + w], sh, sw)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_gray_resize_matches_cv2(sctx, cv2_golden):
+    """Directly against cv2 (same image on the GPU box): cvtColor + crop + resize."""
+    import cv2
+    bgr = cv2_golden["bgr"]
+    for box in [(0, 0, 143, 97), (10, 5, 100, 80), (40, 30, 60, 60)]:
+        x, y, w, h = box
+        g = sctx.stage_gray_resize(bgr, box)
+        ref = cv2.resize(cv2_golden["gray"][y:y + h, x:x + w], (g.shape[1], g.shape[0]), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(g, ref), box
+
+
+@pytest.mark.parametrize("H,W", [(125, 125), (141, 125), (148, 124), (32, 125), (200, 125)])
+def test_channels_bit_exact(O, sctx, H, W):
+    import cv2
+    rng = np.random.default_rng(H * 1000 + W)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), 1.2)
+    planes, integ = sctx.stage_channels(img)
+    op, oi = O.channels(img)
+    assert np.array_equal(planes, op)
+    assert np.array_equal(integ, oi.astype(np.uint32))
+    mm, mi = sctx.stage_channels(img, minmax=True)
+    omm, omi = O.channels(img, features_mask=0b1000)
+    assert np.array_equal(mm, omm) and np.array_equal(mi, omi.astype(np.uint32))
+
+
+def test_channels_golden_plane(sctx, cv2_golden):
+    """Against cv2 itself: gray integral, Sobel planes and the 7x7 Gabor planes are bit-exact; larger kernels +-1 LSB."""
+    img = cv2_golden["plane"]
+    planes, integ = sctx.stage_channels(img)
+    assert np.array_equal(integ[0], cv2_golden["integral"].astype(np.uint32))
+    assert np.array_equal(planes[36], cv2_golden["sobel_dy"]) and np.array_equal(planes[37], cv2_golden["sobel_dx"])
+    ref = cv2_golden["gabor_u8_cv2"]
+    assert np.array_equal(planes[1:8], ref[:7])
+    d = planes[1:36].astype(int) - ref.astype(int)
+    assert np.abs(d).max() <= 1 and (d != 0).mean() < 1e-3
+
+
+def test_channels_degenerate_images(O, sctx):
+    for img in (np.zeros((125, 125), np.uint8), np.full((125, 125), 255, np.uint8), np.tile(np.arange(125, dtype=np.uint8), (125, 1))):
+        planes, integ = sctx.stage_channels(img)
+        op, oi = O.channels(img)
+        assert np.array_equal(planes, op) and np.array_equal(integ, oi.astype(np.uint32))
+
+
+@pytest.mark.parametrize("stride,H,W", [(4, 125, 125), (3, 125, 125), (1, 125, 125), (4, 148, 124), (3, 33, 125), (2, 190, 125), (7, 125, 125)])
+def test_forest_leaf_ids_synthetic_model(O, sctx, synth_models, stride, H, W):
+    _, om = synth_models
+    rng = np.random.default_rng(stride * 100 + H)
+    planes = _planes(rng, 38, H, W)
+    s = O.Sample(planes=planes)
+    ids_o, hp_o, var_o, _ = om.eval_hp(s, stride)
+    assert np.array_equal(sctx.stage_eval_forest(planes, stride), ids_o)
+    fi = rng.integers(0, 5, 20); ti = rng.integers(0, 20, 20)
+    e = om.eval_ffd(s, fi, ti, stride)
+    assert np.array_equal(sctx.stage_eval_forest(planes, stride, fi, ti), e["leaf_ids"])
+    s.close()
+
+
+def test_forest_errors(crf, sctx):
+    planes = np.zeros((10, 125, 125), np.uint8)
+    with pytest.raises(crf.CrfError):  # forests read channels up to 37
+        sctx.stage_eval_forest(planes, 4)
+    with pytest.raises(crf.CrfError):
+        sctx.stage_eval_forest(np.zeros((38, 125, 125), np.uint8), 3, [9], [0])
+    # a face no larger than a patch has an empty grid in the reference (face_utils.cpp:200-202): argument error here
+    with pytest.raises(crf.CrfError):
+        sctx.stage_eval_forest(np.zeros((38, 31, 125), np.uint8), 4)
+
+
+@pytest.mark.parametrize("stride", [4, 1])
+def test_headpose_reduce_and_composition(O, sctx, synth_models, stride):
+    _, om = synth_models
+    rng = np.random.default_rng(77 + stride)
+    for k in range(3):
+        planes = _planes(rng, 38, 125 + 10 * k, 125)
+        s = O.Sample(planes=planes)
+        _, hp_o, var_o, _ = om.eval_hp(s, stride)
+        r = sctx.stage_headpose(planes, stride)
+        assert r["headpose"] == hp_o and r["variance"] == var_o  # same sequential f32 order
+        counts, dom, fi, ti, fl = om.compose(hp_o, var_o)
+        assert np.array_equal(r["tree_counts"], counts) and r["dominant"] == dom and r["flags"] == fl
+        assert np.array_equal(r["forest_idx"], fi) and np.array_equal(r["tree_idx"], ti)
+        s.close()
+
+
+def test_composition_grid_including_pathological(O, sctx, synth_models):
+    """Composition on a grid of (headpose, variance), incl. zero / tiny / negative / NaN variance."""
+    _, om = synth_models
+    hps = [-2.0, -0.6, -0.35, -0.2, -0.05, 0.0, 0.13, 0.2, 0.35, 0.9, 2.0, float("nan")]
+    vars_ = [0.0, 1e-9, 1e-6, 2.5e-5, 1e-4, 0.003, 0.02, 0.05, 0.3, 2.0, -0.01, float("nan"), float("inf")]
+    for hp in hps:
+        for v in vars_:
+            counts, dom, fi, ti, fl = om.compose(np.float32(hp), np.float32(v))
+            r = sctx.stage_compose(float(np.float32(hp)), float(np.float32(v)))
+            assert np.array_equal(r["tree_counts"], counts), (hp, v, r["tree_counts"], counts)
+            assert r["dominant"] == dom and r["flags"] == fl, (hp, v)
+            assert np.array_equal(r["forest_idx"], fi) and np.array_equal(r["tree_idx"], ti), (hp, v)
+
+
+@pytest.mark.parametrize("stride", [3, 1])
+def test_votes_and_meanshift(O, sctx, synth_models, stride):
+    _, om = synth_models
+    rng = np.random.default_rng(5 + stride)
+    planes = _planes(rng, 38, 130, 125)
+    fi = rng.integers(0, 5, 20); ti = rng.integers(0, 20, 20)
+    s = O.Sample(planes=planes)
+    cap = 40000 if stride == 1 else 8000
+    e = om.eval_ffd(s, fi, ti, stride, vote_cap=cap)
+    v = sctx.stage_votes_meanshift(planes, stride, fi, ti, vote_cap=cap)
+    assert np.array_equal(v["n_votes"], e["n_votes"]) and e["n_votes"].max() <= cap and e["n_votes"].sum() > 0
+    assert np.array_equal(v["votes"], e["votes"])  # same votes in the same order
+    assert np.array_equal(v["iters"], e["iters"])
+    assert np.abs(v["mean"] - e["mean"]).max() <= TOL_PX
+    assert np.abs(v["mean"] - e["mean"]).max() <= 1e-3  # what the exp() difference actually allows
+    assert np.abs(v["rounded"] - e["rounded"]).max() <= 1
+    s.close()
+
+
+def test_meanshift_lists(O, sctx):
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 2, 31, 32, 33, 1000, 20000):
+        v = np.zeros((n, 3), np.float32)
+        v[:, 0] = rng.integers(-30, 160, n); v[:, 1] = rng.integers(-30, 160, n); v[:, 2] = rng.choice([0.55, 0.6, 0.75, 1.0], n)
+        mo, ro, io = O.meanshift(v)
+        mg, rg, ig = sctx.stage_meanshift(v)
+        assert ig == io and np.abs(mg - mo).max() <= 1e-3, n
+    # two tight clusters: converges to the heavier one
+    v = np.array([[10, 10, 1.0]] * 50 + [[100, 100, 1.0]] * 30, np.float32)
+    mo, ro, io = O.meanshift(v)
+    mg, rg, ig = sctx.stage_meanshift(v)
+    assert ig == io and np.array_equal(rg, ro)
+
+
+# ------------------------------------------------------------------ whole path
+def _check_faces(got, want, exact_counts=True):
+    assert got["headpose"].tobytes() == want["headpose"].tobytes()  # bit-exact incl. NaN
+    assert got["variance"].tobytes() == want["variance"].tobytes()
+    for k in ("tree_counts", "dominant", "scaled_w", "scaled_h", "n_votes", "ms_iters", "flags"):
+        assert np.array_equal(got[k], want[k]), k
+    assert got["scale"].tobytes() == want["scale"].tobytes()
+    d = np.abs(got["ffd_f"] - want["ffd_f"])
+    assert np.nanmax(d) <= TOL_PX
+    return float(np.nanmax(d)), float((got["ffd"] == want["ffd"]).mean())
+
+
+def test_analyze_crops_synthetic_model(O, crf, sctx, synth_models):
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    _, om = synth_models
+    crops, _ = wl.make_crops(24, seed=31)
+    got = sctx.analyze_crops(crops)
+    want = np.array([om.analyze_face(c, (0, 0, 100, 100)) for c in crops])
+    dmax, int_eq = _check_faces(got, want)
+    assert dmax <= 1e-3 and int_eq >= 0.99
+    hp_only = sctx.analyze_crops(crops, headpose_only=True)
+    assert hp_only["headpose"].tobytes() == want["headpose"].tobytes() and (hp_only["n_votes"] == 0).all()
+
+
+def test_analyze_faces_ragged_boxes(O, sctx, synth_models):
+    """One frame, boxes of many sizes and aspect ratios (W = 124 and 125, H from 60 to 230), incl. image borders."""
+    _, om = synth_models
+    import cv2
+    rng = np.random.default_rng(8)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (600, 800, 3), dtype=np.uint8), (0, 0), 2)
+    boxes = [(0, 0, 100, 100), (700, 480, 100, 120), (50, 60, 212, 180), (300, 100, 131, 240), (10, 300, 400, 200), (500, 10, 90, 133),
+             (123, 77, 250, 250), (600, 300, 64, 64), (400, 350, 334, 170), (20, 20, 120, 160)]
+    got = sctx.analyze_faces(img, boxes)
+    want = np.array([om.analyze_face(img, b) for b in boxes])
+    assert set(want["scaled_w"].tolist()) == {124, 125}
+    _check_faces(got, want)
+
+
+def test_argument_errors(crf, sctx):
+    img = np.zeros((100, 100, 3), np.uint8)
+    for box in [(-1, 0, 50, 50), (60, 60, 50, 50), (0, 0, 0, 10), (0, 0, 100, 20), (0, 0, 20, 100)]:  # outside / empty / flatter than a patch / taller than 521
+        with pytest.raises(crf.CrfError) as e:
+            sctx.analyze_faces(img, [box])
+        assert e.value.code == -1
+    assert len(sctx.analyze_faces(img, [])) == 0
+    assert len(sctx.analyze_crops(np.zeros((0, 100, 100, 3), np.uint8))) == 0
+
+
+def test_batch_api_and_chunk_independence(crf, O, synth_models, gpu):
+    """Results do not depend on how faces are chunked or which frame buffer they came through."""
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, om = synth_models
+    frames, boxes, iob, _ = wl.make_frames(5, 360, 640, 4, seed=4, wmin=60, wmax=150)
+    a = crf.Context(gm, 0, crf._options(None, max_chunk=3)).analyze_batch(frames, boxes, iob)
+    b = crf.Context(gm, 0, crf._options(None, max_chunk=64)).analyze_batch(frames, boxes, iob)
+    assert a.tobytes() == b.tobytes()
+    want = np.array([om.analyze_face(frames[i], bx) for bx, i in zip(boxes, iob)])
+    _check_faces(a, want)
+
+
+def test_counters_match_oracle_visits(O, crf, synth_models, gpu):
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, om = synth_models
+    crops, _ = wl.make_crops(3, seed=2)
+    ctx = crf.Context(gm, 0)
+    ctx.set_profiling(True, True)
+    ctx.reset_counters()
+    ctx.analyze_crops(crops)
+    c = ctx.counters()
+    hp = ffd = votes = 0
+    for cr in crops:
+        rec, st = om.analyze_face(cr, (0, 0, 100, 100), want_stats=True)
+        hp += st[0]; ffd += st[1]; votes += st[2]
+    # the oracle counts node visits incl. the leaf; the device counts node tests (internal nodes only)
+    assert c["hp_node_tests"] == hp - c["hp_traversals"] and c["ffd_node_tests"] == ffd - c["ffd_traversals"]
+    assert c["votes"] == votes and c["faces"] == 3 and c["kernel_launches"] > 0
+
+
+# ------------------------------------------------------------------ shipped forests (staged packed image)
+def test_lfw_golden_end_to_end(rctx, lfw_faces, lfw_golden):
+    """The 20 shipped LFW faces with the shipped forests against the committed oracle records (made from the
+    reference's own text archives) and their ground truth."""
+    names = lfw_golden["names"].tolist()
+    recs = lfw_golden["recs"]
+    errs = []
+    for f in lfw_faces:
+        k = names.index(f["name"])
+        got = rctx.analyze_faces(f["img"], [f["box"]])[0]
+        want = recs[k]
+        assert got["headpose"] == want["headpose"] and got["variance"] == want["variance"]
+        assert np.array_equal(got["tree_counts"], want["tree_counts"]) and np.array_equal(got["n_votes"], want["n_votes"])
+        assert np.abs(got["ffd_f"] - want["ffd_f"]).max() <= 1e-3
+        assert np.array_equal(got["ffd"], want["ffd"])
+        gt = lfw_golden["gt"][k].astype(np.float64)
+        iod = np.linalg.norm((gt[0] + gt[1]) / 2 - (gt[6] + gt[7]) / 2)
+        errs.append(np.linalg.norm(gt - got["ffd"], axis=1) / iod)
+    assert abs(float(np.mean(errs)) - 0.0747) < 0.01
+
+
+def test_lfw_leaf_id_checksums(O, rctx, staged_models, lfw_faces, lfw_golden):
+    _, om = staged_models
+    names = lfw_golden["names"].tolist()
+    for f in lfw_faces[:6]:
+        k = names.index(f["name"])
+        sc = rctx.stage_gray_resize(f["img"], f["box"])
+        planes, _ = rctx.stage_channels(sc)
+        ids = rctx.stage_eval_forest(planes, 4)
+        assert zlib.crc32(ids.tobytes()) == int(lfw_golden["hp_crc"][k])
+        r = rctx.stage_headpose(planes, 4)
+        ids = rctx.stage_eval_forest(planes, 3, r["forest_idx"], r["tree_idx"])
+        assert zlib.crc32(ids.tobytes()) == int(lfw_golden["ffd_crc"][k])
+
+
+def test_stride1_shipped_forests(O, crf, staged_models, gpu):
+    """BASELINE config 2 shape at a size the oracle finishes in seconds: dense stride-1 grids, incl. a pure-noise crop."""
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, om = staged_models
+    crops, _ = wl.make_crops(8, seed=2012)
+    ctx = crf.Context(gm, 0, crf._options(None, hp_stride=1, ffd_stride=1))
+    got = ctx.analyze_crops(crops)
+    idx = [0, 5, 7]
+    want = np.array([om.analyze_face(crops[i], (0, 0, 100, 100), 1, 1) for i in idx])
+    dmax, _ = _check_faces(got[idx], want)
+    assert dmax <= 1e-3
+    assert want["ms_iters"][2].max() == 7  # the noise crop runs MeanShift to its iteration cap
+
+
+def test_full_size_properties(crf, staged_models, gpu):
+    """BASELINE config 2 at full size (4096 crops, stride 1): size-independent properties instead of the oracle —
+    identical crops give identical records wherever they sit in the batch, chunking does not matter, and the
+    host-buffer and device-buffer entry points agree bit for bit."""
+    import torch
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, _ = staged_models
+    base, _ = wl.make_crops(64, seed=2012)
+    rng = np.random.default_rng(0)
+    perm = rng.integers(0, 64, 4096)
+    crops = base[perm]
+    ctx = crf.Context(gm, 0, crf._options(None, hp_stride=1, ffd_stride=1, max_chunk=256))
+    got = ctx.analyze_crops(crops)
+    ref = crf.Context(gm, 0, crf._options(None, hp_stride=1, ffd_stride=1, max_chunk=37)).analyze_crops(base)
+    assert got.tobytes() == ref[perm].tobytes()
+    d_crops = torch.from_numpy(crops).cuda()
+    d_out = torch.empty(4096 * crf.FACE_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.analyze_crops_device(d_crops.data_ptr(), 4096, 100, 100, d_out.data_ptr())
+    assert d_out.cpu().numpy().tobytes() == got.tobytes()
+
+
+def test_face_forest_class_mirror(crf, staged_models, lfw_faces, lfw_golden, gpu):
+    gm, _ = staged_models
+    ff = crf.FaceForest(model=gm)
+    assert ff.is_inizialized
+    f = lfw_faces[0]
+    face = ff.analyzeFace(f["img"], f["box"])
+    k = lfw_golden["names"].tolist().index(f["name"])
+    assert np.array_equal(face.ffd_cordinates, lfw_golden["recs"][k]["ffd"]) and face.bbox == tuple(f["box"])
+    faces = ff.analyzeImage(f["img"], [f["box"], f["box"]])
+    assert len(faces) == 2 and np.array_equal(faces[1].ffd_cordinates, face.ffd_cordinates)

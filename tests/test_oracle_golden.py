@@ -1,0 +1,88 @@
+"""CPU: the oracle against the committed cv2 4.13 golden vectors (tests/golden/make_golden.py) — this is what pins
+the oracle, since the reference ships no tests or vectors for the path and cannot be built here."""
+import numpy as np
+
+
+def test_bgr2gray(O, cv2_golden):
+    assert np.array_equal(O.bgr2gray(cv2_golden["bgr"]), cv2_golden["gray"])
+
+
+def test_resize_bit_exact(O, cv2_golden):
+    k = 0
+    while f"resize_src_{k}" in cv2_golden:
+        dst = cv2_golden[f"resize_dst_{k}"]
+        got = O.resize(cv2_golden[f"resize_src_{k}"], dst.shape[0], dst.shape[1])
+        assert np.array_equal(got, dst), k
+        k += 1
+    assert k >= 7
+
+
+def test_scaled_size_follows_float_math(O):
+    assert O.scaled_size(130, 130)[:2] == (125, 125)
+    assert O.scaled_size(100, 100)[:2] == (125, 125)
+    for w in range(40, 700):
+        sw, sh, s = O.scaled_size(w, w + 7)
+        sc = np.float32(125) / np.float32(w)
+        assert sw == int(np.float32(w) * sc) and sh == int(np.float32(w + 7) * sc) and sw in (124, 125)
+
+
+def test_plain_channels(O, cv2_golden):
+    img = cv2_golden["plane"]
+    planes, integ = O.channels(img, features_mask=0b0101)  # gray + sobel
+    assert np.array_equal(planes[0], img)
+    assert np.array_equal(integ[0], cv2_golden["integral"])
+    assert np.array_equal(planes[1], cv2_golden["sobel_dy"])  # plane 36 of the full stack = d/dy (reference misnames it sob_x)
+    assert np.array_equal(planes[2], cv2_golden["sobel_dx"])
+    mm, _ = O.channels(img, features_mask=0b1000)
+    assert np.array_equal(mm[0], cv2_golden["erode"]) and np.array_equal(mm[1], cv2_golden["dilate"])
+
+
+def test_gabor_7x7_filter2d_bit_exact(O, cv2_golden):
+    img = cv2_golden["plane"]
+    for idx in range(7):
+        re, im = O.gabor_response(img, idx)
+        assert np.array_equal(re, cv2_golden[f"f2d_re_{idx}"]), idx
+        assert np.array_equal(im, cv2_golden[f"f2d_im_{idx}"]), idx
+
+
+def test_gabor_planes_vs_cv2(O, cv2_golden):
+    """nu = 0 planes are bit-exact; for >= 9x9 kernels cv2 switches to a DFT path, so the pin is statistical:
+    every difference is +-1 LSB and rarer than 1e-3 (observed ~1e-5)."""
+    img = cv2_golden["plane"]
+    planes, _ = O.channels(img, features_mask=0b0010)
+    ref = cv2_golden["gabor_u8_cv2"]
+    assert planes.shape == ref.shape == (35,) + img.shape
+    assert np.array_equal(planes[:7], ref[:7])
+    d = planes.astype(int) - ref.astype(int)
+    assert np.abs(d).max() <= 1
+    assert (d != 0).mean() < 1e-3
+
+
+def test_gabor_bank_geometry(O):
+    bank = O.gabor_bank()
+    assert [b[0].shape[0] for b in bank] == [7] * 7 + [9] * 7 + [13] * 7 + [19] * 7 + [25] * 7
+
+
+def test_node_test_integer_division_equivalence():
+    """(int)((float)s / (float)(w*h)) == s / (w*h) == umulhi(s << 1, floor(2^31 / area) + 1) for every area the patch
+    admits and every sum a u8 plane can produce (device_forest.h magic_for_area)."""
+    for area in list(range(1, 485)) + [529, 600, 900, 961]:
+        s = np.arange(0, 255 * area + 1, dtype=np.int64)
+        q = s // area
+        fl = (s.astype(np.float32) / np.float32(area)).astype(np.int64)
+        m = (1 << 31) // area + 1
+        mg = ((s << 1) * m) >> 32
+        assert np.array_equal(q, fl) and np.array_equal(q, mg), area
+
+
+def test_meanshift_empty_and_single(O):
+    mean, rnd, it = O.meanshift(np.zeros((0, 3), np.float32))
+    assert mean.tolist() == [0, 0] and it == 1
+    mean, rnd, it = O.meanshift(np.array([[10, 20, 0.75]], np.float32))
+    assert rnd.tolist() == [10, 20] and it == 1
+
+
+def test_area_under_curve_sums_to_one(O):
+    edges = [-2.5, -0.35, -0.2, 0.2, 0.35, 2.5]
+    tot = sum(float(O.area_under_curve(edges[i], edges[i + 1], 0.1, 0.15)) for i in range(5))
+    assert abs(tot - 1.0) < 0.06
