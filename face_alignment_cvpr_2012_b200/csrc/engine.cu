@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -105,10 +106,11 @@ struct crf_ctx {
   int gabor_width[5] = {0, 0, 0, 0, 0};
   ComposeTables ct{};
   // work buffers
-  Buf d_imgs[2], d_fd, d_scaled, d_stacks, d_mag, d_minmax, d_hp_leaf, d_ffd_leaf, d_face_roots, d_face_ntrees, d_votes, d_vote_counts, d_seg_counts, d_faces,
+  Buf d_imgs[2], d_fd, d_scaled, d_stacks, d_mag, d_minmax, d_hp_leaf, d_ffd_leaf, d_face_roots, d_face_ntrees, d_votes, d_vote_counts, d_vote_base, d_seg_counts, d_faces,
       d_u8planes, d_counters, d_misc;
   crf_counters_t cnt{};
   bool counting = false;
+  int traverse_variant = 0;  // 0 = pick by stride (see launch_traverse)
   size_t work_budget = (size_t)24 << 30;  // bytes of work buffers a launch may use (min(24 GB, half of the free memory at creation))
   StageTimer timer;
   // geometry of the current launch
@@ -147,6 +149,7 @@ struct Plan {
   int n = 0, Hmax = 0, nplanes = 38;
   int hp_stride = 4, ffd_stride = 3;
   int tree_cap = 20;
+  int vote_factor = 3;   // vote capacity per leaf in the batched path (kParts = worst case)
   bool need_gabor = true, want_u8 = false, need_hp = true, need_ffd = true;
 };
 
@@ -162,7 +165,9 @@ static int ensure(crf_ctx* c, const Plan& p) {
   const size_t np_ffd = (size_t)patches_1d(125, p.ffd_stride) * patches_1d(H, p.ffd_stride);
   c->hp_leaf_fs = np_hp * std::max(c->hp_ntrees, 1);
   c->ffd_leaf_fs = np_ffd * p.tree_cap;
-  c->vote_cap = std::max<size_t>(c->ffd_leaf_fs, 1);
+  // votes per face: worst case is kParts per leaf; the batched path budgets vote_factor per leaf and re-runs the rare
+  // face that exceeds it with the worst-case capacity
+  c->vote_cap = std::max<size_t>(c->ffd_leaf_fs * (size_t)std::min(p.vote_factor, kParts), 16);
   c->u8_fs = (size_t)p.nplanes * 125 * H;
   int rc;
   if ((rc = c->d_scaled.reserve(n * c->scaled_fs))) return rc;
@@ -176,8 +181,9 @@ static int ensure(crf_ctx* c, const Plan& p) {
   if ((rc = c->d_face_ntrees.reserve(n * 4))) return rc;
   if (p.need_ffd) {
     if ((rc = c->d_ffd_leaf.reserve(std::max<size_t>(n * c->ffd_leaf_fs * 4, 16)))) return rc;
-    if ((rc = c->d_votes.reserve(n * kParts * c->vote_cap * sizeof(DevVote)))) return rc;
+    if ((rc = c->d_votes.reserve(n * c->vote_cap * sizeof(DevVote)))) return rc;
     if ((rc = c->d_vote_counts.reserve(n * kParts * 4))) return rc;
+    if ((rc = c->d_vote_base.reserve(n * kParts * 4))) return rc;
     if ((rc = c->d_seg_counts.reserve(n * kVoteSegs * kParts * 4))) return rc;
   }
   if (p.want_u8 && (rc = c->d_u8planes.reserve(n * c->u8_fs))) return rc;
@@ -242,7 +248,8 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   return CRF_OK;
 }
 
-static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool hp, int stride, const int32_t* roots, int ntrees, int smem_trees) {
+static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool hp, int stride, const int32_t* roots, int ntrees, int smem_trees,
+                           bool hp_values = false) {
   const int stage = hp ? CRF_STAGE_HP_TRAVERSE : CRF_STAGE_FFD_TRAVERSE;
   Span s(c, stage);
   TraverseArgs a{};
@@ -252,6 +259,7 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
     a.slots = c->d_hp_slots.as<DevSlot>(); a.roots = roots; a.ntrees = ntrees;
     a.leaf_out = c->d_hp_leaf.as<int32_t>(); a.leaf_face_stride = c->hp_leaf_fs;
     a.cnt_tests = CNT_HP_TESTS; a.cnt_trav = CNT_HP_TRAV;
+    if (hp_values) a.leaf_value = c->d_hp_m.as<float>();
   } else {
     a.slots = c->d_mp_slots.as<DevSlot>();
     a.face_roots = c->d_face_roots.as<int32_t>(); a.face_ntrees = c->d_face_ntrees.as<int32_t>();
@@ -260,12 +268,25 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   }
   a.counters = c->counting ? c->d_counters.as<unsigned long long>() : nullptr;
   const int nx = patches_1d(125, stride), ny = patches_1d(Hmax, stride);
-  const int tiles = ((nx + 31) / 32) * ny;
-  if (tiles <= 0) return CRF_OK;
+  if (nx <= 0 || ny <= 0) return CRF_OK;
   const size_t smem = (size_t)32 * smem_trees * 4;
-  constexpr int NW = 5;
-  if (c->counting) k_traverse<NW, true><<<dim3(tiles, n), NW * 32, smem, c->stream>>>(a);
-  else k_traverse<NW, false><<<dim3(tiles, n), NW * 32, smem, c->stream>>>(a);
+  // variant = LW (32 or 8) | MODE << 8 | NW (5 or 10) << 16; CRF_TRAVERSE_VARIANT overrides for experiments
+  const int variant = c->traverse_variant ? c->traverse_variant : ((stride >= 3 ? 8 : 32) | (2 << 8) | (10 << 16));
+  const int LW = variant & 0xff, MODE = (variant >> 8) & 0xff, NW = (variant >> 16) & 0xff;
+  const int tiles = LW == 32 ? ((nx + 31) / 32) * ny : ((nx + 7) / 8) * ((ny + 3) / 4);
+  const dim3 grid(tiles, n);
+#define CRF_TRAV(NW_, LW_, MODE_)                                                                          \
+  if (NW == NW_ && LW == LW_ && MODE == MODE_) {                                                           \
+    if (c->counting) k_traverse<NW_, true, LW_, MODE_><<<grid, NW_ * 32, smem, c->stream>>>(a);            \
+    else k_traverse<NW_, false, LW_, MODE_><<<grid, NW_ * 32, smem, c->stream>>>(a);                       \
+    launched = true;                                                                                       \
+  }
+  bool launched = false;
+  CRF_TRAV(5, 32, 0) CRF_TRAV(5, 32, 1) CRF_TRAV(5, 32, 2) CRF_TRAV(5, 32, 3)
+  CRF_TRAV(5, 8, 0) CRF_TRAV(5, 8, 1) CRF_TRAV(5, 8, 2) CRF_TRAV(5, 8, 3)
+  CRF_TRAV(10, 32, 0) CRF_TRAV(10, 32, 2) CRF_TRAV(10, 8, 2) CRF_TRAV(10, 8, 3)
+#undef CRF_TRAV
+  if (!launched) return fail(CRF_ERR_ARG, "unknown CRF_TRAVERSE_VARIANT");
   KCHECK(); count_launch(c, stage);
   return CRF_OK;
 }
@@ -274,7 +295,7 @@ static int launch_hp_reduce(crf_ctx* c, const FaceDesc* fd, int n, int stride, b
   Span s(c, CRF_STAGE_HP_REDUCE);
   ComposeTables ct = c->ct;
   ct.list_cap = list_cap;
-  k_hp_reduce_compose<<<(n + kFoldChains - 1) / kFoldChains, kFoldThreads, 0, c->stream>>>(fd, n, c->d_hp_leaf.as<int32_t>(), c->hp_leaf_fs, c->hp_ntrees, stride, c->d_hp_m.as<float>(), ct,
+  k_hp_reduce_compose<<<(n + kFoldChains - 1) / kFoldChains, kFoldThreads, kHpSmem, c->stream>>>(fd, n, c->d_hp_leaf.as<float>(), c->hp_leaf_fs, c->hp_ntrees, stride, ct,
                                                           compose ? 1 : 0, faces, c->d_face_roots.as<int32_t>(), c->d_face_ntrees.as<int32_t>());
   KCHECK(); count_launch(c, CRF_STAGE_HP_REDUCE);
   return CRF_OK;
@@ -284,7 +305,7 @@ static int launch_meanshift(crf_ctx* c, const FaceDesc* fd, int nchains, crf_fac
   Span s(c, CRF_STAGE_MEANSHIFT);
   MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
   k_meanshift<<<(nchains + kFoldChains - 1) / kFoldChains, kFoldThreads, kMsSmem, c->stream>>>(fd, nchains, c->d_votes.as<DevVote>(), c->vote_cap,
-                                                                                       c->d_vote_counts.as<int32_t>(), mo, faces,
+                                                                                       c->d_vote_counts.as<int32_t>(), c->d_vote_base.as<int32_t>(), mo, faces,
                                                                                        c->counting ? c->d_counters.as<unsigned long long>() : nullptr);
   KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
   return CRF_OK;
@@ -296,12 +317,14 @@ static int launch_votes_meanshift(crf_ctx* c, const FaceDesc* fd, int n, int str
     VoteArgs a{};
     a.fd = fd; a.leaf_ids = c->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->ffd_leaf_fs; a.face_ntrees = c->d_face_ntrees.as<int32_t>(); a.stride = stride;
     a.mp_mask = c->d_mp_mask.as<uint16_t>(); a.mp_leaf = c->d_mp_leaf.as<DevMpLeaf>(); a.votes = c->d_votes.as<DevVote>(); a.vote_cap = c->vote_cap;
-    a.seg_counts = c->d_seg_counts.as<int32_t>(); a.vote_counts = c->d_vote_counts.as<int32_t>();
+    a.seg_counts = c->d_seg_counts.as<int32_t>(); a.vote_counts = c->d_vote_counts.as<int32_t>(); a.vote_base = c->d_vote_base.as<int32_t>(); a.faces = faces;
     CU(cudaMemsetAsync(a.vote_counts, 0, (size_t)n * kParts * 4, c->stream));
     k_votes_count<<<dim3(kVoteSegs / 8, n), 256, 0, c->stream>>>(a);
     KCHECK();
+    k_votes_offsets<<<(n + 127) / 128, 128, 0, c->stream>>>(a, n);
+    KCHECK();
     k_votes_emit<<<dim3(kVoteSegs / 8, n), 256, 0, c->stream>>>(a);
-    KCHECK(); count_launch(c, CRF_STAGE_VOTES, 2);
+    KCHECK(); count_launch(c, CRF_STAGE_VOTES, 3);
   }
   return launch_meanshift(c, fd, n * kParts, faces);
 }
@@ -313,7 +336,7 @@ static int run_faces(crf_ctx* c, const FaceDesc* d_fd, int n, int Hmax, const ui
   if ((rc = launch_resize(c, d_fd, n, Hmax, d_imgs))) return rc;
   if (imgs_consumed) CU(cudaEventRecord(imgs_consumed, c->stream));
   if ((rc = launch_channels(c, d_fd, n, Hmax, false, false))) return rc;
-  if ((rc = launch_traverse(c, d_fd, n, Hmax, true, c->opt.hp_stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees))) return rc;
+  if ((rc = launch_traverse(c, d_fd, n, Hmax, true, c->opt.hp_stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees, true))) return rc;
   if ((rc = launch_hp_reduce(c, d_fd, n, c->opt.hp_stride, !headpose_only, tree_cap, d_faces))) return rc;
   if (headpose_only) return CRF_OK;
   if ((rc = launch_traverse(c, d_fd, n, Hmax, false, c->opt.ffd_stride, nullptr, 0, tree_cap))) return rc;
@@ -328,10 +351,10 @@ static int pick_chunk(const crf_ctx* c, int Hmax, bool headpose_only) {
   const size_t np_hp = (size_t)patches_1d(125, c->opt.hp_stride) * patches_1d(Hmax, c->opt.hp_stride);
   const size_t np_ffd = headpose_only ? 0 : (size_t)patches_1d(125, c->opt.ffd_stride) * patches_1d(Hmax, c->opt.ffd_stride);
   const size_t per_face = (size_t)Hmax * 128 + (size_t)(Hmax + 1) * kRowStride * 4 * 38 + (size_t)Hmax * 128 * 4 * 35 + np_hp * c->hp_ntrees * 4 +
-                          np_ffd * c->mp_ntrees_cfg * (4 + kParts * sizeof(DevVote)) + 4096;
+                          np_ffd * c->mp_ntrees_cfg * (4 + 3 * sizeof(DevVote)) + 4096;
   const size_t budget = c->work_budget;
   long long chunk = (long long)(budget / per_face);
-  const int cap = c->opt.max_chunk > 0 ? c->opt.max_chunk : 1024;
+  const int cap = c->opt.max_chunk > 0 ? c->opt.max_chunk : 2048;
   return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(chunk, cap), 32768));
 }
 
@@ -353,7 +376,7 @@ static int pull_counters(crf_ctx* c) {
 static int rerun_wide(crf_ctx* c, const FaceDesc* d_fd_all, const std::vector<FaceDesc>& descs, const uint8_t* d_imgs, crf_face_t* d_faces_all,
                       const std::vector<int>& which) {
   for (int i : which) {
-    Plan p; p.n = 1; p.Hmax = descs[i].H; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = kMaxList;
+    Plan p; p.n = 1; p.Hmax = descs[i].H; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = kMaxList; p.vote_factor = kParts;
     int rc = ensure(c, p);
     if (rc) return rc;
     if ((rc = run_faces(c, d_fd_all + i, 1, p.Hmax, d_imgs, d_faces_all + i, false, kMaxList, nullptr))) return rc;
@@ -443,7 +466,7 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
       CU(cudaStreamSynchronize(c->stream));
       c->cnt.d2h_bytes += tmp.size() * sizeof(crf_face_t);
       std::vector<int> wide;
-      for (size_t i = 0; i < tmp.size(); i++) if (tmp[i].flags & 2) wide.push_back(ch.f0 + (int)i);
+      for (size_t i = 0; i < tmp.size(); i++) if (tmp[i].flags & 6) wide.push_back(ch.f0 + (int)i);
       if (!wide.empty()) {
         if ((rc = rerun_wide(c, c->d_fd.as<FaceDesc>(), descs, c->d_imgs[b].as<uint8_t>(), c->d_faces.as<crf_face_t>(), wide))) return rc;
         for (int i : wide)
@@ -558,7 +581,7 @@ void crf_ctx_destroy(crf_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   Buf* all[] = {&c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
                 &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_scaled, &c->d_stacks, &c->d_mag, &c->d_minmax,
-                &c->d_hp_leaf, &c->d_ffd_leaf, &c->d_face_roots, &c->d_face_ntrees, &c->d_votes, &c->d_vote_counts, &c->d_seg_counts, &c->d_faces, &c->d_u8planes, &c->d_counters,
+                &c->d_hp_leaf, &c->d_ffd_leaf, &c->d_face_roots, &c->d_face_ntrees, &c->d_votes, &c->d_vote_counts, &c->d_vote_base, &c->d_seg_counts, &c->d_faces, &c->d_u8planes, &c->d_counters,
                 &c->d_misc};
   for (Buf* b : all) b->release();
   c->timer.destroy();
@@ -581,6 +604,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   c->device = device;
   if (opt) c->opt = *opt; else crf_options_default(&c->opt);
   if (c->opt.hp_stride < 1 || c->opt.ffd_stride < 1) return fail(CRF_ERR_ARG, "strides must be >= 1");
+  if (const char* v = std::getenv("CRF_TRAVERSE_VARIANT")) c->traverse_variant = (int)std::strtol(v, nullptr, 0);
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) {
@@ -646,6 +670,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->work_budget = std::min(c->work_budget, free_b / 2);
   }
+  CU(cudaFuncSetAttribute(k_hp_reduce_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHpSmem));
   CU(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
   if ((rc = c->d_counters.reserve(sizeof(unsigned long long) * CNT_NUM))) return rc;
   CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * CNT_NUM, c->stream));
@@ -745,7 +770,7 @@ int crf_analyze_crops_device(crf_ctx* c, const uint8_t* d_bgr_batch, int n, int 
     CU(cudaMemcpyAsync(tmp.data(), d_out, (size_t)n * sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     std::vector<int> wide;
-    for (int i = 0; i < n; i++) if (tmp[(size_t)i].flags & 2) wide.push_back(i);
+    for (int i = 0; i < n; i++) if (tmp[(size_t)i].flags & 6) wide.push_back(i);
     if (!wide.empty() && (rc = rerun_wide(c, c->d_fd.as<FaceDesc>(), descs, d_bgr_batch, d_out, wide))) return rc;
   }
   CU(cudaStreamSynchronize(c->stream));
@@ -782,6 +807,7 @@ static int stage_upload_scaled(crf_ctx* c, const uint8_t* scaled, int W, int H, 
   FaceDesc d{};
   d.W = W; d.H = H; d.bw = W; d.bh = H; d.scale = 125.f / W; d.scale_x = d.scale_y = 1.0;
   Plan p; p.n = 1; p.Hmax = H; p.nplanes = nplanes; p.need_gabor = gabor; p.want_u8 = want_u8; p.need_hp = hp; p.need_ffd = ffd; p.tree_cap = tree_cap;
+  p.vote_factor = kParts;
   p.hp_stride = hp_stride; p.ffd_stride = ffd_stride;
   int rc;
   if ((rc = ensure(c, p)) || (rc = c->d_fd.reserve(sizeof d))) return rc;
@@ -913,7 +939,7 @@ int crf_stage_headpose(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int H
   if (rc) return rc;
   if ((rc = c->d_faces.reserve(sizeof(crf_face_t)))) return rc;
   CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->stream));
-  if ((rc = launch_traverse(c, c->d_fd.as<FaceDesc>(), 1, H, true, stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees))) return rc;
+  if ((rc = launch_traverse(c, c->d_fd.as<FaceDesc>(), 1, H, true, stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees, true))) return rc;
   if ((rc = launch_hp_reduce(c, c->d_fd.as<FaceDesc>(), 1, stride, true, kMaxList, c->d_faces.as<crf_face_t>()))) return rc;
   rc = stage_fetch_compose(c, headpose, variance, tree_counts, dominant, tree_forest, tree_index, ntrees, flags);
   c->timer.collect();
@@ -951,7 +977,9 @@ int crf_stage_votes_meanshift(crf_ctx* c, const int* tree_forest, const int* tre
   if ((rc = launch_votes_meanshift(c, c->d_fd.as<FaceDesc>(), 1, stride, c->d_faces.as<crf_face_t>()))) return rc;
   (void)saved;
   crf_face_t face;
+  int32_t vbase[kParts];
   CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(vbase, c->d_vote_base.p, sizeof vbase, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   for (int p = 0; p < kParts; p++) {
     if (n_votes) n_votes[p] = face.n_votes[p];
@@ -961,7 +989,7 @@ int crf_stage_votes_meanshift(crf_ctx* c, const int* tree_forest, const int* tre
     if (votes_xyw && vote_cap > 0) {
       const int n = std::min(face.n_votes[p], vote_cap);
       std::vector<DevVote> v((size_t)n);
-      if (n) CU(cudaMemcpy(v.data(), c->d_votes.as<DevVote>() + (size_t)p * c->vote_cap, (size_t)n * sizeof(DevVote), cudaMemcpyDeviceToHost));
+      if (n) CU(cudaMemcpy(v.data(), c->d_votes.as<DevVote>() + vbase[p], (size_t)n * sizeof(DevVote), cudaMemcpyDeviceToHost));
       for (int k = 0; k < n; k++) {
         float* o = votes_xyw + ((size_t)p * vote_cap + k) * 3;
         o[0] = v[k].x; o[1] = v[k].y; o[2] = v[k].w;
@@ -986,6 +1014,8 @@ int crf_stage_meanshift(crf_ctx* c, const float* votes_xyw, int n, float mean_xy
   d.scale = 1.f;
   CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->stream));
   if (n) CU(cudaMemcpyAsync(c->d_votes.p, v.data(), (size_t)n * sizeof(DevVote), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = c->d_vote_base.reserve(kParts * 4))) return rc;
+  CU(cudaMemsetAsync(c->d_vote_base.p, 0, kParts * 4, c->stream));
   CU(cudaMemcpyAsync(c->d_vote_counts.p, &n, 4, cudaMemcpyHostToDevice, c->stream));
   c->vote_cap = (size_t)std::max(n, 1);
   if ((rc = launch_meanshift(c, c->d_fd.as<FaceDesc>(), 1, c->d_faces.as<crf_face_t>()))) return rc;

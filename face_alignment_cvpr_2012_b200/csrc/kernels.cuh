@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(128) k_integral_from_u8(const uint8_t* __restr
 // ---------------------------------------------------------------------------------------------
 // a6, first half: the 35 complex Gabor responses (include/FeatureChannelFactory.hpp:253-270).
 // cv::filter2D = correlation, anchor centre, REFLECT_101, u8 -> f32; canonical accumulation =
-// raster order over the kernel, product and sum rounded separately.  Then
+// raster order over the kernel; product and sum rounded separately for the 7x7 kernels (bit-identical to cv2),
+// one fused multiply-add per tap for the larger ones (where cv2 itself switches to a DFT path).  Then
 // magnitude = sqrt(im*im + re*re).  One CTA = one 16-row band of one (face, orientation) at scale
 // NU (kernel size K); each thread owns 1 x 4 output strips, the band and its halo live in shared
 // memory as f32, coefficients are broadcast LDS.64.  Per-plane min/max via integer atomics
@@ -184,13 +185,15 @@ struct GaborGeom {
 };
 
 template <int K>
-__global__ void __launch_bounds__(256) k_gabor_mag(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
-                                                   const float2* __restrict__ coef /* this scale: [7][K*K] (re, im) raster order */, int nu,
-                                                   float* __restrict__ mag, size_t mag_face_stride, size_t mag_plane_stride,
-                                                   uint32_t* __restrict__ minmax) {
+__global__ void __launch_bounds__(256, 2) k_gabor_mag(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
+                                                      const float2* __restrict__ coef /* this scale: [7][K*K] (re, im) raster order */, int nu,
+                                                      float* __restrict__ mag, size_t mag_face_stride, size_t mag_plane_stride,
+                                                      uint32_t* __restrict__ minmax) {
   using G = GaborGeom<K>;
+  constexpr int KP = K + 1;            // coefficient row padded to an even tap count: two taps per LDS.128
+  constexpr bool FUSED = K >= 9;       // canonical accumulation (SURVEY A.4 / DESIGN.md): unfused for 7x7 (== cv2), fmaf beyond (cv2 is DFT there)
   __shared__ __align__(16) float tile[G::TH][G::PITCH];
-  __shared__ float2 cf[K * K];
+  __shared__ __align__(16) float2 cf[K][KP];
   const FaceDesc d = fd[blockIdx.z];
   const int W = d.W, H = d.H;
   const int r0 = blockIdx.x * G::BAND;
@@ -198,47 +201,72 @@ __global__ void __launch_bounds__(256) k_gabor_mag(const FaceDesc* __restrict__ 
   const int mu = blockIdx.y, plane = nu * 7 + mu;
   const int tid = threadIdx.x;
   const uint8_t* __restrict__ g = scaled + blockIdx.z * scaled_face_stride;
-  for (int i = tid; i < K * K; i += 256) cf[i] = coef[mu * K * K + i];
+  for (int i = tid; i < K * KP; i += 256) {
+    const int jj = i / KP, ii = i - jj * KP;
+    cf[jj][ii] = ii < K ? coef[mu * K * K + jj * K + ii] : make_float2(0.f, 0.f);
+  }
   for (int i = tid; i < G::TH * G::PITCH; i += 256) {
     const int ty = i / G::PITCH, tx = i - ty * G::PITCH;
     const int sy = border101(r0 + ty - G::R, H), sx = border101(tx - G::R, W);
     tile[ty][tx] = (float)g[(size_t)sy * 128 + sx];
   }
   __syncthreads();
+  // each thread: two 1 x 4 strips, rows rA and rA + 8 of the band, sharing every coefficient load
   const int x0 = (tid & 31) * 4;
-  float vmin = __int_as_float(0x7f800000), vmax = 0.f;
-  float* mplane = mag + blockIdx.z * mag_face_stride + (size_t)plane * mag_plane_stride;
+  const int rA = tid >> 5;
+  float re[2][4], im[2][4];
+#pragma unroll
+  for (int o = 0; o < 4; o++) { re[0][o] = re[1][o] = 0.f; im[0][o] = im[1][o] = 0.f; }
 #pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    const int r = (tid >> 5) + 8 * pass;
-    float re[4] = {0.f, 0.f, 0.f, 0.f}, im[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int j = 0; j < K; j++) {
-      float px[4 * G::NF4];
-      const float4* row = reinterpret_cast<const float4*>(&tile[r + j][x0]);
+  for (int j = 0; j < K; j++) {
+    float px[2][4 * G::NF4];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float4* row = reinterpret_cast<const float4*>(&tile[rA + 8 * h + j][x0]);
 #pragma unroll
       for (int q = 0; q < G::NF4; q++) {
         const float4 v = row[q];
-        px[4 * q] = v.x; px[4 * q + 1] = v.y; px[4 * q + 2] = v.z; px[4 * q + 3] = v.w;
+        px[h][4 * q] = v.x; px[h][4 * q + 1] = v.y; px[h][4 * q + 2] = v.z; px[h][4 * q + 3] = v.w;
       }
+    }
+    const float4* crow = reinterpret_cast<const float4*>(&cf[j][0]);
 #pragma unroll
-      for (int i = 0; i < K; i++) {
-        const float2 c = cf[j * K + i];
+    for (int i2 = 0; i2 < KP / 2; i2++) {
+      const float4 c2 = crow[i2];
 #pragma unroll
-        for (int o = 0; o < 4; o++) {
-          re[o] = __fadd_rn(re[o], __fmul_rn(px[o + i], c.x));
-          im[o] = __fadd_rn(im[o], __fmul_rn(px[o + i], c.y));
+      for (int e = 0; e < 2; e++) {
+        const int i = 2 * i2 + e;
+        if (i < K) {
+          const float cr = e ? c2.z : c2.x, ci = e ? c2.w : c2.y;
+#pragma unroll
+          for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+              if (FUSED) {
+                re[h][o] = __fmaf_rn(px[h][o + i], cr, re[h][o]);
+                im[h][o] = __fmaf_rn(px[h][o + i], ci, im[h][o]);
+              } else {
+                re[h][o] = __fadd_rn(re[h][o], __fmul_rn(px[h][o + i], cr));
+                im[h][o] = __fadd_rn(im[h][o], __fmul_rn(px[h][o + i], ci));
+              }
+            }
         }
       }
     }
-    if (r0 + r < H) {
+  }
+  float vmin = __int_as_float(0x7f800000), vmax = 0.f;
+  float* mplane = mag + blockIdx.z * mag_face_stride + (size_t)plane * mag_plane_stride;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int r = r0 + rA + 8 * h;
+    if (r < H) {
       float m[4];
 #pragma unroll
       for (int o = 0; o < 4; o++) {
-        m[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[o], im[o]), __fmul_rn(re[o], re[o])));
+        m[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[h][o], im[h][o]), __fmul_rn(re[h][o], re[h][o])));
         if (x0 + o < W) { vmin = fminf(vmin, m[o]); vmax = fmaxf(vmax, m[o]); }
       }
-      *reinterpret_cast<float4*>(&mplane[(size_t)(r0 + r) * 128 + x0]) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(&mplane[(size_t)r * 128 + x0]) = make_float4(m[0], m[1], m[2], m[3]);
     }
   }
   uint32_t umin = __float_as_uint(vmin), umax = __float_as_uint(vmax);
@@ -304,42 +332,60 @@ struct TraverseArgs {
   int stride;
   int32_t* leaf_out;
   size_t leaf_face_stride;
+  const float* leaf_value;       // if set, write bits(leaf_value[leaf]) instead of the leaf index (head-pose path: expected label per leaf)
   unsigned long long* counters;  // nullptr = no counting
   int cnt_tests, cnt_trav;
 };
 
-template <int NW, bool COUNT>
+__device__ __forceinline__ uint32_t ldg_corner(const uint32_t* p, bool no_alloc) {
+  uint32_t v;
+  if (no_alloc) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  else v = __ldg(p);
+  return v;
+}
+
+// LW = lanes along x (32: one row of 32 x-adjacent patches; 8: an 8 x 4 block of patches).
+// MODE bit 0: corner loads bypass L1 allocation; bit 1: one 256-bit load per node record instead of two 128-bit.
+template <int NW, bool COUNT, int LW, int MODE>
 __global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
   extern __shared__ int32_t s_leaf[];  // [32][nt]
+  constexpr int LH = 32 / LW;
   const int f = blockIdx.y;
   const FaceDesc d = a.fd[f];
   const int nx = (d.W - kPatch + a.stride - 1) / a.stride, ny = (d.H - kPatch + a.stride - 1) / a.stride;
-  const int nxb = (nx + 31) >> 5;
+  const int nxb = (nx + LW - 1) / LW, nyb = (ny + LH - 1) / LH;
   const int tile = blockIdx.x;
-  if (nx <= 0 || ny <= 0 || tile >= nxb * ny) return;
-  const int iy = tile / nxb, ixb = tile - iy * nxb;
+  if (nx <= 0 || ny <= 0 || tile >= nxb * nyb) return;
+  const int iyb = tile / nxb, ixb = tile - iyb * nxb;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ix = ixb * 32 + lane;
-  const bool active = ix < nx;
+  const int ix = ixb * LW + (lane % LW), iy = iyb * LH + (lane / LW);
+  const bool active = ix < nx && iy < ny;
   const int nt = a.face_ntrees ? a.face_ntrees[f] : a.ntrees;
   const int32_t* roots = a.face_roots ? a.face_roots + (size_t)f * kMaxList : a.roots;
-  const uint32_t* __restrict__ origin = a.stacks + f * a.stack_face_stride + (size_t)(iy * a.stride) * kRowStride + (active ? ix : 0) * a.stride;
+  const uint32_t* __restrict__ origin = a.stacks + f * a.stack_face_stride + (size_t)((active ? iy : 0) * a.stride) * kRowStride + (active ? ix : 0) * a.stride;
   const DevSlot* __restrict__ slots = a.slots;
+  constexpr bool NA = (MODE & 1) != 0;
   unsigned tests = 0;
   for (int t = warp; t < nt; t += NW) {
     int cur = roots[t];
     int leaf = -1;
     if (active) {
       for (;;) {
-        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(slots + cur));
-        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(slots + cur) + 1);
+        uint4 q0, q1;
+        if (MODE & 2) {
+          asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(slots + cur));
+        } else {
+          q0 = __ldg(reinterpret_cast<const uint4*>(slots + cur));
+          q1 = __ldg(reinterpret_cast<const uint4*>(slots + cur) + 1);
+        }
         // q0.x = a1 | c1<<16 ; q0.y = a2 | c2<<16 ; q0.z = w1 | w2<<8 | ch<<16 | leaf<<24 ; q0.w = thr (low 16)
         // q1.x = m1 ; q1.y = m2 ; q1.z = child
-        if (q0.z >> 24) { leaf = (int)q1.z; break; }
+        if (q0.z >> 24) { leaf = a.leaf_value ? __float_as_int(__ldg(a.leaf_value + q1.z)) : (int)q1.z; break; }
         const uint32_t* __restrict__ p = origin + (size_t)((q0.z >> 16) & 0xff) * a.plane_stride;
         const uint32_t a1 = q0.x & 0xffff, c1 = q0.x >> 16, a2 = q0.y & 0xffff, c2 = q0.y >> 16, w1 = q0.z & 0xff, w2 = (q0.z >> 8) & 0xff;
-        const uint32_t A1 = __ldg(p + a1), B1 = __ldg(p + a1 + w1), C1 = __ldg(p + a1 + c1), D1 = __ldg(p + a1 + c1 + w1);
-        const uint32_t A2 = __ldg(p + a2), B2 = __ldg(p + a2 + w2), C2 = __ldg(p + a2 + c2), D2 = __ldg(p + a2 + c2 + w2);
+        const uint32_t A1 = ldg_corner(p + a1, NA), B1 = ldg_corner(p + a1 + w1, NA), C1 = ldg_corner(p + a1 + c1, NA), D1 = ldg_corner(p + a1 + c1 + w1, NA);
+        const uint32_t A2 = ldg_corner(p + a2, NA), B2 = ldg_corner(p + a2 + w2, NA), C2 = ldg_corner(p + a2 + c2, NA), D2 = ldg_corner(p + a2 + c2 + w2, NA);
         const uint32_t s1 = D1 - B1 - C1 + A1, s2 = D2 - B2 - C2 + A2;
         const int m1 = (int)__umulhi(s1 << 1, q1.x), m2 = (int)__umulhi(s2 << 1, q1.y);
         const int thr = (int)(short)(q0.w & 0xffff);
@@ -350,17 +396,19 @@ __global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
     s_leaf[lane * nt + t] = leaf;
   }
   __syncthreads();
-  // rows of nt contiguous ints per patch
-  const int npatch_tile = min(32, nx - ixb * 32);
+  // rows of nt contiguous ints per patch, written at the reference's index (x outer, y inner)
   int32_t* out = a.leaf_out + f * a.leaf_face_stride;
-  for (int i = threadIdx.x; i < npatch_tile * nt; i += NW * 32) {
+  int n_active = 0;
+  for (int i = threadIdx.x; i < 32 * nt; i += NW * 32) {
     const int l = i / nt, t = i - l * nt;
-    out[((size_t)(ixb * 32 + l) * ny + iy) * nt + t] = s_leaf[i];
+    const int lx = ixb * LW + (l % LW), ly = iyb * LH + (l / LW);
+    if (lx < nx && ly < ny) out[((size_t)lx * ny + ly) * nt + t] = s_leaf[i];
   }
   if (COUNT) {
     tests = __reduce_add_sync(0xffffffffu, tests);
     if (lane == 0 && tests) atomicAdd(&a.counters[a.cnt_tests], (unsigned long long)tests);
-    if (threadIdx.x == 0) atomicAdd(&a.counters[a.cnt_trav], (unsigned long long)npatch_tile * nt);
+    n_active = __popc(__ballot_sync(0xffffffffu, active));
+    if (threadIdx.x == 0) atomicAdd(&a.counters[a.cnt_trav], (unsigned long long)n_active * nt);
   }
 }
 
@@ -439,12 +487,15 @@ __device__ __forceinline__ void compose_face(float headpose, float variance, con
 constexpr int kFoldChains = 32;
 constexpr int kFoldThreads = 288;  // warp 0 folds, warps 1..8 produce (4 chains each)
 
-constexpr int kHpTile = 128;
+constexpr int kHpTile = 256;
+constexpr size_t kHpSmem = (size_t)2 * kHpTile * 33 * sizeof(float);  // dynamic shared memory of k_hp_reduce_compose
 
-__global__ void __launch_bounds__(kFoldThreads) k_hp_reduce_compose(const FaceDesc* __restrict__ fd, int nfaces, const int32_t* __restrict__ leaf_ids, size_t leaf_face_stride,
-                                                                    int ntrees, int stride, const float* __restrict__ hp_m, ComposeTables ct, int do_compose,
+__global__ void __launch_bounds__(kFoldThreads) k_hp_reduce_compose(const FaceDesc* __restrict__ fd, int nfaces, const float* __restrict__ leaf_m, size_t leaf_face_stride,
+                                                                    int ntrees, int stride, ComposeTables ct, int do_compose,
                                                                     crf_face_t* __restrict__ faces, int32_t* __restrict__ face_roots, int32_t* __restrict__ face_ntrees) {
-  __shared__ float s_m[2][kHpTile][33];
+  extern __shared__ __align__(16) float s_hp_dyn[];
+  typedef float HpTile[kHpTile][33];
+  HpTile* s_m = reinterpret_cast<HpTile*>(s_hp_dyn);  // [2]
   __shared__ int s_n[kFoldChains];
   __shared__ float s_mean[kFoldChains], s_var[kFoldChains];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -470,15 +521,15 @@ __global__ void __launch_bounds__(kFoldThreads) k_hp_reduce_compose(const FaceDe
       const int j = (warp - 1) * 4 + jj;
       const int n = s_n[j];
       if (tile * kHpTile >= n) continue;
-      const int32_t* __restrict__ ids = leaf_ids + (size_t)(f0 + j) * leaf_face_stride;
-      int32_t id[kHpTile / 32];
+      const float* __restrict__ ms = leaf_m + (size_t)(f0 + j) * leaf_face_stride;
+      float v[kHpTile / 32];
 #pragma unroll
       for (int h = 0; h < kHpTile / 32; h++) {
         const int k = tile * kHpTile + h * 32 + lane;
-        id[h] = k < n ? ids[k] : -1;
+        v[h] = k < n ? ms[k] : -1.f;
       }
 #pragma unroll
-      for (int h = 0; h < kHpTile / 32; h++) buf[h * 32 + lane][j] = id[h] >= 0 ? __ldg(hp_m + id[h]) : -1.f;
+      for (int h = 0; h < kHpTile / 32; h++) buf[h * 32 + lane][j] = v[h];
     }
   };
   float cnt = 0, sum = 0, sum_sq = 0;
@@ -534,7 +585,9 @@ __global__ void k_compose_only(float headpose, float variance, ComposeTables ct,
 // a12 (emission): ordered vote lists (src/face_utils.cpp:277-301).  Votes of part i keep
 // the reference's order (leaf index = patch-major, tree-minor) because MeanShift sums them in f32.
 // One CTA per face walks the leaves in chunks of 256 and compacts per part with warp ballots.
-// votes: [face][part][vote_cap] {x, y, weight}.
+// votes: [face][face_vote_cap] {x, y, weight}; the list of part p starts at vote_base[face][p] (exclusive scan of the
+// per-part counts).  face_vote_cap is a budget (a few votes per leaf); a face that exceeds it is flagged (bit 2)
+// and re-run by the engine with the worst-case capacity.
 // ---------------------------------------------------------------------------------------------
 struct __align__(8) DevVote { short x, y; float w; };
 
@@ -548,9 +601,11 @@ struct VoteArgs {
   const int32_t* leaf_ids; size_t leaf_face_stride;
   const int32_t* face_ntrees; int stride;
   const uint16_t* mp_mask; const DevMpLeaf* mp_leaf;
-  DevVote* votes; size_t vote_cap;
+  DevVote* votes; size_t vote_cap;   // votes per face
   int32_t* seg_counts;   // [face][kVoteSegs][kParts]
   int32_t* vote_counts;  // [face][kParts] (zeroed before pass 1)
+  int32_t* vote_base;    // [face][kParts] start of each part's list inside the face's region
+  crf_face_t* faces;
 };
 
 __device__ __forceinline__ void vote_segment(const VoteArgs& a, int f, int seg, int& n, int& k0, int& k1, int& nt, int& ny) {
@@ -585,11 +640,23 @@ __global__ void __launch_bounds__(256) k_votes_count(VoteArgs a) {
   }
 }
 
+// One thread per face: exclusive scan of the 10 per-part counts; capacity check.
+__global__ void k_votes_offsets(VoteArgs a, int nfaces) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nfaces) return;
+  long long run = 0;
+  for (int p = 0; p < kParts; p++) { a.vote_base[f * kParts + p] = (int32_t)run; run += a.vote_counts[f * kParts + p]; }
+  if (run > (long long)a.vote_cap) {   // over budget: emit nothing, flag the face for the wide re-run
+    for (int p = 0; p < kParts; p++) { a.vote_base[f * kParts + p] = 0; a.vote_counts[f * kParts + p] = -1; }
+    a.faces[f].flags |= 4;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
   const int f = blockIdx.y, lane = threadIdx.x & 31, seg = blockIdx.x * 8 + (threadIdx.x >> 5);
   int n, k0, k1, nt, ny;
   vote_segment(a, f, seg, n, k0, k1, nt, ny);
-  if (k0 >= k1) return;
+  if (k0 >= k1 || a.vote_counts[f * kParts] < 0) return;
   // base of this segment for every part: sum over the earlier segments (lanes stride over them)
   int base[kParts];
   const int32_t* sc = a.seg_counts + (size_t)f * kVoteSegs * kParts;
@@ -597,10 +664,10 @@ __global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
   for (int p = 0; p < kParts; p++) {
     int v = 0;
     for (int s = lane; s < seg; s += 32) v += sc[s * kParts + p];
-    base[p] = __reduce_add_sync(0xffffffffu, v);
+    base[p] = __reduce_add_sync(0xffffffffu, v) + a.vote_base[f * kParts + p];
   }
   const int32_t* __restrict__ ids = a.leaf_ids + f * a.leaf_face_stride;
-  DevVote* __restrict__ fv = a.votes + (size_t)f * kParts * a.vote_cap;
+  DevVote* __restrict__ fv = a.votes + (size_t)f * a.vote_cap;
   for (int k = k0 + lane; k - lane < k1; k += 32) {
     int leaf = 0;
     unsigned mask = 0;
@@ -620,7 +687,7 @@ __global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
           v.x = (short)(L.off[p][0] + cx);
           v.y = (short)(L.off[p][1] + cy);
           v.w = L.weight;
-          fv[(size_t)p * a.vote_cap + base[p] + __popc(bal[p] & ((1u << lane) - 1u))] = v;
+          fv[base[p] + __popc(bal[p] & ((1u << lane) - 1u))] = v;
         }
       }
     }
@@ -678,8 +745,8 @@ __device__ __forceinline__ void vote_terms(const DevVote q, bool first_pass, flo
 constexpr int kMsTile = 64;
 constexpr size_t kMsSmem = (size_t)2 * 3 * kMsTile * 33 * sizeof(float);  // dynamic shared memory of k_meanshift
 
-__global__ void __launch_bounds__(kFoldThreads) k_meanshift(const FaceDesc* __restrict__ fd, int nchains, const DevVote* __restrict__ votes, size_t vote_cap,
-                                                            const int32_t* __restrict__ vote_counts, MeanShiftOpt o, crf_face_t* __restrict__ faces,
+__global__ void __launch_bounds__(kFoldThreads, 3) k_meanshift(const FaceDesc* __restrict__ fd, int nchains, const DevVote* __restrict__ votes, size_t vote_cap,
+                                                               const int32_t* __restrict__ vote_counts, const int32_t* __restrict__ vote_base, MeanShiftOpt o, crf_face_t* __restrict__ faces,
                                                             unsigned long long* counters) {
   extern __shared__ __align__(16) float s_dyn[];
   typedef float Tile[kMsTile][33];
@@ -687,6 +754,7 @@ __global__ void __launch_bounds__(kFoldThreads) k_meanshift(const FaceDesc* __re
   Tile* s_x = s_w + 2;
   Tile* s_y = s_w + 4;
   __shared__ int s_n[kFoldChains], s_active[kFoldChains];
+  __shared__ const DevVote* s_list[kFoldChains];
   __shared__ float s_mx[kFoldChains], s_my[kFoldChains];
   __shared__ unsigned long long s_tab[32];
   __shared__ int s_maxn;
@@ -694,8 +762,10 @@ __global__ void __launch_bounds__(kFoldThreads) k_meanshift(const FaceDesc* __re
   const int c0 = blockIdx.x * kFoldChains;
   if (threadIdx.x < kFoldChains) {
     const int c = c0 + threadIdx.x;
-    s_n[threadIdx.x] = c < nchains ? vote_counts[c] : 0;
-    s_active[threadIdx.x] = c < nchains;
+    const int cnt = c < nchains ? vote_counts[c] : 0;
+    s_n[threadIdx.x] = max(cnt, 0);
+    s_active[threadIdx.x] = c < nchains && cnt >= 0;   // cnt < 0: face over the vote budget, left to the wide re-run
+    s_list[threadIdx.x] = c < nchains ? votes + (size_t)(c / kParts) * vote_cap + vote_base[c] : votes;
     s_mx[threadIdx.x] = 0.f; s_my[threadIdx.x] = 0.f;
     s_tab[threadIdx.x] = c_expf.tab[threadIdx.x];
   }
@@ -725,7 +795,7 @@ __global__ void __launch_bounds__(kFoldThreads) k_meanshift(const FaceDesc* __re
         for (int h = 0; h < kMsTile / 32; h++) {
           const int k = tile * kMsTile + h * 32 + lane;
           ok[jj][h] = k < n;
-          if (ok[jj][h]) q[jj][h] = votes[(size_t)(c0 + j) * vote_cap + k];
+          if (ok[jj][h]) q[jj][h] = s_list[j][k];
         }
       }
 #pragma unroll

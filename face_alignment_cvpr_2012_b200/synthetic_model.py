@@ -19,8 +19,9 @@ def _fmt(v: float) -> str:
 
 
 class _TreeWriter:
-    def __init__(self, kind: str, max_depth: int, rng: np.random.Generator, channels: int, leaf_prob: float, max_rect: int):
+    def __init__(self, kind: str, max_depth: int, rng: np.random.Generator, channels: int, leaf_prob: float, max_rect: int, always_vote: bool = False):
         self.kind, self.max_depth, self.rng, self.channels, self.leaf_prob, self.max_rect = kind, max_depth, rng, channels, leaf_prob, max_rect
+        self.always_vote = always_vote
         self.tok: list[str] = []
         self.oid = 0
         self.first = dict(node=True, split=True, leaf=True)
@@ -48,7 +49,7 @@ class _TreeWriter:
                 fg = float(np.float32(labels.sum() / n))
                 t += [str(n), _fmt(fg), "5", "0"] + [str(int(v)) for v in labels]
             else:
-                n = int(self.rng.integers(1, 40))
+                n = int(self.rng.integers(3 if self.always_vote else 1, 40))
                 t.append(str(n))
                 if self.first["leaf"]:
                     t += ["0", "0"]  # class info of vector<Point>
@@ -56,9 +57,14 @@ class _TreeWriter:
                 if self.first["leaf"]:
                     t += ["0", "0"]  # class info of Point
                 t += [str(int(v)) for v in self.rng.integers(-60, 61, 20)]
-                t += ["10", "0"] + [_fmt(v) for v in self.rng.uniform(0.5, 45, 10)]
-                t += ["10", "0"] + [_fmt(v) for v in self.rng.uniform(0, 1, 10) ** 2]
-                t.append(_fmt(float(self.rng.choice([0.0, 0.25, 0.5, 0.6, 0.75, 1.0, float(self.rng.uniform(0, 1))]))))
+                if self.always_vote:   # every leaf votes for every part (exercises the vote-budget overflow path)
+                    t += ["10", "0"] + [_fmt(v) for v in self.rng.uniform(0.5, 20, 10)]
+                    t += ["10", "0"] + [_fmt(v) for v in self.rng.uniform(0.5, 1, 10)]
+                    t.append(_fmt(float(self.rng.choice([0.75, 1.0]))))
+                else:
+                    t += ["10", "0"] + [_fmt(v) for v in self.rng.uniform(0.5, 45, 10)]
+                    t += ["10", "0"] + [_fmt(v) for v in self.rng.uniform(0, 1, 10) ** 2]
+                    t.append(_fmt(float(self.rng.choice([0.0, 0.25, 0.5, 0.6, 0.75, 1.0, float(self.rng.uniform(0, 1))]))))
             self.first["leaf"] = False
         else:
             if self.first["split"]:
@@ -75,8 +81,8 @@ class _TreeWriter:
 
 
 def tree_text(kind: str, max_depth: int, rng: np.random.Generator, channels: int = 38, leaf_prob: float = 0.15, max_rect: int = 22,
-              ntrees: int = 15, face_size: int = 125, ratio: str = "0.25", finished: bool = True) -> str:
-    w = _TreeWriter(kind, max_depth, rng, channels, leaf_prob, max_rect)
+              ntrees: int = 15, face_size: int = 125, ratio: str = "0.25", finished: bool = True, always_vote: bool = False) -> str:
+    w = _TreeWriter(kind, max_depth, rng, channels, leaf_prob, max_rect, always_vote)
     w.node(0)
     n_nodes = 2 ** (max_depth + 1) - 1
     path = "data/trees_headpose" if kind == "hp" else "data/trees_ffd"

@@ -455,9 +455,12 @@ static const std::vector<GaborKernel>& gabor_bank() {
 }
 
 // cv::filter2D(src u8 -> CV_32F, kernel), correlation, anchor centre, REFLECT_101.
-// CANONICAL accumulation: raster order over the kernel, skipping exact-zero
-// coefficients, acc = acc + (float)px * k with separately rounded product and sum.  This is
-// bit-identical to cv2 4.13 for the 7x7 kernels; for 9x9+ cv2 takes a DFT path (last-bit noise).
+// CANONICAL accumulation: raster order over the kernel, acc starts at 0.
+// 7x7 kernels: acc = acc + (float)px * k with separately rounded product and sum — bit-identical to
+// cv2 4.13.  9x9 and larger: cv2 (2.4.9 and 4.13 alike) switches to a DFT path that no direct sum can
+// match bit for bit, so the canonical form there is acc = fmaf(px, k, acc) (one rounding per tap, the
+// more accurate direct sum); its distance to cv2 is pinned statistically (+-1 LSB of the u8 plane).
+// Skipping exact-zero coefficients, as cv2 does, cannot change a value (x + 0*px == x).
 static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int kw, PlaneF& dst) {
   const int H = src.rows, W = src.cols, r = kw / 2;
   dst.rows = H; dst.cols = W; dst.d.resize((size_t)H * W);
@@ -484,10 +487,18 @@ static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int 
   for (int y = 0; y < H; y++) {
     std::fill(acc.begin(), acc.end(), 0.f);
     float* __restrict a = acc.data();
-    for (size_t t = 0; t < nt; t++) {
-      const float* __restrict row = &pad[(size_t)y * PW + tap_off[t]];
-      const float k = tap_k[t];
-      for (int x = 0; x < W; x++) a[x] = a[x] + row[x] * k;
+    if (kw >= 9) {   // one fused multiply-add per tap (cv2 takes its DFT path for these sizes: no direct-sum order is "the" reference)
+      for (size_t t = 0; t < nt; t++) {
+        const float* __restrict row = &pad[(size_t)y * PW + tap_off[t]];
+        const float k = tap_k[t];
+        for (int x = 0; x < W; x++) a[x] = std::fmaf(row[x], k, a[x]);
+      }
+    } else {         // 7x7: separately rounded product and sum == cv2's filter2D bit for bit
+      for (size_t t = 0; t < nt; t++) {
+        const float* __restrict row = &pad[(size_t)y * PW + tap_off[t]];
+        const float k = tap_k[t];
+        for (int x = 0; x < W; x++) a[x] = a[x] + row[x] * k;
+      }
     }
     std::memcpy(&dst.d[(size_t)y * W], a, sizeof(float) * (size_t)W);
   }

@@ -221,6 +221,19 @@ def test_analyze_faces_ragged_boxes(O, sctx, synth_models):
     _check_faces(got, want)
 
 
+def test_vote_budget_overflow_is_rerun(crf, O, gpu, tmp_path):
+    """A forest whose every leaf votes for every part needs 10 votes per leaf; the batched path budgets 3 and must
+    re-run such faces with the worst-case capacity, giving the oracle's result all the same."""
+    from face_alignment_cvpr_2012_b200 import synthetic_model as sm, workloads as wl
+    hp, ffd = sm.write_model(tmp_path / "allvote", seed=21, hp_depth=6, ffd_depth=6, always_vote=True)
+    gm, om = crf.Model(hp, ffd, 15, 20), O.Model(hp, ffd, 15, 20)
+    crops, _ = wl.make_crops(5, seed=77)
+    got = crf.Context(gm, 0).analyze_crops(crops)
+    want = np.array([om.analyze_face(c, (0, 0, 100, 100)) for c in crops])
+    assert (want["n_votes"].sum(axis=1) > 3 * 1024 * 20).all()
+    _check_faces(got, want)
+
+
 def test_argument_errors(crf, sctx):
     img = np.zeros((100, 100, 3), np.uint8)
     for box in [(-1, 0, 50, 50), (60, 60, 50, 50), (0, 0, 0, 10), (0, 0, 100, 20), (0, 0, 20, 100)]:  # outside / empty / flatter than a patch / taller than 521
