@@ -51,3 +51,16 @@ def test_product_never_imports_the_oracle():
         if p.suffix in (".py", ".cu", ".cuh", ".cc", ".h") or p.name == "Makefile":
             m = bad.search(p.read_text())
             assert m is None, (p, m.group(0))
+
+
+def test_cpp_compat_header_builds_and_mirrors_error_behaviour(crf, synth_dirs, tmp_path):
+    """include/crf_b200_compat.hpp (the reference-side binding of INTEGRATION.md) compiles with g++ and behaves like
+    the reference's FaceForest when the forests are missing or, here, when there is no GPU."""
+    import subprocess
+    from face_alignment_cvpr_2012_b200 import capi
+    exe = tmp_path / "compat_smoke"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cpp" / "compat_smoke.cc"), "-o", str(exe),
+                    "-L", str(capi.LIB_PATH.parent), "-lcrf_b200", f"-Wl,-rpath,{capi.LIB_PATH.parent}"], check=True)
+    hp, ffd = synth_dirs
+    r = subprocess.run([str(exe), hp, ffd], capture_output=True, text=True)
+    assert r.returncode == 0 and "compat_smoke ok" in r.stdout, r.stdout + r.stderr

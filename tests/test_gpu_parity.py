@@ -355,3 +355,21 @@ def test_face_forest_class_mirror(crf, staged_models, lfw_faces, lfw_golden, gpu
     assert np.array_equal(face.ffd_cordinates, lfw_golden["recs"][k]["ffd"]) and face.bbox == tuple(f["box"])
     faces = ff.analyzeImage(f["img"], [f["box"], f["box"]])
     assert len(faces) == 2 and np.array_equal(faces[1].ffd_cordinates, face.ffd_cordinates)
+
+
+def test_cpp_compat_header_on_gpu(crf, synth_dirs, synth_models, O, gpu, tmp_path):
+    """The C++ binding end to end: reference-shaped FaceForest::analyzeImage through libcrf_b200.so vs the oracle."""
+    import subprocess
+    from face_alignment_cvpr_2012_b200 import capi
+    exe = tmp_path / "compat_smoke"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(capi.LIB_PATH.parents[2] / "include"), str(capi.LIB_PATH.parents[2] / "tests" / "cpp" / "compat_smoke.cc"),
+                    "-o", str(exe), "-L", str(capi.LIB_PATH.parent), "-lcrf_b200", f"-Wl,-rpath,{capi.LIB_PATH.parent}"], check=True)
+    hp, ffd = synth_dirs
+    r = subprocess.run([str(exe), hp, ffd, "run"], capture_output=True, text=True)
+    assert r.returncode == 0 and "compat_smoke ok" in r.stdout, r.stdout + r.stderr
+    _, om = synth_models
+    px = ((np.arange(120 * 160 * 3, dtype=np.uint64) * 2654435761 % (1 << 32)) >> 24).astype(np.uint8).reshape(120, 160, 3)
+    want = [om.analyze_face(px, b) for b in [(10, 5, 100, 100), (40, 10, 90, 105)]]
+    line = [l for l in r.stdout.split("\n") if l.startswith("headpose")][0].split()
+    assert abs(float(line[1]) - float(want[0]["headpose"])) < 1e-5 and abs(float(line[2]) - float(want[1]["headpose"])) < 1e-5
+    assert line[-1] == f"({want[0]['ffd'][0][0]},{want[0]['ffd'][0][1]})"
