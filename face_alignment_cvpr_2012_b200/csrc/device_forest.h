@@ -12,7 +12,15 @@
 
 namespace crf {
 
-constexpr int kRowStride = 128;  // u32 words per integral row (CRF_ROW_STRIDE)
+constexpr int kRowStride = 128;  // elements per integral row (CRF_ROW_STRIDE)
+// Element type of the integral planes.  uint32_t: exact sums, 4 corner loads per rectangle.  uint16_t: sums modulo 2^16
+// with rectangles cut into strips of area <= 257 (see DevSlot) — built, parity-green and MEASURED 1.7x SLOWER on B200
+// (the traversal is bound by L1 wavefronts, i.e. by the number of load instructions x lines, not by bytes: the 16 % of
+// rectangles that need a second strip add loads and a divergent path, and half-width rows save no wavefronts).
+typedef uint32_t stack_t;
+constexpr bool kStack16 = sizeof(stack_t) == 2;
+constexpr int kStripArea = kStack16 ? 257 : (1 << 20);   // 255 * 257 < 2^16; one strip always with 32-bit sums
+constexpr uint32_t kSumMask = kStack16 ? 0xffffu : 0xffffffffu;
 constexpr int kPatch = 31;       // ForestParam::getPatchSize() for face_size 125 (include/Constants.hpp:26-30)
 constexpr int kHalfPatch = 15;   // patch_size / 2 (src/face_utils.cpp:281-282)
 constexpr int kParts = 10;
@@ -21,17 +29,22 @@ constexpr int kMaxList = 128;    // composed-forest capacity per face (pathologi
 // One slot = one tree node.  Children of an internal node are adjacent: left = child, right = child + 1
 // (left is serialised first: include/TreeNode.hpp:161-162).  Slots of a tree are laid out breadth-first
 // so the hot top levels share cache lines.
+// With 16-bit planes (kStack16) a rectangle sum D - B - C + A is exact modulo 2^16, hence exact outright for areas
+// <= 257 (u8 pixels); larger rectangles are cut into `ns` horizontal strips of at most floor(257 / w) rows, each
+// summed exactly.  With the default 32-bit planes ns is always 1.
 struct alignas(32) DevSlot {
-  uint16_t a1, c1;   // rect1: a = y*kRowStride + x (word offset of the top-left corner), c = h*kRowStride
-  uint16_t a2, c2;   // rect2
-  uint8_t w1, w2;    // rect widths
+  uint16_t a1;       // rect1: y*kRowStride + x (element offset of the top-left corner)
+  uint8_t w1, ns1;   // width; number of strips (1..4)
+  uint16_t hs1;      // rows of a full strip * kRowStride
+  uint16_t hl1;      // rows of the last strip * kRowStride
+  uint16_t a2;       // rect2
+  uint8_t w2, ns2;
+  uint16_t hs2, hl2;
   uint8_t ch;        // feature channel == plane index
   uint8_t is_leaf;
   int16_t thr;       // ThresholdSplit::threshold clamped to [-256, 255] (|mean1 - mean2| <= 255)
-  uint16_t pad0;
   uint32_t m1, m2;   // floor(2^31 / area) + 1: mean = umulhi(sum << 1, m) == sum / area for sum <= 255*area
   int32_t child;     // internal: slot of the left child; leaf: forest-global leaf index
-  uint32_t pad1;
 };
 static_assert(sizeof(DevSlot) == 32, "slot must be one 32-byte sector");
 

@@ -96,7 +96,7 @@ using namespace crf;
 
 struct crf_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   crf_options_t opt{};
   int hp_ntrees = 0, mp_ntrees_cfg = 0, num_channels = 38;
@@ -105,16 +105,26 @@ struct crf_ctx {
   Buf d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5];
   int gabor_width[5] = {0, 0, 0, 0, 0};
   ComposeTables ct{};
-  // work buffers
-  Buf d_imgs[2], d_fd, d_scaled, d_stacks, d_mag, d_minmax, d_hp_leaf, d_ffd_leaf, d_face_roots, d_face_ntrees, d_votes, d_vote_counts, d_vote_base, d_seg_counts, d_faces,
-      d_u8planes, d_counters, d_misc;
+  // work buffers: two complete sets, so that consecutive chunks run on two streams and kernels bound by different
+  // units (fp32 issue for the Gabor bank, L1/L2 gathers for the forests, latency for the sequential folds) overlap
+  struct WorkSet {
+    cudaStream_t stream = nullptr;
+    Buf d_scaled, d_stacks, d_mag, d_minmax, d_hp_leaf, d_ffd_leaf, d_face_roots, d_face_ntrees, d_votes, d_vote_counts, d_vote_base, d_seg_counts, d_u8planes, d_int32;
+    size_t scaled_fs = 0, stack_fs = 0, plane_stride = 0, mag_fs = 0, mag_ps = 0, hp_leaf_fs = 0, ffd_leaf_fs = 0, vote_cap = 0, u8_fs = 0;
+    Buf* all[14] = {&d_scaled, &d_stacks, &d_mag, &d_minmax, &d_hp_leaf, &d_ffd_leaf, &d_face_roots, &d_face_ntrees, &d_votes, &d_vote_counts, &d_vote_base,
+                    &d_seg_counts, &d_u8planes, &d_int32};
+  };
+  WorkSet ws[2];
+  WorkSet* w = &ws[0];   // set of the chunk being enqueued
+  Buf d_imgs[2], d_fd, d_faces, d_counters, d_misc;
   crf_counters_t cnt{};
   bool counting = false;
   int traverse_variant = 0;  // 0 = pick by stride (see launch_traverse)
-  size_t work_budget = (size_t)24 << 30;  // bytes of work buffers a launch may use (min(24 GB, half of the free memory at creation))
+  // 1 = consecutive chunks run back to back on one stream (default: measured faster — co-resident Gabor CTAs shrink the L1
+  // the gathers live on, and two chunks' stacks thrash L2); 2 = alternate chunks between two streams / work sets
+  int nstreams = 1;
+  size_t work_budget = (size_t)24 << 30;  // bytes of work buffers the two sets may use together (min(24 GB, half of the free memory at creation))
   StageTimer timer;
-  // geometry of the current launch
-  size_t scaled_fs = 0, stack_fs = 0, plane_stride = 0, mag_fs = 0, mag_ps = 0, hp_leaf_fs = 0, ffd_leaf_fs = 0, vote_cap = 0, u8_fs = 0;
 };
 
 namespace crf {
@@ -122,10 +132,10 @@ namespace crf {
 struct Span {
   crf_ctx* c; int stage; cudaEvent_t a = nullptr;
   Span(crf_ctx* ctx, int st) : c(ctx), stage(st) {
-    if (c->timer.on) { a = c->timer.get(); cudaEventRecord(a, c->stream); }
+    if (c->timer.on) { a = c->timer.get(); cudaEventRecord(a, c->w->stream); }
   }
   ~Span() {
-    if (c->timer.on) { cudaEvent_t b = c->timer.get(); cudaEventRecord(b, c->stream); c->timer.spans.push_back({stage, a, b}); }
+    if (c->timer.on) { cudaEvent_t b = c->timer.get(); cudaEventRecord(b, c->w->stream); c->timer.spans.push_back({stage, a, b}); }
   }
 };
 static inline void count_launch(crf_ctx* c, int stage, int n = 1) { c->cnt.kernel_launches += n; c->timer.launches[stage] += n; }
@@ -156,37 +166,38 @@ struct Plan {
 static int ensure(crf_ctx* c, const Plan& p) {
   const size_t n = (size_t)std::max(p.n, 1);
   const int H = p.Hmax;
-  c->scaled_fs = (size_t)H * 128;
-  c->plane_stride = (size_t)(H + 1) * kRowStride;
-  c->stack_fs = c->plane_stride * p.nplanes;
-  c->mag_ps = (size_t)H * 128;
-  c->mag_fs = c->mag_ps * 35;
+  c->w->scaled_fs = (size_t)H * 128;
+  c->w->plane_stride = (size_t)(H + 1) * kRowStride;
+  c->w->stack_fs = c->w->plane_stride * p.nplanes;
+  c->w->mag_ps = (size_t)H * 128;
+  c->w->mag_fs = c->w->mag_ps * 35;
   const size_t np_hp = (size_t)patches_1d(125, p.hp_stride) * patches_1d(H, p.hp_stride);
   const size_t np_ffd = (size_t)patches_1d(125, p.ffd_stride) * patches_1d(H, p.ffd_stride);
-  c->hp_leaf_fs = np_hp * std::max(c->hp_ntrees, 1);
-  c->ffd_leaf_fs = np_ffd * p.tree_cap;
+  c->w->hp_leaf_fs = np_hp * std::max(c->hp_ntrees, 1);
+  c->w->ffd_leaf_fs = np_ffd * p.tree_cap;
   // votes per face: worst case is kParts per leaf; the batched path budgets vote_factor per leaf and re-runs the rare
   // face that exceeds it with the worst-case capacity
-  c->vote_cap = std::max<size_t>(c->ffd_leaf_fs * (size_t)std::min(p.vote_factor, kParts), 16);
-  c->u8_fs = (size_t)p.nplanes * 125 * H;
+  c->w->vote_cap = std::max<size_t>(c->w->ffd_leaf_fs * (size_t)std::min(p.vote_factor, kParts), 16);
+  c->w->u8_fs = (size_t)p.nplanes * 125 * H;
   int rc;
-  if ((rc = c->d_scaled.reserve(n * c->scaled_fs))) return rc;
-  if ((rc = c->d_stacks.reserve(n * c->stack_fs * 4))) return rc;
+  if ((rc = c->w->d_scaled.reserve(n * c->w->scaled_fs))) return rc;
+  if ((rc = c->w->d_stacks.reserve(n * c->w->stack_fs * sizeof(stack_t)))) return rc;
+  if (p.want_u8 && (rc = c->w->d_int32.reserve(n * c->w->stack_fs * 4))) return rc;
   if (p.need_gabor) {
-    if ((rc = c->d_mag.reserve(n * c->mag_fs * 4))) return rc;
-    if ((rc = c->d_minmax.reserve(n * 35 * 2 * 4))) return rc;
+    if ((rc = c->w->d_mag.reserve(n * c->w->mag_fs * 4))) return rc;
+    if ((rc = c->w->d_minmax.reserve(n * 35 * 2 * 4))) return rc;
   }
-  if (p.need_hp && (rc = c->d_hp_leaf.reserve(std::max<size_t>(n * c->hp_leaf_fs * 4, 16)))) return rc;
-  if ((rc = c->d_face_roots.reserve(n * kMaxList * 4))) return rc;
-  if ((rc = c->d_face_ntrees.reserve(n * 4))) return rc;
+  if (p.need_hp && (rc = c->w->d_hp_leaf.reserve(std::max<size_t>(n * c->w->hp_leaf_fs * 4, 16)))) return rc;
+  if ((rc = c->w->d_face_roots.reserve(n * kMaxList * 4))) return rc;
+  if ((rc = c->w->d_face_ntrees.reserve(n * 4))) return rc;
   if (p.need_ffd) {
-    if ((rc = c->d_ffd_leaf.reserve(std::max<size_t>(n * c->ffd_leaf_fs * 4, 16)))) return rc;
-    if ((rc = c->d_votes.reserve(n * c->vote_cap * sizeof(DevVote)))) return rc;
-    if ((rc = c->d_vote_counts.reserve(n * kParts * 4))) return rc;
-    if ((rc = c->d_vote_base.reserve(n * kParts * 4))) return rc;
-    if ((rc = c->d_seg_counts.reserve(n * kVoteSegs * kParts * 4))) return rc;
+    if ((rc = c->w->d_ffd_leaf.reserve(std::max<size_t>(n * c->w->ffd_leaf_fs * 4, 16)))) return rc;
+    if ((rc = c->w->d_votes.reserve(n * c->w->vote_cap * sizeof(DevVote)))) return rc;
+    if ((rc = c->w->d_vote_counts.reserve(n * kParts * 4))) return rc;
+    if ((rc = c->w->d_vote_base.reserve(n * kParts * 4))) return rc;
+    if ((rc = c->w->d_seg_counts.reserve(n * kVoteSegs * kParts * 4))) return rc;
   }
-  if (p.want_u8 && (rc = c->d_u8planes.reserve(n * c->u8_fs))) return rc;
+  if (p.want_u8 && (rc = c->w->d_u8planes.reserve(n * c->w->u8_fs))) return rc;
   return CRF_OK;
 }
 
@@ -208,42 +219,43 @@ static int make_desc(const crf_ctx* c, int rows, int cols, size_t step, size_t i
   return CRF_OK;
 }
 
-// ---- stage launchers (all on c->stream; fd/faces point at the first face of the launch) ----------
+// ---- stage launchers (all on c->w->stream; fd/faces point at the first face of the launch) ----------
 static int launch_resize(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, const uint8_t* d_imgs) {
   Span s(c, CRF_STAGE_RESIZE);
-  k_gray_resize<<<dim3(Hmax, n), 128, 0, c->stream>>>(fd, d_imgs, c->d_scaled.as<uint8_t>(), c->scaled_fs);
+  k_gray_resize<<<dim3(Hmax, n), 128, 0, c->w->stream>>>(fd, d_imgs, c->w->d_scaled.as<uint8_t>(), c->w->scaled_fs);
   KCHECK(); count_launch(c, CRF_STAGE_RESIZE);
   return CRF_OK;
 }
 
 static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool minmax_planes, bool want_u8) {
-  uint8_t* u8 = want_u8 ? c->d_u8planes.as<uint8_t>() : nullptr;
+  uint8_t* u8 = want_u8 ? c->w->d_u8planes.as<uint8_t>() : nullptr;
+  uint32_t* dbg32 = want_u8 ? c->w->d_int32.as<uint32_t>() : nullptr;   // full 32-bit integrals, stage API only
   {
     Span s(c, CRF_STAGE_PLAIN);
     PlainPlanes pp{};
     int nw;
     if (!minmax_planes) { nw = 3; pp.which[0] = 0; pp.plane[0] = 0; pp.which[1] = 1; pp.plane[1] = 36; pp.which[2] = 2; pp.plane[2] = 37; }
     else { nw = 2; pp.which[0] = 3; pp.plane[0] = 0; pp.which[1] = 4; pp.plane[1] = 1; }
-    k_plain_channels<<<dim3(nw, n), 128, 0, c->stream>>>(fd, c->d_scaled.as<uint8_t>(), c->scaled_fs, c->d_stacks.as<uint32_t>(), c->stack_fs,
-                                                         c->plane_stride, u8, c->u8_fs, pp);
+    k_plain_channels<<<dim3(nw, n), 128, 0, c->w->stream>>>(fd, c->w->d_scaled.as<uint8_t>(), c->w->scaled_fs, c->w->d_stacks.as<stack_t>(), c->w->stack_fs,
+                                                         c->w->plane_stride, u8, c->w->u8_fs, dbg32, pp);
     KCHECK(); count_launch(c, CRF_STAGE_PLAIN);
   }
   if (minmax_planes) return CRF_OK;
   Span s(c, CRF_STAGE_GABOR);
-  k_init_minmax<<<(n * 70 + 255) / 256, 256, 0, c->stream>>>(c->d_minmax.as<uint32_t>(), n * 70);
+  k_init_minmax<<<(n * 70 + 255) / 256, 256, 0, c->w->stream>>>(c->w->d_minmax.as<uint32_t>(), n * 70);
   KCHECK();
   const dim3 grid((Hmax + 15) / 16, 7, n);
-  const uint8_t* sc = c->d_scaled.as<uint8_t>();
-  float* mag = c->d_mag.as<float>();
-  uint32_t* mm = c->d_minmax.as<uint32_t>();
+  const uint8_t* sc = c->w->d_scaled.as<uint8_t>();
+  float* mag = c->w->d_mag.as<float>();
+  uint32_t* mm = c->w->d_minmax.as<uint32_t>();
   // heaviest scale first
-  k_gabor_mag<25><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[4].as<float2>(), 4, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
-  k_gabor_mag<19><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[3].as<float2>(), 3, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
-  k_gabor_mag<13><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[2].as<float2>(), 2, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
-  k_gabor_mag<9><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[1].as<float2>(), 1, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
-  k_gabor_mag<7><<<grid, 256, 0, c->stream>>>(fd, sc, c->scaled_fs, c->d_coef[0].as<float2>(), 0, mag, c->mag_fs, c->mag_ps, mm); KCHECK();
-  k_gabor_quant_integral<<<dim3(35, n), 128, 0, c->stream>>>(fd, mag, c->mag_fs, c->mag_ps, mm, c->d_stacks.as<uint32_t>(), c->stack_fs, c->plane_stride, 1,
-                                                             u8, c->u8_fs);
+  k_gabor_mag<25><<<grid, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef[4].as<float2>(), 4, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  k_gabor_mag<19><<<grid, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef[3].as<float2>(), 3, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  k_gabor_mag<13><<<grid, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef[2].as<float2>(), 2, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  k_gabor_mag<9><<<grid, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef[1].as<float2>(), 1, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  k_gabor_mag<7><<<grid, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef[0].as<float2>(), 0, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  k_gabor_quant_integral<<<dim3(35, n), 128, 0, c->w->stream>>>(fd, mag, c->w->mag_fs, c->w->mag_ps, mm, c->w->d_stacks.as<stack_t>(), c->w->stack_fs, c->w->plane_stride, 1,
+                                                             u8, c->w->u8_fs, dbg32);
   KCHECK(); count_launch(c, CRF_STAGE_GABOR, 7);
   return CRF_OK;
 }
@@ -253,17 +265,17 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   const int stage = hp ? CRF_STAGE_HP_TRAVERSE : CRF_STAGE_FFD_TRAVERSE;
   Span s(c, stage);
   TraverseArgs a{};
-  a.fd = fd; a.stacks = c->d_stacks.as<uint32_t>(); a.stack_face_stride = c->stack_fs; a.plane_stride = c->plane_stride;
+  a.fd = fd; a.stacks = c->w->d_stacks.as<stack_t>(); a.stack_face_stride = c->w->stack_fs; a.plane_stride = c->w->plane_stride;
   a.stride = stride;
   if (hp) {
     a.slots = c->d_hp_slots.as<DevSlot>(); a.roots = roots; a.ntrees = ntrees;
-    a.leaf_out = c->d_hp_leaf.as<int32_t>(); a.leaf_face_stride = c->hp_leaf_fs;
+    a.leaf_out = c->w->d_hp_leaf.as<int32_t>(); a.leaf_face_stride = c->w->hp_leaf_fs;
     a.cnt_tests = CNT_HP_TESTS; a.cnt_trav = CNT_HP_TRAV;
     if (hp_values) a.leaf_value = c->d_hp_m.as<float>();
   } else {
     a.slots = c->d_mp_slots.as<DevSlot>();
-    a.face_roots = c->d_face_roots.as<int32_t>(); a.face_ntrees = c->d_face_ntrees.as<int32_t>();
-    a.leaf_out = c->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->ffd_leaf_fs;
+    a.face_roots = c->w->d_face_roots.as<int32_t>(); a.face_ntrees = c->w->d_face_ntrees.as<int32_t>();
+    a.leaf_out = c->w->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->w->ffd_leaf_fs;
     a.cnt_tests = CNT_FFD_TESTS; a.cnt_trav = CNT_FFD_TRAV;
   }
   a.counters = c->counting ? c->d_counters.as<unsigned long long>() : nullptr;
@@ -277,8 +289,8 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   const dim3 grid(tiles, n);
 #define CRF_TRAV(NW_, LW_, MODE_)                                                                          \
   if (NW == NW_ && LW == LW_ && MODE == MODE_) {                                                           \
-    if (c->counting) k_traverse<NW_, true, LW_, MODE_><<<grid, NW_ * 32, smem, c->stream>>>(a);            \
-    else k_traverse<NW_, false, LW_, MODE_><<<grid, NW_ * 32, smem, c->stream>>>(a);                       \
+    if (c->counting) k_traverse<NW_, true, LW_, MODE_><<<grid, NW_ * 32, smem, c->w->stream>>>(a);            \
+    else k_traverse<NW_, false, LW_, MODE_><<<grid, NW_ * 32, smem, c->w->stream>>>(a);                       \
     launched = true;                                                                                       \
   }
   bool launched = false;
@@ -295,8 +307,8 @@ static int launch_hp_reduce(crf_ctx* c, const FaceDesc* fd, int n, int stride, b
   Span s(c, CRF_STAGE_HP_REDUCE);
   ComposeTables ct = c->ct;
   ct.list_cap = list_cap;
-  k_hp_reduce_compose<<<(n + kFoldChains - 1) / kFoldChains, kFoldThreads, kHpSmem, c->stream>>>(fd, n, c->d_hp_leaf.as<float>(), c->hp_leaf_fs, c->hp_ntrees, stride, ct,
-                                                          compose ? 1 : 0, faces, c->d_face_roots.as<int32_t>(), c->d_face_ntrees.as<int32_t>());
+  k_hp_reduce_compose<<<(n + kFoldChains - 1) / kFoldChains, kFoldThreads, kHpSmem, c->w->stream>>>(fd, n, c->w->d_hp_leaf.as<float>(), c->w->hp_leaf_fs, c->hp_ntrees, stride, ct,
+                                                          compose ? 1 : 0, faces, c->w->d_face_roots.as<int32_t>(), c->w->d_face_ntrees.as<int32_t>());
   KCHECK(); count_launch(c, CRF_STAGE_HP_REDUCE);
   return CRF_OK;
 }
@@ -304,8 +316,8 @@ static int launch_hp_reduce(crf_ctx* c, const FaceDesc* fd, int n, int stride, b
 static int launch_meanshift(crf_ctx* c, const FaceDesc* fd, int nchains, crf_face_t* faces) {
   Span s(c, CRF_STAGE_MEANSHIFT);
   MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
-  k_meanshift<<<(nchains + kFoldChains - 1) / kFoldChains, kFoldThreads, kMsSmem, c->stream>>>(fd, nchains, c->d_votes.as<DevVote>(), c->vote_cap,
-                                                                                       c->d_vote_counts.as<int32_t>(), c->d_vote_base.as<int32_t>(), mo, faces,
+  k_meanshift<<<(nchains + kFoldChains - 1) / kFoldChains, kFoldThreads, kMsSmem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap,
+                                                                                       c->w->d_vote_counts.as<int32_t>(), c->w->d_vote_base.as<int32_t>(), mo, faces,
                                                                                        c->counting ? c->d_counters.as<unsigned long long>() : nullptr);
   KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
   return CRF_OK;
@@ -315,15 +327,15 @@ static int launch_votes_meanshift(crf_ctx* c, const FaceDesc* fd, int n, int str
   {
     Span s(c, CRF_STAGE_VOTES);
     VoteArgs a{};
-    a.fd = fd; a.leaf_ids = c->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->ffd_leaf_fs; a.face_ntrees = c->d_face_ntrees.as<int32_t>(); a.stride = stride;
-    a.mp_mask = c->d_mp_mask.as<uint16_t>(); a.mp_leaf = c->d_mp_leaf.as<DevMpLeaf>(); a.votes = c->d_votes.as<DevVote>(); a.vote_cap = c->vote_cap;
-    a.seg_counts = c->d_seg_counts.as<int32_t>(); a.vote_counts = c->d_vote_counts.as<int32_t>(); a.vote_base = c->d_vote_base.as<int32_t>(); a.faces = faces;
-    CU(cudaMemsetAsync(a.vote_counts, 0, (size_t)n * kParts * 4, c->stream));
-    k_votes_count<<<dim3(kVoteSegs / 8, n), 256, 0, c->stream>>>(a);
+    a.fd = fd; a.leaf_ids = c->w->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->w->ffd_leaf_fs; a.face_ntrees = c->w->d_face_ntrees.as<int32_t>(); a.stride = stride;
+    a.mp_mask = c->d_mp_mask.as<uint16_t>(); a.mp_leaf = c->d_mp_leaf.as<DevMpLeaf>(); a.votes = c->w->d_votes.as<DevVote>(); a.vote_cap = c->w->vote_cap;
+    a.seg_counts = c->w->d_seg_counts.as<int32_t>(); a.vote_counts = c->w->d_vote_counts.as<int32_t>(); a.vote_base = c->w->d_vote_base.as<int32_t>(); a.faces = faces;
+    CU(cudaMemsetAsync(a.vote_counts, 0, (size_t)n * kParts * 4, c->w->stream));
+    k_votes_count<<<dim3(kVoteSegs / 8, n), 256, 0, c->w->stream>>>(a);
     KCHECK();
-    k_votes_offsets<<<(n + 127) / 128, 128, 0, c->stream>>>(a, n);
+    k_votes_offsets<<<(n + 127) / 128, 128, 0, c->w->stream>>>(a, n);
     KCHECK();
-    k_votes_emit<<<dim3(kVoteSegs / 8, n), 256, 0, c->stream>>>(a);
+    k_votes_emit<<<dim3(kVoteSegs / 8, n), 256, 0, c->w->stream>>>(a);
     KCHECK(); count_launch(c, CRF_STAGE_VOTES, 3);
   }
   return launch_meanshift(c, fd, n * kParts, faces);
@@ -334,7 +346,7 @@ static int run_faces(crf_ctx* c, const FaceDesc* d_fd, int n, int Hmax, const ui
                      cudaEvent_t imgs_consumed) {
   int rc;
   if ((rc = launch_resize(c, d_fd, n, Hmax, d_imgs))) return rc;
-  if (imgs_consumed) CU(cudaEventRecord(imgs_consumed, c->stream));
+  if (imgs_consumed) CU(cudaEventRecord(imgs_consumed, c->w->stream));
   if ((rc = launch_channels(c, d_fd, n, Hmax, false, false))) return rc;
   if ((rc = launch_traverse(c, d_fd, n, Hmax, true, c->opt.hp_stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees, true))) return rc;
   if ((rc = launch_hp_reduce(c, d_fd, n, c->opt.hp_stride, !headpose_only, tree_cap, d_faces))) return rc;
@@ -350,9 +362,9 @@ static int run_faces(crf_ctx* c, const FaceDesc* d_fd, int n, int Hmax, const ui
 static int pick_chunk(const crf_ctx* c, int Hmax, bool headpose_only) {
   const size_t np_hp = (size_t)patches_1d(125, c->opt.hp_stride) * patches_1d(Hmax, c->opt.hp_stride);
   const size_t np_ffd = headpose_only ? 0 : (size_t)patches_1d(125, c->opt.ffd_stride) * patches_1d(Hmax, c->opt.ffd_stride);
-  const size_t per_face = (size_t)Hmax * 128 + (size_t)(Hmax + 1) * kRowStride * 4 * 38 + (size_t)Hmax * 128 * 4 * 35 + np_hp * c->hp_ntrees * 4 +
+  const size_t per_face = (size_t)Hmax * 128 + (size_t)(Hmax + 1) * kRowStride * sizeof(stack_t) * 38 + (size_t)Hmax * 128 * 4 * 35 + np_hp * c->hp_ntrees * 4 +
                           np_ffd * c->mp_ntrees_cfg * (4 + 3 * sizeof(DevVote)) + 4096;
-  const size_t budget = c->work_budget;
+  const size_t budget = c->work_budget / c->nstreams;
   long long chunk = (long long)(budget / per_face);
   const int cap = c->opt.max_chunk > 0 ? c->opt.max_chunk : 2048;
   return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(chunk, cap), 32768));
@@ -361,12 +373,13 @@ static int pick_chunk(const crf_ctx* c, int Hmax, bool headpose_only) {
 static int pull_counters(crf_ctx* c) {
   if (!c->counting) return CRF_OK;
   unsigned long long h[CNT_NUM];
-  CU(cudaMemcpyAsync(h, c->d_counters.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpyAsync(h, c->d_counters.p, sizeof h, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
   c->cnt.hp_node_tests += h[CNT_HP_TESTS]; c->cnt.ffd_node_tests += h[CNT_FFD_TESTS];
   c->cnt.hp_traversals += h[CNT_HP_TRAV]; c->cnt.ffd_traversals += h[CNT_FFD_TRAV];
   c->cnt.votes += h[CNT_VOTES]; c->cnt.vote_passes += h[CNT_VOTE_PASSES];
-  CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof h, c->stream));
+  CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof h, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
   return CRF_OK;
 }
 
@@ -419,22 +432,24 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
     chunks.push_back(std::move(ch));
   }
   int rc;
+  c->w = &c->ws[0];
+  cudaStream_t s0 = c->ws[0].stream;
   if ((rc = c->d_fd.reserve((size_t)n * sizeof(FaceDesc)))) return rc;
   if ((rc = c->d_faces.reserve((size_t)n * sizeof(crf_face_t)))) return rc;
-  CU(cudaMemcpyAsync(c->d_fd.p, descs.data(), (size_t)n * sizeof(FaceDesc), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemsetAsync(c->d_faces.p, 0, (size_t)n * sizeof(crf_face_t), c->stream));
+  CU(cudaMemcpyAsync(c->d_fd.p, descs.data(), (size_t)n * sizeof(FaceDesc), cudaMemcpyHostToDevice, s0));
+  CU(cudaMemsetAsync(c->d_faces.p, 0, (size_t)n * sizeof(crf_face_t), s0));
   c->cnt.h2d_bytes += (size_t)n * sizeof(FaceDesc);
   size_t max_frames = 0; int Hmax_all = 0, max_faces = 0;
   for (auto& ch : chunks) { max_frames = std::max(max_frames, ch.frames.size()); Hmax_all = std::max(Hmax_all, ch.Hmax); max_faces = std::max(max_faces, ch.f1 - ch.f0); }
   for (int b = 0; b < 2; b++) if ((rc = c->d_imgs[b].reserve(max_frames * img_bytes))) return rc;
   Plan p; p.n = max_faces; p.Hmax = Hmax_all; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
   p.need_ffd = !headpose_only;
-  if ((rc = ensure(c, p))) return rc;
-  // the allocation above must not race with earlier work still using the buffers
+  const int nsets = chunks.size() > 1 ? c->nstreams : 1;
+  for (int k = 0; k < nsets; k++) { c->w = &c->ws[k]; if ((rc = ensure(c, p))) return rc; }
+  CU(cudaStreamSynchronize(s0));   // descriptors and the zeroed records are visible to both streams
   auto copy_chunk = [&](size_t k) -> int {
     const Chunk& ch = chunks[k];
     const int b = (int)(k & 1);
-    if (k >= 2) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
     // consecutive frames that are also consecutive in host memory go in one copy
     size_t i = 0;
     while (i < ch.frames.size()) {
@@ -447,41 +462,43 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
     CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
     return CRF_OK;
   };
+  // results of chunk k: D2H, pathological faces re-run with the wide capacities (needs the chunk's frames and work set)
+  auto finish_chunk = [&](size_t k) -> int {
+    const Chunk& ch = chunks[k];
+    const int b = (int)(k & 1);
+    c->w = &c->ws[k % nsets];
+    const size_t m = (size_t)(ch.f1 - ch.f0);
+    CU(cudaMemcpyAsync(out + ch.f0, c->d_faces.as<crf_face_t>() + ch.f0, m * sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->w->stream));
+    CU(cudaStreamSynchronize(c->w->stream));
+    c->cnt.d2h_bytes += m * sizeof(crf_face_t);
+    if (headpose_only) return CRF_OK;
+    std::vector<int> wide;
+    for (size_t i = 0; i < m; i++) if (out[ch.f0 + i].flags & 6) wide.push_back(ch.f0 + (int)i);
+    if (wide.empty()) return CRF_OK;
+    int rc2 = rerun_wide(c, c->d_fd.as<FaceDesc>(), descs, c->d_imgs[b].as<uint8_t>(), c->d_faces.as<crf_face_t>(), wide);
+    if (rc2) return rc2;
+    for (int i : wide) CU(cudaMemcpyAsync(out + i, c->d_faces.as<crf_face_t>() + i, sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->w->stream));
+    CU(cudaStreamSynchronize(c->w->stream));
+    Plan q = p; q.n = (int)m; q.Hmax = ch.Hmax;
+    return ensure(c, q);   // restore the batched geometry of this set
+  };
+  // two-deep software pipeline: chunk k runs on stream k&1 while chunk k-1 finishes on the other one
   if ((rc = copy_chunk(0))) return rc;
   for (size_t k = 0; k < chunks.size(); k++) {
     const Chunk& ch = chunks[k];
     const int b = (int)(k & 1);
-    if (k + 1 < chunks.size() && (rc = copy_chunk(k + 1))) return rc;
-    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    c->w = &c->ws[k % nsets];
     Plan q = p; q.n = ch.f1 - ch.f0; q.Hmax = ch.Hmax;
-    if ((rc = ensure(c, q))) return rc;  // only recomputes strides (capacity already there)
+    if ((rc = ensure(c, q))) return rc;  // only recomputes the strides (capacity is already there)
+    CU(cudaStreamWaitEvent(c->w->stream, c->ev_copied[b], 0));
     if ((rc = run_faces(c, c->d_fd.as<FaceDesc>() + ch.f0, ch.f1 - ch.f0, ch.Hmax, c->d_imgs[b].as<uint8_t>(), c->d_faces.as<crf_face_t>() + ch.f0,
-                        headpose_only, c->mp_ntrees_cfg, c->ev_consumed[b])))
+                        headpose_only, c->mp_ntrees_cfg, nullptr)))
       return rc;
-    // pathological compositions of this chunk (needs the chunk's frames, so check before they are overwritten)
-    if (!headpose_only) {
-      // flags live in the results; a cheap strided copy of the whole records of the chunk
-      std::vector<crf_face_t> tmp((size_t)(ch.f1 - ch.f0));
-      CU(cudaMemcpyAsync(tmp.data(), c->d_faces.as<crf_face_t>() + ch.f0, tmp.size() * sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      c->cnt.d2h_bytes += tmp.size() * sizeof(crf_face_t);
-      std::vector<int> wide;
-      for (size_t i = 0; i < tmp.size(); i++) if (tmp[i].flags & 6) wide.push_back(ch.f0 + (int)i);
-      if (!wide.empty()) {
-        if ((rc = rerun_wide(c, c->d_fd.as<FaceDesc>(), descs, c->d_imgs[b].as<uint8_t>(), c->d_faces.as<crf_face_t>(), wide))) return rc;
-        for (int i : wide)
-          CU(cudaMemcpyAsync(&tmp[(size_t)(i - ch.f0)], c->d_faces.as<crf_face_t>() + i, sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        CU(cudaEventRecord(c->ev_consumed[b], c->stream));
-      }
-      std::memcpy(out + ch.f0, tmp.data(), tmp.size() * sizeof(crf_face_t));
-    }
+    if (k >= 1 && (rc = finish_chunk(k - 1))) return rc;
+    if (k + 1 < chunks.size() && (rc = copy_chunk(k + 1))) return rc;   // its image buffer was chunk k-1's: free now
   }
-  if (headpose_only) {
-    CU(cudaMemcpyAsync(out, c->d_faces.p, (size_t)n * sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->stream));
-    c->cnt.d2h_bytes += (size_t)n * sizeof(crf_face_t);
-  }
-  CU(cudaStreamSynchronize(c->stream));
+  if ((rc = finish_chunk(chunks.size() - 1))) return rc;
+  c->w = &c->ws[0];
   c->cnt.faces += n;
   c->timer.collect();
   return pull_counters(c);
@@ -578,15 +595,16 @@ int crf_device_count(void) {
 void crf_ctx_destroy(crf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto& w : c->ws) if (w.stream) cudaStreamSynchronize(w.stream);
   Buf* all[] = {&c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
-                &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_scaled, &c->d_stacks, &c->d_mag, &c->d_minmax,
-                &c->d_hp_leaf, &c->d_ffd_leaf, &c->d_face_roots, &c->d_face_ntrees, &c->d_votes, &c->d_vote_counts, &c->d_vote_base, &c->d_seg_counts, &c->d_faces, &c->d_u8planes, &c->d_counters,
-                &c->d_misc};
+                &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc};
   for (Buf* b : all) b->release();
+  for (auto& w : c->ws) {
+    for (Buf* b : w.all) b->release();
+    if (w.stream) cudaStreamDestroy(w.stream);
+  }
   c->timer.destroy();
   for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
-  if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
 }
@@ -605,7 +623,8 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if (opt) c->opt = *opt; else crf_options_default(&c->opt);
   if (c->opt.hp_stride < 1 || c->opt.ffd_stride < 1) return fail(CRF_ERR_ARG, "strides must be >= 1");
   if (const char* v = std::getenv("CRF_TRAVERSE_VARIANT")) c->traverse_variant = (int)std::strtol(v, nullptr, 0);
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if (const char* v = std::getenv("CRF_STREAMS")) c->nstreams = std::strtol(v, nullptr, 0) == 2 ? 2 : 1;
+  for (auto& w : c->ws) CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) {
     CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
@@ -625,9 +644,9 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   c->mp_ntrees_cfg = m->m.mp_ntrees_cfg;
   c->num_channels = m->m.num_channels;
   if (c->hp_ntrees > kMaxList || c->mp_ntrees_cfg > kMaxList || c->mp_ntrees_cfg < 1) return fail(CRF_ERR_UNSUPPORTED, "forest size outside 1..128 trees");
-  if ((rc = upload(c->d_hp_slots, c->hp.slots, c->stream)) || (rc = upload(c->d_hp_roots, c->hp.roots, c->stream)) || (rc = upload(c->d_hp_m, c->hp.hp_m, c->stream)) ||
-      (rc = upload(c->d_mp_slots, c->mp.slots, c->stream)) || (rc = upload(c->d_mp_roots, c->mp.roots, c->stream)) ||
-      (rc = upload(c->d_mp_mask, c->mp.mp_mask, c->stream)) || (rc = upload(c->d_mp_leaf, c->mp.mp_leaf, c->stream)))
+  if ((rc = upload(c->d_hp_slots, c->hp.slots, c->w->stream)) || (rc = upload(c->d_hp_roots, c->hp.roots, c->w->stream)) || (rc = upload(c->d_hp_m, c->hp.hp_m, c->w->stream)) ||
+      (rc = upload(c->d_mp_slots, c->mp.slots, c->w->stream)) || (rc = upload(c->d_mp_roots, c->mp.roots, c->w->stream)) ||
+      (rc = upload(c->d_mp_mask, c->mp.mp_mask, c->w->stream)) || (rc = upload(c->d_mp_leaf, c->mp.mp_leaf, c->w->stream)))
     return rc;
   // Riemann abscissae of areaUnderCurve (src/face_utils.cpp:304-323) for the bins of src/FaceForest.cpp:216-222
   {
@@ -640,7 +659,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
       for (double x = poseT[j]; x < poseT[j + 1]; x += step) xs.push_back(x);
     }
     c->ct.bin_begin[5] = (int)xs.size();
-    if ((rc = upload(c->d_xs, xs, c->stream))) return rc;
+    if ((rc = upload(c->d_xs, xs, c->w->stream))) return rc;
     c->ct.xs = c->d_xs.as<double>();
     c->ct.jungle_roots = c->d_mp_roots.as<int32_t>();
     for (int i = 0; i < 5; i++) { c->ct.forest_base[i] = c->mp.forest_base[i]; c->ct.forest_ntrees[i] = c->mp.forest_ntrees[i]; }
@@ -653,7 +672,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
     const int expect[5] = {7, 9, 13, 19, 25};
     for (int i = 0; i < 5; i++) {
       if (c->gabor_width[i] != expect[i]) return fail(CRF_ERR_STATE, "unexpected Gabor kernel width");
-      if ((rc = upload(c->d_coef[i], coef[i], c->stream))) return rc;
+      if ((rc = upload(c->d_coef[i], coef[i], c->w->stream))) return rc;
     }
   }
   {
@@ -664,7 +683,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
       std::memcpy(&u, &v, 8);
       t.tab[i] = u - ((unsigned long long)i << 47);
     }
-    CU(cudaMemcpyToSymbolAsync(c_expf, &t, sizeof t, 0, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyToSymbolAsync(c_expf, &t, sizeof t, 0, cudaMemcpyHostToDevice, c->w->stream));
   }
   {
     size_t free_b = 0, total_b = 0;
@@ -673,9 +692,9 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   CU(cudaFuncSetAttribute(k_hp_reduce_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHpSmem));
   CU(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
   if ((rc = c->d_counters.reserve(sizeof(unsigned long long) * CNT_NUM))) return rc;
-  CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * CNT_NUM, c->stream));
+  CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * CNT_NUM, c->w->stream));
   if ((rc = c->d_misc.reserve(4096))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
   guard.c = nullptr;
   *out = c;
   return CRF_OK;
@@ -707,7 +726,7 @@ int crf_ctx_reset_counters(crf_ctx* c) {
   return CRF_OK;
 }
 
-void* crf_ctx_stream(crf_ctx* c) { return c ? (void*)c->stream : nullptr; }
+void* crf_ctx_stream(crf_ctx* c) { return c ? (void*)c->ws[0].stream : nullptr; }
 
 int crf_host_alloc(void** p, size_t bytes) {
   if (!p) return fail(CRF_ERR_ARG, "null argument");
@@ -753,27 +772,36 @@ int crf_analyze_crops_device(crf_ctx* c, const uint8_t* d_bgr_batch, int n, int 
     Hmax = std::max(Hmax, descs[i].H);
   }
   int rc;
+  c->w = &c->ws[0];
+  cudaStream_t s0 = c->ws[0].stream;
   if ((rc = c->d_fd.reserve((size_t)n * sizeof(FaceDesc)))) return rc;
-  CU(cudaMemcpyAsync(c->d_fd.p, descs.data(), (size_t)n * sizeof(FaceDesc), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(crf_face_t), c->stream));
+  CU(cudaMemcpyAsync(c->d_fd.p, descs.data(), (size_t)n * sizeof(FaceDesc), cudaMemcpyHostToDevice, s0));
+  CU(cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(crf_face_t), s0));
   const int chunk = pick_chunk(c, Hmax, headpose_only != 0);
   Plan p; p.n = std::min(n, chunk); p.Hmax = Hmax; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
   p.need_ffd = !headpose_only;
-  if ((rc = ensure(c, p))) return rc;
-  for (int f0 = 0; f0 < n; f0 += chunk) {
+  const int nsets = n > chunk ? c->nstreams : 1;
+  for (int k = 0; k < nsets; k++) { c->w = &c->ws[k]; if ((rc = ensure(c, p))) return rc; }
+  CU(cudaStreamSynchronize(s0));
+  // consecutive chunks alternate between the two streams / work sets
+  int k = 0;
+  for (int f0 = 0; f0 < n; f0 += chunk, k++) {
     const int m = std::min(chunk, n - f0);
+    c->w = &c->ws[k % nsets];
     if ((rc = run_faces(c, c->d_fd.as<FaceDesc>() + f0, m, Hmax, d_bgr_batch, d_out + f0, headpose_only != 0, c->mp_ntrees_cfg, nullptr))) return rc;
   }
+  for (int q = 0; q < nsets; q++) CU(cudaStreamSynchronize(c->ws[q].stream));
+  c->w = &c->ws[0];
   if (!headpose_only) {
-    // pathological compositions: fetch the flags, re-run those faces with the widest list
+    // faces whose composition or vote count exceeded the batched capacities: fetch the flags, re-run those faces wide
     std::vector<crf_face_t> tmp((size_t)n);
-    CU(cudaMemcpyAsync(tmp.data(), d_out, (size_t)n * sizeof(crf_face_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(tmp.data(), d_out, (size_t)n * sizeof(crf_face_t), cudaMemcpyDeviceToHost, s0));
+    CU(cudaStreamSynchronize(s0));
     std::vector<int> wide;
     for (int i = 0; i < n; i++) if (tmp[(size_t)i].flags & 6) wide.push_back(i);
     if (!wide.empty() && (rc = rerun_wide(c, c->d_fd.as<FaceDesc>(), descs, d_bgr_batch, d_out, wide))) return rc;
+    CU(cudaStreamSynchronize(s0));
   }
-  CU(cudaStreamSynchronize(c->stream));
   c->cnt.faces += n;
   c->timer.collect();
   return pull_counters(c);
@@ -791,11 +819,11 @@ int crf_stage_gray_resize(crf_ctx* c, const uint8_t* bgr, int rows, int cols, si
   if (rc) return rc;
   Plan p; p.n = 1; p.Hmax = d.H; p.need_gabor = false; p.need_hp = false; p.need_ffd = false;
   if ((rc = ensure(c, p)) || (rc = c->d_fd.reserve(sizeof d)) || (rc = c->d_imgs[0].reserve((size_t)rows * step))) return rc;
-  CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_imgs[0].p, bgr, (size_t)rows * step, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->w->stream));
+  CU(cudaMemcpyAsync(c->d_imgs[0].p, bgr, (size_t)rows * step, cudaMemcpyHostToDevice, c->w->stream));
   if ((rc = launch_resize(c, c->d_fd.as<FaceDesc>(), 1, d.H, c->d_imgs[0].as<uint8_t>()))) return rc;
-  CU(cudaMemcpy2DAsync(scaled, d.W, c->d_scaled.p, 128, d.W, d.H, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy2DAsync(scaled, d.W, c->w->d_scaled.p, 128, d.W, d.H, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
   if (W) *W = d.W;
   if (H) *H = d.H;
   return CRF_OK;
@@ -811,18 +839,18 @@ static int stage_upload_scaled(crf_ctx* c, const uint8_t* scaled, int W, int H, 
   p.hp_stride = hp_stride; p.ffd_stride = ffd_stride;
   int rc;
   if ((rc = ensure(c, p)) || (rc = c->d_fd.reserve(sizeof d))) return rc;
-  CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->stream));
-  if (scaled) CU(cudaMemcpy2DAsync(c->d_scaled.p, 128, scaled, W, W, H, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->w->stream));
+  if (scaled) CU(cudaMemcpy2DAsync(c->w->d_scaled.p, 128, scaled, W, W, H, cudaMemcpyHostToDevice, c->w->stream));
   return CRF_OK;
 }
 
 static int stage_download_planes(crf_ctx* c, int nplanes, int W, int H, uint8_t* planes_u8, uint32_t* integrals) {
-  if (planes_u8) CU(cudaMemcpyAsync(planes_u8, c->d_u8planes.p, (size_t)nplanes * W * H, cudaMemcpyDeviceToHost, c->stream));
+  if (planes_u8) CU(cudaMemcpyAsync(planes_u8, c->w->d_u8planes.p, (size_t)nplanes * W * H, cudaMemcpyDeviceToHost, c->w->stream));
   if (integrals)
     for (int pl = 0; pl < nplanes; pl++)
-      CU(cudaMemcpy2DAsync(integrals + (size_t)pl * (H + 1) * (W + 1), (size_t)(W + 1) * 4, c->d_stacks.as<uint32_t>() + (size_t)pl * c->plane_stride,
-                           (size_t)kRowStride * 4, (size_t)(W + 1) * 4, H + 1, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+      CU(cudaMemcpy2DAsync(integrals + (size_t)pl * (H + 1) * (W + 1), (size_t)(W + 1) * 4, c->w->d_int32.as<uint32_t>() + (size_t)pl * c->w->plane_stride,
+                           (size_t)kRowStride * 4, (size_t)(W + 1) * 4, H + 1, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
   return CRF_OK;
 }
 
@@ -852,8 +880,8 @@ static int stage_planes_to_stack(crf_ctx* c, const uint8_t* planes_u8, int C, in
   if (C < 1 || C > 64) return fail(CRF_ERR_ARG, "plane count outside 1..64");
   int rc = stage_upload_scaled(c, nullptr, W, H, C, false, true, hp, ffd, tree_cap, hp_stride, ffd_stride);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(c->d_u8planes.p, planes_u8, (size_t)C * W * H, cudaMemcpyHostToDevice, c->stream));
-  k_integral_from_u8<<<dim3(C, 1), 128, 0, c->stream>>>(c->d_u8planes.as<uint8_t>(), W, H, c->d_stacks.as<uint32_t>(), c->stack_fs, c->plane_stride);
+  CU(cudaMemcpyAsync(c->w->d_u8planes.p, planes_u8, (size_t)C * W * H, cudaMemcpyHostToDevice, c->w->stream));
+  k_integral_from_u8<<<dim3(C, 1), 128, 0, c->w->stream>>>(c->w->d_u8planes.as<uint8_t>(), W, H, c->w->d_stacks.as<stack_t>(), c->w->stack_fs, c->w->plane_stride);
   KCHECK(); count_launch(c, CRF_STAGE_PLAIN);
   return CRF_OK;
 }
@@ -872,9 +900,9 @@ static int stage_set_list(crf_ctx* c, const int* tree_forest, const int* tree_in
       return fail(CRF_ERR_ARG, "bad composed forest");
     list[i] = c->mp.roots[c->mp.forest_base[tree_forest[i]] + tree_index[i]];
   }
-  CU(cudaMemcpyAsync(c->d_face_roots.p, list.data(), kMaxList * 4, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_face_ntrees.p, &ntrees, 4, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));  // `list` and `ntrees` are stack/local host memory
+  CU(cudaMemcpyAsync(c->w->d_face_roots.p, list.data(), kMaxList * 4, cudaMemcpyHostToDevice, c->w->stream));
+  CU(cudaMemcpyAsync(c->w->d_face_ntrees.p, &ntrees, 4, cudaMemcpyHostToDevice, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));  // `list` and `ntrees` are stack/local host memory
   return CRF_OK;
 }
 
@@ -893,8 +921,8 @@ int crf_stage_eval_forest(crf_ctx* c, int which, const int* tree_forest, const i
   if ((rc = launch_traverse(c, c->d_fd.as<FaceDesc>(), 1, H, hp, stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, std::max(nt, 1)))) return rc;
   const size_t n = (size_t)patches_1d(W, stride) * patches_1d(H, stride) * nt;
   std::vector<int32_t> raw(n);
-  if (n) CU(cudaMemcpyAsync(raw.data(), hp ? c->d_hp_leaf.p : c->d_ffd_leaf.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  if (n) CU(cudaMemcpyAsync(raw.data(), hp ? c->w->d_hp_leaf.p : c->w->d_ffd_leaf.p, n * 4, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
   for (size_t i = 0; i < n; i++) leaf_ids[i] = pf.leaf_oid[(size_t)raw[i]];
   c->timer.collect();
   return pull_counters(c);
@@ -915,10 +943,10 @@ static int stage_fetch_compose(crf_ctx* c, float* headpose, float* variance, int
   crf_face_t face;
   std::vector<int32_t> list((size_t)kMaxList);
   int nt = 0;
-  CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(list.data(), c->d_face_roots.p, kMaxList * 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(&nt, c->d_face_ntrees.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaMemcpyAsync(list.data(), c->w->d_face_roots.p, kMaxList * 4, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaMemcpyAsync(&nt, c->w->d_face_ntrees.p, 4, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
   if (headpose) *headpose = face.headpose;
   if (variance) *variance = face.variance;
   if (tree_counts) std::memcpy(tree_counts, face.tree_counts, sizeof face.tree_counts);
@@ -938,7 +966,7 @@ int crf_stage_headpose(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int H
   int rc = stage_planes_to_stack(c, planes_u8, C, W, H, true, false, 1, stride, stride);
   if (rc) return rc;
   if ((rc = c->d_faces.reserve(sizeof(crf_face_t)))) return rc;
-  CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->stream));
+  CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->w->stream));
   if ((rc = launch_traverse(c, c->d_fd.as<FaceDesc>(), 1, H, true, stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees, true))) return rc;
   if ((rc = launch_hp_reduce(c, c->d_fd.as<FaceDesc>(), 1, stride, true, kMaxList, c->d_faces.as<crf_face_t>()))) return rc;
   rc = stage_fetch_compose(c, headpose, variance, tree_counts, dominant, tree_forest, tree_index, ntrees, flags);
@@ -951,11 +979,11 @@ int crf_stage_compose(crf_ctx* c, float headpose, float variance, int tree_count
   if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
   CU(cudaSetDevice(c->device));
   int rc;
-  if ((rc = c->d_faces.reserve(sizeof(crf_face_t))) || (rc = c->d_face_roots.reserve(kMaxList * 4)) || (rc = c->d_face_ntrees.reserve(4))) return rc;
-  CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->stream));
+  if ((rc = c->d_faces.reserve(sizeof(crf_face_t))) || (rc = c->w->d_face_roots.reserve(kMaxList * 4)) || (rc = c->w->d_face_ntrees.reserve(4))) return rc;
+  CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->w->stream));
   ComposeTables ct = c->ct;
   ct.list_cap = kMaxList;
-  k_compose_only<<<1, 32, 0, c->stream>>>(headpose, variance, ct, c->d_faces.as<crf_face_t>(), c->d_face_roots.as<int32_t>(), c->d_face_ntrees.as<int32_t>());
+  k_compose_only<<<1, 32, 0, c->w->stream>>>(headpose, variance, ct, c->d_faces.as<crf_face_t>(), c->w->d_face_roots.as<int32_t>(), c->w->d_face_ntrees.as<int32_t>());
   KCHECK(); count_launch(c, CRF_STAGE_HP_REDUCE);
   return stage_fetch_compose(c, nullptr, nullptr, tree_counts, dominant, tree_forest, tree_index, ntrees, flags);
 }
@@ -971,16 +999,16 @@ int crf_stage_votes_meanshift(crf_ctx* c, const int* tree_forest, const int* tre
   if (rc) return rc;
   if ((rc = stage_set_list(c, tree_forest, tree_index, ntrees))) return rc;
   if ((rc = c->d_faces.reserve(sizeof(crf_face_t)))) return rc;
-  CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->stream));
+  CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->w->stream));
   if ((rc = launch_traverse(c, c->d_fd.as<FaceDesc>(), 1, H, false, stride, nullptr, 0, std::max(ntrees, 1)))) return rc;
   const int saved = c->opt.ffd_stride;
   if ((rc = launch_votes_meanshift(c, c->d_fd.as<FaceDesc>(), 1, stride, c->d_faces.as<crf_face_t>()))) return rc;
   (void)saved;
   crf_face_t face;
   int32_t vbase[kParts];
-  CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(vbase, c->d_vote_base.p, sizeof vbase, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaMemcpyAsync(vbase, c->w->d_vote_base.p, sizeof vbase, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
   for (int p = 0; p < kParts; p++) {
     if (n_votes) n_votes[p] = face.n_votes[p];
     if (mean_xy) { mean_xy[p][0] = face.ffd_f[p][0]; mean_xy[p][1] = face.ffd_f[p][1]; }
@@ -989,7 +1017,7 @@ int crf_stage_votes_meanshift(crf_ctx* c, const int* tree_forest, const int* tre
     if (votes_xyw && vote_cap > 0) {
       const int n = std::min(face.n_votes[p], vote_cap);
       std::vector<DevVote> v((size_t)n);
-      if (n) CU(cudaMemcpy(v.data(), c->d_votes.as<DevVote>() + vbase[p], (size_t)n * sizeof(DevVote), cudaMemcpyDeviceToHost));
+      if (n) CU(cudaMemcpy(v.data(), c->w->d_votes.as<DevVote>() + vbase[p], (size_t)n * sizeof(DevVote), cudaMemcpyDeviceToHost));
       for (int k = 0; k < n; k++) {
         float* o = votes_xyw + ((size_t)p * vote_cap + k) * 3;
         o[0] = v[k].x; o[1] = v[k].y; o[2] = v[k].w;
@@ -1007,21 +1035,21 @@ int crf_stage_meanshift(crf_ctx* c, const float* votes_xyw, int n, float mean_xy
   std::vector<DevVote> v((size_t)n);
   for (int i = 0; i < n; i++) { v[i].x = (short)votes_xyw[3 * i]; v[i].y = (short)votes_xyw[3 * i + 1]; v[i].w = votes_xyw[3 * i + 2]; }
   int rc;
-  if ((rc = c->d_votes.reserve(std::max<size_t>((size_t)n * sizeof(DevVote), 16))) || (rc = c->d_vote_counts.reserve(kParts * 4)) ||
+  if ((rc = c->w->d_votes.reserve(std::max<size_t>((size_t)n * sizeof(DevVote), 16))) || (rc = c->w->d_vote_counts.reserve(kParts * 4)) ||
       (rc = c->d_faces.reserve(sizeof(crf_face_t))) || (rc = c->d_fd.reserve(sizeof(FaceDesc))))
     return rc;
   FaceDesc d{};
   d.scale = 1.f;
-  CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->stream));
-  if (n) CU(cudaMemcpyAsync(c->d_votes.p, v.data(), (size_t)n * sizeof(DevVote), cudaMemcpyHostToDevice, c->stream));
-  if ((rc = c->d_vote_base.reserve(kParts * 4))) return rc;
-  CU(cudaMemsetAsync(c->d_vote_base.p, 0, kParts * 4, c->stream));
-  CU(cudaMemcpyAsync(c->d_vote_counts.p, &n, 4, cudaMemcpyHostToDevice, c->stream));
-  c->vote_cap = (size_t)std::max(n, 1);
+  CU(cudaMemcpyAsync(c->d_fd.p, &d, sizeof d, cudaMemcpyHostToDevice, c->w->stream));
+  if (n) CU(cudaMemcpyAsync(c->w->d_votes.p, v.data(), (size_t)n * sizeof(DevVote), cudaMemcpyHostToDevice, c->w->stream));
+  if ((rc = c->w->d_vote_base.reserve(kParts * 4))) return rc;
+  CU(cudaMemsetAsync(c->w->d_vote_base.p, 0, kParts * 4, c->w->stream));
+  CU(cudaMemcpyAsync(c->w->d_vote_counts.p, &n, 4, cudaMemcpyHostToDevice, c->w->stream));
+  c->w->vote_cap = (size_t)std::max(n, 1);
   if ((rc = launch_meanshift(c, c->d_fd.as<FaceDesc>(), 1, c->d_faces.as<crf_face_t>()))) return rc;
   crf_face_t face;
-  CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpyAsync(&face, c->d_faces.p, sizeof face, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
   if (mean_xy) { mean_xy[0] = face.ffd_f[0][0]; mean_xy[1] = face.ffd_f[0][1]; }
   if (rounded_xy) { rounded_xy[0] = face.ffd_scaled[0][0]; rounded_xy[1] = face.ffd_scaled[0][1]; }
   if (iters) *iters = face.ms_iters[0];

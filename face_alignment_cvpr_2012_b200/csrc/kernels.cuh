@@ -72,14 +72,16 @@ __global__ void __launch_bounds__(128) k_gray_resize(const FaceDesc* __restrict_
 // cv::integral (FeatureChannelFactory.hpp:51 etc.) of one W x H plane whose pixels
 // come from `pix(r, c)`.  128 threads.  Column sums run down the rows in registers (no
 // communication), then each 32-row band is scanned horizontally by warps and written with
-// fully coalesced 512-byte rows.  u32 on the device (exact; f32 in the reference is exact < 2^24).
-// out: (H+1) rows x kRowStride words.  u8out (optional): dense H x W copy of the 8-bit plane.
+// fully coalesced rows.  Exact u32 sums (the reference's f32 integrals hold the same integers < 2^24), stored as
+// stack_t (device_forest.h).  out: (H+1) rows x kRowStride elements.  u8out (optional): dense H x W copy of the
+// 8-bit plane; out32 (optional): the full 32-bit integral, same pitch (stage API / parity tests).
 // ---------------------------------------------------------------------------------------------
 template <class PixFn>
-__device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, uint32_t* __restrict__ out, uint8_t* __restrict__ u8out) {
+__device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, stack_t* __restrict__ out, uint8_t* __restrict__ u8out, uint32_t* __restrict__ out32) {
   __shared__ __align__(16) uint32_t band[32][kRowStride];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   out[tid] = 0;  // row 0
+  if (out32) out32[tid] = 0;
   uint32_t run = 0;
   for (int r0 = 0; r0 < H; r0 += 32) {
     const int nr = min(32, H - r0);
@@ -107,8 +109,11 @@ __device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, uint32_t
       *reinterpret_cast<uint4*>(&band[r][lane * 4]) = v;
     }
     __syncthreads();
-    for (int r = 0; r < nr; r++)  // I[y+1][x+1] = sum; column 0 stays zero
-      out[(size_t)(r0 + r + 1) * kRowStride + tid] = tid == 0 ? 0u : band[r][tid - 1];
+    for (int r = 0; r < nr; r++) {  // I[y+1][x+1] = sum; column 0 stays zero
+      const uint32_t v = tid == 0 ? 0u : band[r][tid - 1];
+      out[(size_t)(r0 + r + 1) * kRowStride + tid] = (stack_t)v;   // truncates only in the 16-bit layout (device_forest.h)
+      if (out32) out32[(size_t)(r0 + r + 1) * kRowStride + tid] = v;
+    }
     __syncthreads();
   }
 }
@@ -119,17 +124,18 @@ __device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, uint32_t
 struct PlainPlanes { int which[5]; int plane[5]; };
 
 __global__ void __launch_bounds__(128) k_plain_channels(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
-                                                        uint32_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride,
-                                                        uint8_t* __restrict__ u8planes, size_t u8_face_stride, PlainPlanes pp) {
+                                                        stack_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride,
+                                                        uint8_t* __restrict__ u8planes, size_t u8_face_stride, uint32_t* __restrict__ dbg32, PlainPlanes pp) {
   const FaceDesc d = fd[blockIdx.y];
   const int W = d.W, H = d.H;
   const uint8_t* __restrict__ g = scaled + blockIdx.y * scaled_face_stride;
   const int which = pp.which[blockIdx.x], plane = pp.plane[blockIdx.x];
-  uint32_t* out = stacks + blockIdx.y * stack_face_stride + (size_t)plane * plane_stride;
+  stack_t* out = stacks + blockIdx.y * stack_face_stride + (size_t)plane * plane_stride;
   uint8_t* u8o = u8planes ? u8planes + blockIdx.y * u8_face_stride + (size_t)plane * W * H : nullptr;
+  uint32_t* o32 = dbg32 ? dbg32 + blockIdx.y * stack_face_stride + (size_t)plane * plane_stride : nullptr;
   auto G = [&](int y, int x) -> int { return g[(size_t)y * 128 + x]; };
   if (which == 0) {
-    integral_plane([&](int r, int c) -> uint32_t { return G(r, c); }, W, H, out, u8o);
+    integral_plane([&](int r, int c) -> uint32_t { return G(r, c); }, W, H, out, u8o, o32);
   } else if (which == 1 || which == 2) {
     const bool is_dx = which == 2;
     integral_plane([&](int r, int c) -> uint32_t {
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(128) k_plain_channels(const FaceDesc* __restri
       if (is_dx) v = (G(ym, xp) + 2 * G(r, xp) + G(yp, xp)) - (G(ym, xm) + 2 * G(r, xm) + G(yp, xm));
       else v = (G(yp, xm) + 2 * G(yp, c) + G(yp, xp)) - (G(ym, xm) + 2 * G(ym, c) + G(ym, xp));
       return (uint32_t)min(max(v, 0), 255);
-    }, W, H, out, u8o);
+    }, W, H, out, u8o, o32);
   } else {
     const bool is_max = which == 4;
     integral_plane([&](int r, int c) -> uint32_t {
@@ -151,16 +157,16 @@ __global__ void __launch_bounds__(128) k_plain_channels(const FaceDesc* __restri
           lo = min(lo, v); hi = max(hi, v);
         }
       return (uint32_t)(is_max ? hi : lo);
-    }, W, H, out, u8o);
+    }, W, H, out, u8o, o32);
   }
 }
 
 // Integral of caller-supplied dense u8 planes [C][H][W] (stage API: synthetic channels).
 __global__ void __launch_bounds__(128) k_integral_from_u8(const uint8_t* __restrict__ planes, int W, int H,
-                                                          uint32_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride) {
+                                                          stack_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride) {
   const uint8_t* __restrict__ p = planes + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * W * H;
-  uint32_t* out = stacks + blockIdx.y * stack_face_stride + (size_t)blockIdx.x * plane_stride;
-  integral_plane([&](int r, int c) -> uint32_t { return p[(size_t)r * W + c]; }, W, H, out, nullptr);
+  stack_t* out = stacks + blockIdx.y * stack_face_stride + (size_t)blockIdx.x * plane_stride;
+  integral_plane([&](int r, int c) -> uint32_t { return p[(size_t)r * W + c]; }, W, H, out, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -284,8 +290,8 @@ __global__ void __launch_bounds__(256, 2) k_gabor_mag(const FaceDesc* __restrict
 // grid = (35, faces), 128 threads.  Gabor planes are 1..35 of the stack.
 __global__ void __launch_bounds__(128) k_gabor_quant_integral(const FaceDesc* __restrict__ fd, const float* __restrict__ mag, size_t mag_face_stride,
                                                               size_t mag_plane_stride, const uint32_t* __restrict__ minmax,
-                                                              uint32_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride, int first_plane,
-                                                              uint8_t* __restrict__ u8planes, size_t u8_face_stride) {
+                                                              stack_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride, int first_plane,
+                                                              uint8_t* __restrict__ u8planes, size_t u8_face_stride, uint32_t* __restrict__ dbg32) {
   const FaceDesc d = fd[blockIdx.y];
   const int gp = blockIdx.x;
   const float* __restrict__ m = mag + blockIdx.y * mag_face_stride + (size_t)gp * mag_plane_stride;
@@ -295,13 +301,14 @@ __global__ void __launch_bounds__(128) k_gabor_quant_integral(const FaceDesc* __
   const double dshift = 0.0 - smin * dscale;
   const float a = (float)dscale, b = (float)dshift;
   const int plane = first_plane + gp;
-  uint32_t* out = stacks + blockIdx.y * stack_face_stride + (size_t)plane * plane_stride;
+  stack_t* out = stacks + blockIdx.y * stack_face_stride + (size_t)plane * plane_stride;
   uint8_t* u8o = u8planes ? u8planes + blockIdx.y * u8_face_stride + (size_t)plane * d.W * d.H : nullptr;
+  uint32_t* o32 = dbg32 ? dbg32 + blockIdx.y * stack_face_stride + (size_t)plane * plane_stride : nullptr;
   integral_plane([&](int r, int c) -> uint32_t {
     const float v = __fmaf_rn(m[(size_t)r * 128 + c], a, b);
     const int iv = __float2int_rn(__fmul_rn(v, 255.f));
     return (uint32_t)min(max(iv, 0), 255);
-  }, d.W, d.H, out, u8o);
+  }, d.W, d.H, out, u8o, o32);
 }
 
 __global__ void k_init_minmax(uint32_t* mm, int n) {
@@ -322,7 +329,7 @@ __global__ void k_init_minmax(uint32_t* mm, int n) {
 // ---------------------------------------------------------------------------------------------
 struct TraverseArgs {
   const FaceDesc* fd;
-  const uint32_t* stacks;
+  const stack_t* stacks;
   size_t stack_face_stride, plane_stride;
   const DevSlot* slots;
   const int32_t* roots;        // shared tree list (head pose) or nullptr
@@ -337,11 +344,28 @@ struct TraverseArgs {
   int cnt_tests, cnt_trav;
 };
 
-__device__ __forceinline__ uint32_t ldg_corner(const uint32_t* p, bool no_alloc) {
-  uint32_t v;
-  if (no_alloc) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  else v = __ldg(p);
-  return v;
+__device__ __forceinline__ uint32_t ldg_corner(const stack_t* p, bool no_alloc) {
+  if (no_alloc) {
+    if (kStack16) { uint16_t v; asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p)); return v; }
+    uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+  }
+  return __ldg(p);
+}
+
+// Sum of one rectangle from the modulo-2^16 integral: `ns` strips, each exact (device_forest.h).
+template <bool NA>
+__device__ __forceinline__ uint32_t rect_sum_strips(const stack_t* __restrict__ p, uint32_t a, uint32_t w, uint32_t ns, uint32_t hs, uint32_t hl) {
+  uint32_t L = ldg_corner(p + a, NA), R = ldg_corner(p + a + w, NA);
+  uint32_t s = 0;
+  for (uint32_t k = 1; k < ns; k++) {
+    a += hs;
+    const uint32_t L2 = ldg_corner(p + a, NA), R2 = ldg_corner(p + a + w, NA);
+    s += (R2 - L2 - R + L) & kSumMask;
+    L = L2; R = R2;
+  }
+  a += hl;
+  const uint32_t L2 = ldg_corner(p + a, NA), R2 = ldg_corner(p + a + w, NA);
+  return s + ((R2 - L2 - R + L) & kSumMask);
 }
 
 // LW = lanes along x (32: one row of 32 x-adjacent patches; 8: an 8 x 4 block of patches).
@@ -362,7 +386,7 @@ __global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
   const bool active = ix < nx && iy < ny;
   const int nt = a.face_ntrees ? a.face_ntrees[f] : a.ntrees;
   const int32_t* roots = a.face_roots ? a.face_roots + (size_t)f * kMaxList : a.roots;
-  const uint32_t* __restrict__ origin = a.stacks + f * a.stack_face_stride + (size_t)((active ? iy : 0) * a.stride) * kRowStride + (active ? ix : 0) * a.stride;
+  const stack_t* __restrict__ origin = a.stacks + f * a.stack_face_stride + (size_t)((active ? iy : 0) * a.stride) * kRowStride + (active ? ix : 0) * a.stride;
   const DevSlot* __restrict__ slots = a.slots;
   constexpr bool NA = (MODE & 1) != 0;
   unsigned tests = 0;
@@ -379,17 +403,25 @@ __global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
           q0 = __ldg(reinterpret_cast<const uint4*>(slots + cur));
           q1 = __ldg(reinterpret_cast<const uint4*>(slots + cur) + 1);
         }
-        // q0.x = a1 | c1<<16 ; q0.y = a2 | c2<<16 ; q0.z = w1 | w2<<8 | ch<<16 | leaf<<24 ; q0.w = thr (low 16)
-        // q1.x = m1 ; q1.y = m2 ; q1.z = child
-        if (q0.z >> 24) { leaf = a.leaf_value ? __float_as_int(__ldg(a.leaf_value + q1.z)) : (int)q1.z; break; }
-        const uint32_t* __restrict__ p = origin + (size_t)((q0.z >> 16) & 0xff) * a.plane_stride;
-        const uint32_t a1 = q0.x & 0xffff, c1 = q0.x >> 16, a2 = q0.y & 0xffff, c2 = q0.y >> 16, w1 = q0.z & 0xff, w2 = (q0.z >> 8) & 0xff;
-        const uint32_t A1 = ldg_corner(p + a1, NA), B1 = ldg_corner(p + a1 + w1, NA), C1 = ldg_corner(p + a1 + c1, NA), D1 = ldg_corner(p + a1 + c1 + w1, NA);
-        const uint32_t A2 = ldg_corner(p + a2, NA), B2 = ldg_corner(p + a2 + w2, NA), C2 = ldg_corner(p + a2 + c2, NA), D2 = ldg_corner(p + a2 + c2 + w2, NA);
-        const uint32_t s1 = D1 - B1 - C1 + A1, s2 = D2 - B2 - C2 + A2;
-        const int m1 = (int)__umulhi(s1 << 1, q1.x), m2 = (int)__umulhi(s2 << 1, q1.y);
-        const int thr = (int)(short)(q0.w & 0xffff);
-        cur = (int)q1.z + ((m1 - m2) > thr ? 1 : 0);  // go left iff mean1 - mean2 <= threshold
+        // q0.x = a1 | w1<<16 | ns1<<24 ; q0.y = hs1 | hl1<<16 ; q0.z, q0.w = the same for rect2
+        // q1.x = ch | leaf<<8 | thr<<16 ; q1.y = m1 ; q1.z = m2 ; q1.w = child
+        if ((q1.x >> 8) & 0xff) { leaf = a.leaf_value ? __float_as_int(__ldg(a.leaf_value + q1.w)) : (int)q1.w; break; }
+        const stack_t* __restrict__ p = origin + (size_t)(q1.x & 0xff) * a.plane_stride;
+        const uint32_t a1 = q0.x & 0xffff, w1 = (q0.x >> 16) & 0xff, ns1 = q0.x >> 24, a2 = q0.z & 0xffff, w2 = (q0.z >> 16) & 0xff, ns2 = q0.z >> 24;
+        uint32_t s1, s2;
+        if (!kStack16 || (ns1 | ns2) == 1) {  // both rectangles in one strip (always, with 32-bit planes): 8 independent loads
+          const uint32_t e1 = a1 + (q0.y >> 16), e2 = a2 + (q0.w >> 16);
+          const uint32_t A1 = ldg_corner(p + a1, NA), B1 = ldg_corner(p + a1 + w1, NA), C1 = ldg_corner(p + e1, NA), D1 = ldg_corner(p + e1 + w1, NA);
+          const uint32_t A2 = ldg_corner(p + a2, NA), B2 = ldg_corner(p + a2 + w2, NA), C2 = ldg_corner(p + e2, NA), D2 = ldg_corner(p + e2 + w2, NA);
+          s1 = (D1 - B1 - C1 + A1) & kSumMask;
+          s2 = (D2 - B2 - C2 + A2) & kSumMask;
+        } else {
+          s1 = rect_sum_strips<NA>(p, a1, w1, ns1, q0.y & 0xffff, q0.y >> 16);
+          s2 = rect_sum_strips<NA>(p, a2, w2, ns2, q0.w & 0xffff, q0.w >> 16);
+        }
+        const int m1 = (int)__umulhi(s1 << 1, q1.y), m2 = (int)__umulhi(s2 << 1, q1.z);
+        const int thr = (int)(short)(q1.x >> 16);
+        cur = (int)q1.w + ((m1 - m2) > thr ? 1 : 0);  // go left iff mean1 - mean2 <= threshold
         if (COUNT) tests++;
       }
     }

@@ -1,4 +1,5 @@
 // Packs host-side FlatForests into the device image (device_forest.h).
+#include <algorithm>
 #include <deque>
 
 #include "../../include/crf_b200.h"
@@ -88,12 +89,19 @@ int pack_forests(const std::vector<const FlatForest*>& forests, ForestKind kind,
           const uint32_t area1 = (uint32_t)n.r1[2] * n.r1[3], area2 = (uint32_t)n.r2[2] * n.r2[3];
           if (area1 == 0 || area2 == 0) { err = "empty rectangle"; return CRF_ERR_UNSUPPORTED; }
           if (n.r1[0] + n.r1[2] > kPatch || n.r1[1] + n.r1[3] > kPatch || n.r2[0] + n.r2[2] > kPatch || n.r2[1] + n.r2[3] > kPatch) { err = "rectangle leaves the patch"; return CRF_ERR_UNSUPPORTED; }
+          auto strips = [](int w, int h, uint8_t& ns, uint16_t& hs, uint16_t& hl) {
+            const int rows = std::max(1, kStripArea / w);          // rows per strip so that w * rows <= 257
+            const int n_ = (h + rows - 1) / rows;
+            ns = (uint8_t)n_;
+            hs = (uint16_t)(rows * kRowStride);
+            hl = (uint16_t)((h - (n_ - 1) * rows) * kRowStride);
+          };
           s.a1 = (uint16_t)(n.r1[1] * kRowStride + n.r1[0]);
-          s.c1 = (uint16_t)(n.r1[3] * kRowStride);
           s.w1 = n.r1[2];
+          strips(n.r1[2], n.r1[3], s.ns1, s.hs1, s.hl1);
           s.a2 = (uint16_t)(n.r2[1] * kRowStride + n.r2[0]);
-          s.c2 = (uint16_t)(n.r2[3] * kRowStride);
           s.w2 = n.r2[2];
+          strips(n.r2[2], n.r2[3], s.ns2, s.hs2, s.hl2);
           s.ch = n.channel;
           s.thr = n.threshold;
           s.m1 = magic_for_area(area1);

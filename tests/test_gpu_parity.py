@@ -108,6 +108,22 @@ def test_forest_leaf_ids_synthetic_model(O, sctx, synth_models, stride, H, W):
     s.close()
 
 
+def test_forest_large_rectangles(crf, O, gpu, tmp_path):
+    """Rectangles up to 30x30 (area 900): the modulo-2^16 integral layout needs up to 4 strips per rectangle."""
+    from face_alignment_cvpr_2012_b200 import synthetic_model as sm
+    hp, ffd = sm.write_model(tmp_path / "bigrect", seed=9, hp_depth=9, ffd_depth=9, max_rect=30)
+    gm, om = crf.Model(hp, ffd, 15, 20), O.Model(hp, ffd, 15, 20)
+    ctx = crf.Context(gm, 0)
+    rng = np.random.default_rng(12)
+    for planes in (_planes(rng, 38, 125, 125), np.full((38, 125, 125), 255, np.uint8), _planes(rng, 38, 140, 124, smooth=False)):
+        s = O.Sample(planes=planes)
+        ids_o, _, _, _ = om.eval_hp(s, 2)
+        assert np.array_equal(ctx.stage_eval_forest(planes, 2), ids_o)
+        fi = rng.integers(0, 5, 20); ti = rng.integers(0, 20, 20)
+        assert np.array_equal(ctx.stage_eval_forest(planes, 3, fi, ti), om.eval_ffd(s, fi, ti, 3)["leaf_ids"])
+        s.close()
+
+
 def test_forest_errors(crf, sctx):
     planes = np.zeros((10, 125, 125), np.uint8)
     with pytest.raises(crf.CrfError):  # forests read channels up to 37
