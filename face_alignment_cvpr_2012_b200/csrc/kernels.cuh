@@ -285,6 +285,116 @@ __global__ void __launch_bounds__(256, 2) k_gabor_mag(const FaceDesc* __restrict
   }
 }
 
+// a6 for the 9x9 .. 25x25 kernels: all 7 orientations of one scale per thread, symmetric-pair accumulation.
+// The Gabor real part is exactly even and the imaginary part exactly odd under (x,y) -> (-x,-y) (checked on the host
+// when the bank is built), so the canonical sum for these sizes (cv2 itself takes a DFT path here) is
+//   re = fmaf(p(t) + p(mirror t), k_re(t), re),  im = fmaf(p(t) - p(mirror t), k_im(t), im)
+// over the first half of the kernel in raster order, then the centre tap for re.  The exact pixel sum / difference is
+// shared by the 7 orientations: 2 adds + 14 FFMA per (tap pair, pixel) instead of 28 FFMA.
+// One CTA = a 16-row band of one face; a thread owns a 1 x 4 strip and 56 accumulators.
+// coef: [ (K*K+1)/2 taps ][8] float2 (re, im) per orientation, slot 7 unused (keeps LDS.128 alignment).
+// grid = (bands, faces), 256 threads.
+template <int K>
+__global__ void __launch_bounds__(256) k_gabor_sym(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
+                                                   const float4* __restrict__ coef, int nu, float* __restrict__ mag, size_t mag_face_stride,
+                                                   size_t mag_plane_stride, uint32_t* __restrict__ minmax) {
+  using G = GaborGeom<K>;
+  constexpr int R = K / 2, NT = (K * K + 1) / 2;   // first-half taps + centre
+  __shared__ __align__(16) float tile[G::TH][G::PITCH];
+  __shared__ __align__(16) float4 cf[NT][4];        // [tap][(re0,im0,re1,im1), (re2..), (re4..), (re6,im6,-,-)]
+  const FaceDesc d = fd[blockIdx.y];
+  const int W = d.W, H = d.H;
+  const int r0 = blockIdx.x * G::BAND;
+  if (r0 >= H) return;
+  const int tid = threadIdx.x;
+  const uint8_t* __restrict__ g = scaled + blockIdx.y * scaled_face_stride;
+  for (int i = tid; i < NT * 4; i += 256) (&cf[0][0])[i] = coef[i];
+  for (int i = tid; i < G::TH * G::PITCH; i += 256) {
+    const int ty = i / G::PITCH, tx = i - ty * G::PITCH;
+    const int sy = border101(r0 + ty - R, H), sx = border101(tx - R, W);
+    tile[ty][tx] = (float)g[(size_t)sy * 128 + sx];
+  }
+  __syncthreads();
+  const int x0 = (tid & 31) * 4;
+  float vmin[7], vmax[7];
+#pragma unroll
+  for (int m = 0; m < 7; m++) { vmin[m] = __int_as_float(0x7f800000); vmax[m] = 0.f; }
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    const int r = (tid >> 5) + 8 * pass;
+    float re[7][4], im[7][4];
+#pragma unroll
+    for (int m = 0; m < 7; m++)
+#pragma unroll
+      for (int o = 0; o < 4; o++) { re[m][o] = 0.f; im[m][o] = 0.f; }
+#pragma unroll 1
+    for (int j = 0; j <= R; j++) {
+      const float* top = &tile[r + j][x0];
+      const float* bot = &tile[r + K - 1 - j][x0];
+      const int ni = j < R ? K : R;   // the centre row contributes only the taps left of the centre
+      // sliding windows: wt = top[i .. i+3], wb = bot[K-1-i .. K-1-i+3]
+      float wt0 = top[0], wt1 = top[1], wt2 = top[2], wt3 = top[3];
+      float wb0 = bot[K - 1], wb1 = bot[K], wb2 = bot[K + 1], wb3 = bot[K + 2];
+      const float4* c4 = &cf[j * K][0];
+#pragma unroll 1
+      for (int i = 0; i < ni; i++) {
+        const float4 ca = c4[0], cb = c4[1], cc = c4[2], cd = c4[3];
+        c4 += 4;
+        const float s[4] = {wt0 + wb0, wt1 + wb1, wt2 + wb2, wt3 + wb3};
+        const float df[4] = {wt0 - wb0, wt1 - wb1, wt2 - wb2, wt3 - wb3};
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+          re[0][o] = __fmaf_rn(s[o], ca.x, re[0][o]); im[0][o] = __fmaf_rn(df[o], ca.y, im[0][o]);
+          re[1][o] = __fmaf_rn(s[o], ca.z, re[1][o]); im[1][o] = __fmaf_rn(df[o], ca.w, im[1][o]);
+          re[2][o] = __fmaf_rn(s[o], cb.x, re[2][o]); im[2][o] = __fmaf_rn(df[o], cb.y, im[2][o]);
+          re[3][o] = __fmaf_rn(s[o], cb.z, re[3][o]); im[3][o] = __fmaf_rn(df[o], cb.w, im[3][o]);
+          re[4][o] = __fmaf_rn(s[o], cc.x, re[4][o]); im[4][o] = __fmaf_rn(df[o], cc.y, im[4][o]);
+          re[5][o] = __fmaf_rn(s[o], cc.z, re[5][o]); im[5][o] = __fmaf_rn(df[o], cc.w, im[5][o]);
+          re[6][o] = __fmaf_rn(s[o], cd.x, re[6][o]); im[6][o] = __fmaf_rn(df[o], cd.y, im[6][o]);
+        }
+        // slide: top window moves right, bottom window moves left
+        wt0 = wt1; wt1 = wt2; wt2 = wt3; wt3 = top[i + 4];
+        wb3 = wb2; wb2 = wb1; wb1 = wb0; wb0 = bot[K - 2 - i];
+      }
+    }
+    {  // centre tap (real part only: the imaginary coefficient is exactly 0)
+      const float4 ca = cf[NT - 1][0], cb = cf[NT - 1][1], cc = cf[NT - 1][2], cd = cf[NT - 1][3];
+      const float* mid = &tile[r + R][x0 + R];
+#pragma unroll
+      for (int o = 0; o < 4; o++) {
+        const float p = mid[o];
+        re[0][o] = __fmaf_rn(p, ca.x, re[0][o]); re[1][o] = __fmaf_rn(p, ca.z, re[1][o]);
+        re[2][o] = __fmaf_rn(p, cb.x, re[2][o]); re[3][o] = __fmaf_rn(p, cb.z, re[3][o]);
+        re[4][o] = __fmaf_rn(p, cc.x, re[4][o]); re[5][o] = __fmaf_rn(p, cc.z, re[5][o]);
+        re[6][o] = __fmaf_rn(p, cd.x, re[6][o]);
+      }
+    }
+    if (r0 + r < H) {
+#pragma unroll
+      for (int m = 0; m < 7; m++) {
+        float v[4];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+          v[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[m][o], im[m][o]), __fmul_rn(re[m][o], re[m][o])));
+          if (x0 + o < W) { vmin[m] = fminf(vmin[m], v[o]); vmax[m] = fmaxf(vmax[m], v[o]); }
+        }
+        float* mplane = mag + blockIdx.y * mag_face_stride + (size_t)(nu * 7 + m) * mag_plane_stride;
+        *reinterpret_cast<float4*>(&mplane[(size_t)(r0 + r) * 128 + x0]) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 7; m++) {
+    const uint32_t umin = __reduce_min_sync(0xffffffffu, __float_as_uint(vmin[m]));
+    const uint32_t umax = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax[m]));
+    if ((tid & 31) == 0) {
+      uint32_t* mm = minmax + ((size_t)blockIdx.y * 35 + nu * 7 + m) * 2;
+      atomicMin(&mm[0], umin);
+      atomicMax(&mm[1], umax);
+    }
+  }
+}
+
 // a6, second half: cv::normalize(NORM_MINMAX, 0, 1) as one single-rounded FMA, convertTo(8U, x255)
 // with round-half-even, then cv::integral (FeatureChannelFactory.hpp:271-283).
 // grid = (35, faces), 128 threads.  Gabor planes are 1..35 of the stack.

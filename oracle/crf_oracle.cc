@@ -461,7 +461,11 @@ static const std::vector<GaborKernel>& gabor_bank() {
 // match bit for bit, so the canonical form there is acc = fmaf(px, k, acc) (one rounding per tap, the
 // more accurate direct sum); its distance to cv2 is pinned statistically (+-1 LSB of the u8 plane).
 // Skipping exact-zero coefficients, as cv2 does, cannot change a value (x + 0*px == x).
-static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int kw, PlaneF& dst) {
+// parity: 0 = plain raster accumulation; +1 / -1 = the kernel is exactly even / odd under (x,y) -> (-x,-y)
+// (Gabor real / imaginary part) and, for kw >= 9, mirrored taps are accumulated as one fused multiply-add of the
+// exact pixel sum / difference:  acc = fmaf(p(t) +- p(mirror t), k(t), acc) over the first half of the kernel in
+// raster order, then the centre tap.
+static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int kw, PlaneF& dst, int parity = 0) {
   const int H = src.rows, W = src.cols, r = kw / 2;
   dst.rows = H; dst.cols = W; dst.d.resize((size_t)H * W);
   // padded float copy so the inner loop is branch-free (thread-local scratch: no malloc churn)
@@ -473,6 +477,33 @@ static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int 
     int sy = border101(y - r, H);
     for (int x = 0; x < PW; x++) pad[(size_t)y * PW + x] = (float)src.at(sy, border101(x - r, W));
   }
+  acc.resize((size_t)W);
+  if (kw >= 9 && parity != 0) {
+    const int centre = r * kw + r;
+    for (int t = 0; t < centre; t++) {   // the symmetry is a property of the coefficient tables; checked, not assumed
+      const float a = kern[(size_t)t], b = kern[(size_t)(kw * kw - 1 - t)];
+      if ((parity > 0 && a != b) || (parity < 0 && a != -b)) { std::fprintf(stderr, "gabor kernel is not %s\n", parity > 0 ? "even" : "odd"); std::abort(); }
+    }
+    for (int y = 0; y < H; y++) {
+      std::fill(acc.begin(), acc.end(), 0.f);
+      float* __restrict a = acc.data();
+      for (int t = 0; t < centre; t++) {
+        const int j = t / kw, i = t - j * kw;
+        const float* __restrict top = &pad[(size_t)(y + j) * PW + i];
+        const float* __restrict bot = &pad[(size_t)(y + kw - 1 - j) * PW + (kw - 1 - i)];
+        const float k = kern[(size_t)t];
+        if (parity > 0) for (int x = 0; x < W; x++) a[x] = std::fmaf(top[x] + bot[x], k, a[x]);
+        else            for (int x = 0; x < W; x++) a[x] = std::fmaf(top[x] - bot[x], k, a[x]);
+      }
+      if (parity > 0) {
+        const float* __restrict mid = &pad[(size_t)(y + r) * PW + r];
+        const float k = kern[(size_t)centre];
+        for (int x = 0; x < W; x++) a[x] = std::fmaf(mid[x], k, a[x]);
+      }
+      std::memcpy(&dst.d[(size_t)y * W], a, sizeof(float) * (size_t)W);
+    }
+    return;
+  }
   std::vector<int> tap_off; std::vector<float> tap_k;
   for (int j = 0; j < kw; j++)
     for (int i = 0; i < kw; i++) {
@@ -483,22 +514,13 @@ static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int 
   const size_t nt = tap_k.size();
   // Row-at-a-time so the compiler can vectorise ACROSS pixels; every pixel still sees its taps in
   // raster order with separately rounded product and sum (build uses -ffp-contract=off).
-  acc.resize((size_t)W);
   for (int y = 0; y < H; y++) {
     std::fill(acc.begin(), acc.end(), 0.f);
     float* __restrict a = acc.data();
-    if (kw >= 9) {   // one fused multiply-add per tap (cv2 takes its DFT path for these sizes: no direct-sum order is "the" reference)
-      for (size_t t = 0; t < nt; t++) {
-        const float* __restrict row = &pad[(size_t)y * PW + tap_off[t]];
-        const float k = tap_k[t];
-        for (int x = 0; x < W; x++) a[x] = std::fmaf(row[x], k, a[x]);
-      }
-    } else {         // 7x7: separately rounded product and sum == cv2's filter2D bit for bit
-      for (size_t t = 0; t < nt; t++) {
-        const float* __restrict row = &pad[(size_t)y * PW + tap_off[t]];
-        const float k = tap_k[t];
-        for (int x = 0; x < W; x++) a[x] = a[x] + row[x] * k;
-      }
+    for (size_t t = 0; t < nt; t++) {
+      const float* __restrict row = &pad[(size_t)y * PW + tap_off[t]];
+      const float k = tap_k[t];
+      for (int x = 0; x < W; x++) a[x] = a[x] + row[x] * k;   // 7x7 (and any non-Gabor kernel): == cv2's filter2D bit for bit
     }
     std::memcpy(&dst.d[(size_t)y * W], a, sizeof(float) * (size_t)W);
   }
@@ -508,8 +530,8 @@ static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int 
 static void gabor_transform(const Plane8& src, const GaborKernel& gk, Plane8& out8) {
   static thread_local PlaneF r_mat, i_mat;
   static thread_local std::vector<float> mag;
-  filter2d_f32(src, gk.re, gk.width, r_mat);
-  filter2d_f32(src, gk.im, gk.width, i_mat);
+  filter2d_f32(src, gk.re, gk.width, r_mat, +1);
+  filter2d_f32(src, gk.im, gk.width, i_mat, -1);
   const size_t n = r_mat.d.size();
   mag.resize(n);
   double smin = 0, smax = 0;
