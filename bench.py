@@ -41,6 +41,20 @@ CROP = 100
 WORKLOAD = "C2: batch of 4096 synthetic 100x100 face crops per GPU, head-pose forest + FFD forest, dense stride-1 patches"
 
 
+def ncu_traffic(faces: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the FFD traversal launch from the committed `ncu --set full`
+    capture of this workload (profiles/r1_traffic.json, written by tools/ncu_traffic.py), scaled to the faces per launch."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    if not p.exists():
+        return None, None
+    try:
+        t = json.loads(p.read_text())
+        k = t["k_traverse_ffd"]
+        return k["dram_bytes_per_launch"] * faces / k["faces_per_launch"], f"{p.name}: ncu capture at {k['faces_per_launch']} faces/launch, scaled per face"
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -259,7 +273,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         gabor_ms = stage_ms["gabor"] / args.steps
         gabor_flops = 35980.0 * 125 * 125 * F
         sm_clock = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-        fp32_peak = 148 * 128 * 2 * sm_clock * 1e6 / 1e12  # non-tensor FMA peak at the clock seen; mul+add issue as 2 instructions -> 1/2 of it
+        fp32_peak = 148 * 128 * 2 * sm_clock * 1e6 / 1e12  # non-tensor FMA peak at the clock seen
+        launches_ffd = max(stage_launches["ffd_traverse"] // args.steps, 1)
+        traffic, traffic_src = ncu_traffic(F // launches_ffd)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+int32",
@@ -272,16 +288,17 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_traverse (FFD forest, stride 1)", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
-                         "alg_bytes_per_launch": alg_bytes / max(stage_launches["ffd_traverse"] // args.steps, 1), "ms_per_step": ffd_ms,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+                         "alg_bytes_per_launch": alg_bytes / launches_ffd, "launches_per_step": launches_ffd, "ms_per_step": ffd_ms,
                          "note": "gather working set (integral stacks of the faces in flight + 55 MB of node records) is L2-resident, so the HBM-equivalent "
                                  "fraction can exceed 1; see profiles/ for dram bytes and L2 throughput"},
             "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "kernels": [
                 {"kernel": "k_traverse (head-pose forest)", "bound": "hbm", "ms_per_step": hp_ms,
                  "achieved": (48 * work["hp_node_tests"] + 4 * work["hp_traversals"]) / (hp_ms * 1e-3) / 1e9 if hp_ms > 0 else 0.0, "unit": "GB/s"},
-                {"kernel": "k_gabor_mag x5 + quantise/integral", "bound": "fp32 (non-tensor, unfused mul+add)", "ms_per_step": gabor_ms,
-                 "achieved": gabor_flops / (gabor_ms * 1e-3) / 1e12 if gabor_ms > 0 else 0.0, "peak": fp32_peak / 2, "unit": "TFLOP/s"},
+                {"kernel": "k_gabor_sym<9..25> + k_gabor_mag<7> + quantise/integral", "bound": "fp32 issue (non-tensor FFMA)", "ms_per_step": gabor_ms,
+                 "achieved": gabor_flops / (gabor_ms * 1e-3) / 1e12 if gabor_ms > 0 else 0.0, "peak": fp32_peak, "unit": "TFLOP/s",
+                 "note": "achieved = direct-form FLOPs (35 980 per pixel, SURVEY 8d) / time; the symmetric-pair kernel executes 0.57 instructions per direct-form MAC"},
             ],
             "work_per_step": {k: work[k] for k in ("hp_node_tests", "ffd_node_tests", "hp_traversals", "ffd_traversals", "votes", "vote_passes")},
         }

@@ -50,10 +50,12 @@ static_assert(sizeof(DevSlot) == 32, "slot must be one 32-byte sector");
 
 // MPLeaf (include/MPSample.hpp:137-159) with the vote predicate of src/face_utils.cpp:285-290 folded
 // into `mask` (bit i: part i votes) for the options of the context.
-struct DevMpLeaf {
+struct alignas(16) DevMpLeaf {   // 48 bytes: three 128-bit loads
   int16_t off[kParts][2];
   float weight;  // forground
+  uint32_t pad;
 };
+static_assert(sizeof(DevMpLeaf) == 48, "leaf record is three 16-byte words");
 
 struct PackedForest {
   std::vector<DevSlot> slots;

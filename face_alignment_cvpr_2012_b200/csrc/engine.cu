@@ -140,7 +140,8 @@ struct crf_ctx {
   // 1 = consecutive chunks run back to back on one stream (default: measured faster — co-resident Gabor CTAs shrink the L1
   // the gathers live on, and two chunks' stacks thrash L2); 2 = alternate chunks between two streams / work sets
   int nstreams = 1;
-  size_t work_budget = (size_t)24 << 30;  // bytes of work buffers the two sets may use together (min(24 GB, half of the free memory at creation))
+  int ms_variant = 3;   // resident MeanShift CTAs per SM the kernel is compiled for (register cap); CRF_MS_VARIANT overrides
+  size_t work_budget = (size_t)64 << 30;  // bytes of work buffers a launch may use (min(64 GB, half of the free memory at creation))
   StageTimer timer;
 };
 
@@ -334,9 +335,13 @@ static int launch_hp_reduce(crf_ctx* c, const FaceDesc* fd, int n, int stride, b
 static int launch_meanshift(crf_ctx* c, const FaceDesc* fd, int nchains, crf_face_t* faces) {
   Span s(c, CRF_STAGE_MEANSHIFT);
   MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
-  k_meanshift<<<(nchains + kFoldChains - 1) / kFoldChains, kFoldThreads, kMsSmem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap,
-                                                                                       c->w->d_vote_counts.as<int32_t>(), c->w->d_vote_base.as<int32_t>(), mo, faces,
-                                                                                       c->counting ? c->d_counters.as<unsigned long long>() : nullptr);
+  const dim3 grid((nchains + kFoldChains - 1) / kFoldChains);
+  unsigned long long* cnt = c->counting ? c->d_counters.as<unsigned long long>() : nullptr;
+#define CRF_MS(MINB)                                                                                                                                    \
+  k_meanshift<MINB><<<grid, kFoldThreads, kMsSmem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(), \
+                                                                  c->w->d_vote_base.as<int32_t>(), mo, faces, cnt)
+  if (c->ms_variant == 2) CRF_MS(2); else if (c->ms_variant == 4) CRF_MS(4); else CRF_MS(3);
+#undef CRF_MS
   KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
   return CRF_OK;
 }
@@ -375,7 +380,7 @@ static int run_faces(crf_ctx* c, const FaceDesc* d_fd, int n, int Hmax, const ui
 }
 
 // Faces resident per launch: as many as fit a work-buffer budget (the ordered vote lists are sized for the worst
-// case of every leaf voting for every part), at most 1024 unless the caller asks otherwise.  Latency-bound tails
+// case of every leaf voting for every part), at most 4096 unless the caller asks otherwise.  Latency-bound tails
 // (sequential folds) want many faces in flight; nothing else depends on the choice (results are chunk-invariant).
 static int pick_chunk(const crf_ctx* c, int Hmax, bool headpose_only) {
   const size_t np_hp = (size_t)patches_1d(125, c->opt.hp_stride) * patches_1d(Hmax, c->opt.hp_stride);
@@ -384,7 +389,7 @@ static int pick_chunk(const crf_ctx* c, int Hmax, bool headpose_only) {
                           np_ffd * c->mp_ntrees_cfg * (4 + 3 * sizeof(DevVote)) + 4096;
   const size_t budget = c->work_budget / c->nstreams;
   long long chunk = (long long)(budget / per_face);
-  const int cap = c->opt.max_chunk > 0 ? c->opt.max_chunk : 2048;
+  const int cap = c->opt.max_chunk > 0 ? c->opt.max_chunk : 4096;
   return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(chunk, cap), 32768));
 }
 
@@ -641,6 +646,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if (opt) c->opt = *opt; else crf_options_default(&c->opt);
   if (c->opt.hp_stride < 1 || c->opt.ffd_stride < 1) return fail(CRF_ERR_ARG, "strides must be >= 1");
   if (const char* v = std::getenv("CRF_TRAVERSE_VARIANT")) c->traverse_variant = (int)std::strtol(v, nullptr, 0);
+  if (const char* v = std::getenv("CRF_MS_VARIANT")) c->ms_variant = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_STREAMS")) c->nstreams = std::strtol(v, nullptr, 0) == 2 ? 2 : 1;
   for (auto& w : c->ws) CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -713,7 +719,9 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->work_budget = std::min(c->work_budget, free_b / 2);
   }
   CU(cudaFuncSetAttribute(k_hp_reduce_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHpSmem));
-  CU(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+  CU(cudaFuncSetAttribute(k_meanshift<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+  CU(cudaFuncSetAttribute(k_meanshift<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+  CU(cudaFuncSetAttribute(k_meanshift<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
   if ((rc = c->d_counters.reserve(sizeof(unsigned long long) * CNT_NUM))) return rc;
   CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * CNT_NUM, c->w->stream));
   if ((rc = c->d_misc.reserve(4096))) return rc;

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) k_gabor_sym(const FaceDesc* __restrict__ 
       float wt0 = top[0], wt1 = top[1], wt2 = top[2], wt3 = top[3];
       float wb0 = bot[K - 1], wb1 = bot[K], wb2 = bot[K + 1], wb3 = bot[K + 2];
       const float4* c4 = &cf[j * K][0];
-#pragma unroll 1
+#pragma unroll 4
       for (int i = 0; i < ni; i++) {
         const float4 ca = c4[0], cb = c4[1], cc = c4[2], cd = c4[3];
         c4 += 4;
@@ -768,11 +768,18 @@ __global__ void __launch_bounds__(256) k_votes_count(VoteArgs a) {
   vote_segment(a, f, seg, n, k0, k1, nt, ny);
   const int32_t* __restrict__ ids = a.leaf_ids + f * a.leaf_face_stride;
   int cnt = 0;  // lane p < kParts accumulates part p
-  for (int k = k0 + lane; k - lane < k1; k += 32) {
-    const unsigned mask = k < k1 ? (unsigned)__ldg(a.mp_mask + ids[k]) : 0u;
+  for (int kb = k0; kb < k1; kb += 128) {   // four steps per trip: the id -> mask gathers of all four are in flight together
+    int id[4];
+    unsigned mask[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int k = kb + u * 32 + lane; id[u] = k < k1 ? ids[k] : -1; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) mask[u] = id[u] >= 0 ? (unsigned)__ldg(a.mp_mask + id[u]) : 0u;
 #pragma unroll
     for (int p = 0; p < kParts; p++) {
-      const int c = __popc(__ballot_sync(0xffffffffu, (mask >> p) & 1u));
+      int c = 0;
+#pragma unroll
+      for (int u = 0; u < 4; u++) c += __popc(__ballot_sync(0xffffffffu, (mask[u] >> p) & 1u));
       if (lane == p) cnt += c;
     }
   }
@@ -810,10 +817,14 @@ __global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
   }
   const int32_t* __restrict__ ids = a.leaf_ids + f * a.leaf_face_stride;
   DevVote* __restrict__ fv = a.votes + (size_t)f * a.vote_cap;
+  int leaf_n = 0;
+  unsigned mask_n = 0;
+  if (k0 + lane < k1) { leaf_n = ids[k0 + lane]; mask_n = __ldg(a.mp_mask + leaf_n); }
   for (int k = k0 + lane; k - lane < k1; k += 32) {
-    int leaf = 0;
-    unsigned mask = 0;
-    if (k < k1) { leaf = ids[k]; mask = __ldg(a.mp_mask + leaf); }
+    const int leaf = leaf_n;
+    const unsigned mask = mask_n;
+    leaf_n = 0; mask_n = 0;
+    if (k + 32 < k1) { leaf_n = ids[k + 32]; mask_n = __ldg(a.mp_mask + leaf_n); }   // next step's gathers overlap this step's emission
     unsigned bal[kParts];
 #pragma unroll
     for (int p = 0; p < kParts; p++) bal[p] = __ballot_sync(0xffffffffu, (mask >> p) & 1u);
@@ -821,7 +832,10 @@ __global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
       const int patch = k / nt;
       const int ix = patch / ny, iy = patch - ix * ny;
       const int cx = ix * a.stride + kHalfPatch, cy = iy * a.stride + kHalfPatch;  // patch centre (src/face_utils.cpp:281-282)
-      const DevMpLeaf L = a.mp_leaf[leaf];
+      union { uint4 q[3]; DevMpLeaf L; } u;
+      const uint4* lp = reinterpret_cast<const uint4*>(a.mp_leaf + leaf);
+      u.q[0] = __ldg(lp); u.q[1] = __ldg(lp + 1); u.q[2] = __ldg(lp + 2);
+      const DevMpLeaf& L = u.L;
 #pragma unroll
       for (int p = 0; p < kParts; p++) {
         if ((mask >> p) & 1u) {
@@ -887,7 +901,8 @@ __device__ __forceinline__ void vote_terms(const DevVote q, bool first_pass, flo
 constexpr int kMsTile = 64;
 constexpr size_t kMsSmem = (size_t)2 * 3 * kMsTile * 33 * sizeof(float);  // dynamic shared memory of k_meanshift
 
-__global__ void __launch_bounds__(kFoldThreads, 3) k_meanshift(const FaceDesc* __restrict__ fd, int nchains, const DevVote* __restrict__ votes, size_t vote_cap,
+template <int MINB>
+__global__ void __launch_bounds__(kFoldThreads, MINB) k_meanshift(const FaceDesc* __restrict__ fd, int nchains, const DevVote* __restrict__ votes, size_t vote_cap,
                                                                const int32_t* __restrict__ vote_counts, const int32_t* __restrict__ vote_base, MeanShiftOpt o, crf_face_t* __restrict__ faces,
                                                             unsigned long long* counters) {
   extern __shared__ __align__(16) float s_dyn[];

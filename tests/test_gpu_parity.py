@@ -272,6 +272,33 @@ def test_batch_api_and_chunk_independence(crf, O, synth_models, gpu):
     _check_faces(a, want)
 
 
+def test_mixed_resolution_images(crf, O, synth_models, gpu):
+    """BASELINE config 5 shape: images from 480p to 4K, 1-8 boxes each, face boxes from 64 px to >1000 px wide
+    (heavy down-scaling in cv::resize, tall scaled faces), each image through crf_analyze_faces."""
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, om = synth_models
+    ctx = crf.Context(gm, 0)
+    imgs, _ = wl.make_mixed(10, seed=2015)
+    widths = []
+    for frame, boxes in imgs:
+        got = ctx.analyze_faces(frame, boxes)
+        want = np.array([om.analyze_face(frame, b) for b in boxes])
+        _check_faces(got, want)
+        widths += [int(b[2]) for b in boxes]
+    assert min(widths) < 100 and max(widths) > 900
+
+
+def test_headpose_only_many_crops(crf, O, synth_models, gpu):
+    """BASELINE config 4 shape (head-pose forest only, stride 4) on a few hundred crops incl. pure-noise ones."""
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, om = synth_models
+    crops, _ = wl.make_crops(300, seed=2014)
+    got = crf.Context(gm, 0, crf._options(None, max_chunk=128)).analyze_crops(crops, headpose_only=True)
+    idx = list(range(0, 300, 23)) + [7, 15]
+    want = np.array([om.analyze_face(crops[i], (0, 0, 100, 100), headpose_only=True) for i in idx])
+    assert got["headpose"][idx].tobytes() == want["headpose"].tobytes() and got["variance"][idx].tobytes() == want["variance"].tobytes()
+
+
 def test_counters_match_oracle_visits(O, crf, synth_models, gpu):
     from face_alignment_cvpr_2012_b200 import workloads as wl
     gm, om = synth_models
