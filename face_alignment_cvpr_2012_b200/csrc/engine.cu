@@ -302,9 +302,11 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   if (nx <= 0 || ny <= 0) return CRF_OK;
   const size_t smem = (size_t)32 * smem_trees * 4;
   // variant = LW (32 or 8) | MODE << 8 | NW (5 or 10) << 16; CRF_TRAVERSE_VARIANT overrides for experiments
-  const int variant = c->traverse_variant ? c->traverse_variant : ((stride >= 3 ? 8 : 32) | (2 << 8) | (10 << 16));
+  // defaults from tools/traverse_variants.py on B200: one warp per tree for the 15-tree head-pose forest, 10 warps for 20 trees;
+  // rows of 32 x-adjacent patches at dense strides, 8 x 4 blocks at sparse ones; 256-bit slot loads
+  const int variant = c->traverse_variant ? c->traverse_variant : ((stride >= 3 ? 8 : 32) | (2 << 8) | ((hp && stride < 3 ? 15 : 10) << 16));
   const int LW = variant & 0xff, MODE = (variant >> 8) & 0xff, NW = (variant >> 16) & 0xff;
-  const int tiles = LW == 32 ? ((nx + 31) / 32) * ny : ((nx + 7) / 8) * ((ny + 3) / 4);
+  const int tiles = LW != 8 ? ((nx + 31) / 32) * ny : ((nx + 7) / 8) * ((ny + 3) / 4);
   const dim3 grid(tiles, n);
 #define CRF_TRAV(NW_, LW_, MODE_)                                                                          \
   if (NW == NW_ && LW == LW_ && MODE == MODE_) {                                                           \
@@ -313,9 +315,16 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
     launched = true;                                                                                       \
   }
   bool launched = false;
+  static_assert(!kStack16, "k_traverse_pair assumes single-strip rectangles");
+  if (LW == 2) {   // two lanes per patch (MODE unused); tiles as for LW = 32
+    const dim3 g2(((nx + 31) / 32) * ny, n);
+    if (NW == 10) { if (c->counting) k_traverse_pair<10, true><<<g2, 320, smem, c->w->stream>>>(a); else k_traverse_pair<10, false><<<g2, 320, smem, c->w->stream>>>(a); launched = true; }
+    if (NW == 20) { if (c->counting) k_traverse_pair<20, true><<<g2, 640, smem, c->w->stream>>>(a); else k_traverse_pair<20, false><<<g2, 640, smem, c->w->stream>>>(a); launched = true; }
+  }
   CRF_TRAV(5, 32, 0) CRF_TRAV(5, 32, 1) CRF_TRAV(5, 32, 2) CRF_TRAV(5, 32, 3)
   CRF_TRAV(5, 8, 0) CRF_TRAV(5, 8, 1) CRF_TRAV(5, 8, 2) CRF_TRAV(5, 8, 3)
   CRF_TRAV(10, 32, 0) CRF_TRAV(10, 32, 2) CRF_TRAV(10, 8, 2) CRF_TRAV(10, 8, 3)
+  CRF_TRAV(15, 32, 2) CRF_TRAV(20, 32, 2) CRF_TRAV(4, 32, 2) CRF_TRAV(8, 32, 2)
 #undef CRF_TRAV
   if (!launched) return fail(CRF_ERR_ARG, "unknown CRF_TRAVERSE_VARIANT");
   KCHECK(); count_launch(c, stage);
