@@ -315,12 +315,6 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
     launched = true;                                                                                       \
   }
   bool launched = false;
-  static_assert(!kStack16, "k_traverse_pair assumes single-strip rectangles");
-  if (LW == 2) {   // two lanes per patch (MODE unused); tiles as for LW = 32
-    const dim3 g2(((nx + 31) / 32) * ny, n);
-    if (NW == 10) { if (c->counting) k_traverse_pair<10, true><<<g2, 320, smem, c->w->stream>>>(a); else k_traverse_pair<10, false><<<g2, 320, smem, c->w->stream>>>(a); launched = true; }
-    if (NW == 20) { if (c->counting) k_traverse_pair<20, true><<<g2, 640, smem, c->w->stream>>>(a); else k_traverse_pair<20, false><<<g2, 640, smem, c->w->stream>>>(a); launched = true; }
-  }
   CRF_TRAV(5, 32, 0) CRF_TRAV(5, 32, 1) CRF_TRAV(5, 32, 2) CRF_TRAV(5, 32, 3)
   CRF_TRAV(5, 8, 0) CRF_TRAV(5, 8, 1) CRF_TRAV(5, 8, 2) CRF_TRAV(5, 8, 3)
   CRF_TRAV(10, 32, 0) CRF_TRAV(10, 32, 2) CRF_TRAV(10, 8, 2) CRF_TRAV(10, 8, 3)

@@ -554,83 +554,11 @@ __global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
   }
 }
 
-// Two lanes per patch.  ncu on the one-lane-per-patch kernel shows each corner load touching 6.8 cache lines on average
-// (lanes of a warp sit on ~6 different nodes below the top levels) and the L1 data pipe saturated by those wavefronts
-// (l1tex__data_pipe_lsu_wavefronts 94 %).  The two corners of a rectangle row (A,B / C,D) almost always share a line, so
-// here the even lane of a patch loads the left column (A, C) and the odd lane the right column (B, D) IN THE SAME
-// INSTRUCTION: a diverged patch costs one wavefront per rectangle row instead of two.  The halves meet through one
-// shuffle per rectangle: s = (D - B) - (C - A).  A warp covers 16 x-adjacent patches; a CTA the same 32-patch row tile.
-template <int NW, bool COUNT>
-__global__ void __launch_bounds__(NW * 32) k_traverse_pair(TraverseArgs a) {
-  extern __shared__ int32_t s_leaf[];  // [32][nt]
-  const int f = blockIdx.y;
-  const FaceDesc d = a.fd[f];
-  const int nx = (d.W - kPatch + a.stride - 1) / a.stride, ny = (d.H - kPatch + a.stride - 1) / a.stride;
-  const int nxb = (nx + 31) >> 5;
-  const int tile = blockIdx.x;
-  if (nx <= 0 || ny <= 0 || tile >= nxb * ny) return;
-  const int iy = tile / nxb, ixb = tile - iy * nxb;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int side = lane & 1;
-  const int nt = a.face_ntrees ? a.face_ntrees[f] : a.ntrees;
-  const int32_t* roots = a.face_roots ? a.face_roots + (size_t)f * kMaxList : a.roots;
-  const DevSlot* __restrict__ slots = a.slots;
-  const stack_t* __restrict__ row = a.stacks + f * a.stack_face_stride + (size_t)(iy * a.stride) * kRowStride;
-  unsigned tests = 0;
-  for (int item = warp; item < 2 * nt; item += NW) {   // item = (tree, half of the 32-patch tile)
-    const int t = item >> 1;
-    const int pl = ((item & 1) << 4) + (lane >> 1);    // patch of this lane inside the tile
-    const int ix = ixb * 32 + pl;
-    const bool active = ix < nx;
-    const stack_t* __restrict__ origin = row + (active ? ix : 0) * a.stride;
-    int cur = roots[t];
-    int leaf = -1;
-    bool done = !active;
-    while (__any_sync(0xffffffffu, !done)) {
-      uint32_t p1 = 0, p2 = 0, m1q = 0, m2q = 0;
-      int child = 0, thr = 0;
-      bool test = false;
-      if (!done) {
-        uint4 q0, q1;
-        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(slots + cur));
-        if ((q1.x >> 8) & 0xff) {
-          leaf = a.leaf_value ? __float_as_int(__ldg(a.leaf_value + q1.w)) : (int)q1.w;
-          done = true;
-        } else {
-          const stack_t* __restrict__ p = origin + (size_t)(q1.x & 0xff) * a.plane_stride;
-          const uint32_t c1 = (q0.x & 0xffff) + (side ? (q0.x >> 16) & 0xff : 0u);   // a1 (+ w1 for the right column)
-          const uint32_t c2 = (q0.z & 0xffff) + (side ? (q0.z >> 16) & 0xff : 0u);
-          const uint32_t t1 = __ldg(p + c1), b1 = __ldg(p + c1 + (q0.y >> 16));      // hl = h * kRowStride (single strip with 32-bit planes)
-          const uint32_t t2 = __ldg(p + c2), b2 = __ldg(p + c2 + (q0.w >> 16));
-          p1 = b1 - t1; p2 = b2 - t2;
-          m1q = q1.y; m2q = q1.z; child = (int)q1.w; thr = (int)(short)(q1.x >> 16);
-          test = true;
-        }
-      }
-      const uint32_t o1 = __shfl_xor_sync(0xffffffffu, p1, 1), o2 = __shfl_xor_sync(0xffffffffu, p2, 1);
-      if (test) {
-        const uint32_t s1 = side ? p1 - o1 : o1 - p1, s2 = side ? p2 - o2 : o2 - p2;   // (D - B) - (C - A)
-        const int mean1 = (int)__umulhi(s1 << 1, m1q), mean2 = (int)__umulhi(s2 << 1, m2q);
-        cur = child + ((mean1 - mean2) > thr ? 1 : 0);  // go left iff mean1 - mean2 <= threshold
-        if (COUNT) tests += side ^ 1;
-      }
-    }
-    if (!side) s_leaf[pl * nt + t] = leaf;
-  }
-  __syncthreads();
-  const int npatch_tile = min(32, nx - ixb * 32);
-  int32_t* out = a.leaf_out + f * a.leaf_face_stride;
-  for (int i = threadIdx.x; i < npatch_tile * nt; i += NW * 32) {
-    const int l = i / nt, t = i - l * nt;
-    out[((size_t)(ixb * 32 + l) * ny + iy) * nt + t] = s_leaf[i];
-  }
-  if (COUNT) {
-    tests = __reduce_add_sync(0xffffffffu, tests);
-    if (lane == 0 && tests) atomicAdd(&a.counters[a.cnt_tests], (unsigned long long)tests);
-    if (threadIdx.x == 0) atomicAdd(&a.counters[a.cnt_trav], (unsigned long long)npatch_tile * nt);
-  }
-}
+// Measured alternatives that did NOT pay on B200 (tools/traverse_variants.py; kept out of the source): two lanes per
+// patch loading the left / right rectangle columns in one instruction and meeting through a shuffle (halves the cache
+// lines touched per load at diverged levels: 1.4x slower at stride 1, with or without 2-4 trees in flight per lane),
+// L1 no-allocate corner loads (1.2x slower), 8x4 lane blocks at stride 1 (1.2x slower), 16-bit integral planes with
+// strip-split rectangles (1.7x slower, device_forest.h).
 
 // ---------------------------------------------------------------------------------------------
 // a8 (reduce) + a11: head-pose mean/variance in the reference's sequential f32 order

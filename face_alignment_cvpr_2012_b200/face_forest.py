@@ -22,6 +22,7 @@ from .capi import FACE_DTYPE, CrfError, Options, Rect
 class ForestParam:
     """include/Constants.hpp:24-60 — the fields the inference path reads."""
     tree_path: str = ""
+    image_path: str = ""
     ntrees: int = 0
     max_depth: int = 0
     face_size: int = 125
@@ -41,7 +42,7 @@ def loadConfigFile(path: str) -> ForestParam:
         raise FileNotFoundError(f"file not found {path}")
     vals = [lines[i].strip() for i in range(1, len(lines), 2)]
     # order of data/config_*.txt: image index, tree path, ntrees, ntests, max depth, min patches, images, patches, face size, ratio, features
-    p.tree_path = vals[1]; p.ntrees = int(vals[2]); p.max_depth = int(vals[4])
+    p.image_path = vals[0]; p.tree_path = vals[1]; p.ntrees = int(vals[2]); p.max_depth = int(vals[4])
     p.face_size = int(vals[8]); p.patch_size_ratio = float(vals[9]); p.features = [int(v) for v in vals[10].split()]
     return p
 

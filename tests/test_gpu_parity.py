@@ -416,3 +416,28 @@ def test_cpp_compat_header_on_gpu(crf, synth_dirs, synth_models, O, gpu, tmp_pat
     line = [l for l in r.stdout.split("\n") if l.startswith("headpose")][0].split()
     assert abs(float(line[1]) - float(want[0]["headpose"])) < 1e-5 and abs(float(line[2]) - float(want[1]["headpose"])) < 1e-5
     assert line[-1] == f"({want[0]['ffd'][0][0]},{want[0]['ffd'][0][1]})"
+
+
+def test_eval_ffd_driver(crf, staged_models, lfw_faces, lfw_golden, gpu, tmp_path):
+    """the reference's eval_ffd workflow (config files -> annotations -> analyzeFace -> output/errors.txt)
+    on the 20 shipped LFW faces; errors equal the ones derived from the committed oracle records."""
+    from face_alignment_cvpr_2012_b200 import eval as ev, workloads as wl
+    idx = wl.STAGED / "imgs" / "index_random_subset.txt"
+    ann = ev.loadAnnotations(str(idx))
+    assert len(ann) == 20 and ann[0].parts.shape == (10, 2)
+    test10 = ev.split_test(ann)            # 90/10 split per pose class, as src/eval_ffd.cpp:155-169
+    assert 0 < len(test10) <= 5 and len(ev.split_test(ann, everything=True)) == 20
+    ff = crf.FaceForest(model=staged_models[0])
+    out = tmp_path / "output" / "errors.txt"
+    err = ev.evalForest_ffd(ff, ev.split_test(ann, everything=True), str(idx), str(out))
+    assert err.shape == (20, 10) and abs(float(err.mean()) - 0.0747) < 0.01
+    rows = [l.split() for l in out.read_text().strip().split("\n")]
+    assert len(rows) == 20 and all(len(r) == 10 for r in rows)
+    names = lfw_golden["names"].tolist()
+    order = [a for cls in range(-2, 3) for a in ann if a.pose == cls]
+    for a, e in zip(order, err):
+        k = names.index(a.url)
+        gt = lfw_golden["gt"][k].astype(np.float64)
+        iod = np.linalg.norm((gt[0] + gt[1]) / 2 - (gt[6] + gt[7]) / 2)
+        want = np.linalg.norm(gt - lfw_golden["recs"][k]["ffd"], axis=1) / iod
+        assert np.allclose(e, want, rtol=1e-5, atol=1e-6)

@@ -134,4 +134,4 @@ def test_config_file_parser(crf):
         pytest.skip("/root/reference not present")
     p = crf.loadConfigFile(str(cfg))
     assert (p.ntrees, p.max_depth, p.face_size, p.features, p.tree_path) == (20, 20, 125, [0, 1, 2], "data/trees_ffd")
-    assert p.getPatchSize() == 31
+    assert p.getPatchSize() == 31 and p.image_path.endswith("lfw_ffd_ann.txt")
