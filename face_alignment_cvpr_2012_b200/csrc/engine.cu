@@ -338,12 +338,17 @@ static int launch_hp_reduce(crf_ctx* c, const FaceDesc* fd, int n, int stride, b
 static int launch_meanshift(crf_ctx* c, const FaceDesc* fd, int nchains, crf_face_t* faces) {
   Span s(c, CRF_STAGE_MEANSHIFT);
   MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
-  const dim3 grid((nchains + kFoldChains - 1) / kFoldChains);
+  // 32 chains share a fold warp when there are enough chains to fill the GPU; small batches spread over more CTAs
+  const int cpc = nchains >= 8192 ? 32 : (nchains >= 2048 ? 16 : 8);
+  const dim3 grid((nchains + cpc - 1) / cpc);
   unsigned long long* cnt = c->counting ? c->d_counters.as<unsigned long long>() : nullptr;
 #define CRF_MS(MINB)                                                                                                                                    \
-  k_meanshift<MINB><<<grid, kFoldThreads, kMsSmem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(), \
-                                                                  c->w->d_vote_base.as<int32_t>(), mo, faces, cnt)
-  if (c->ms_variant == 2) CRF_MS(2); else if (c->ms_variant == 4) CRF_MS(4); else CRF_MS(3);
+  k_meanshift<MINB, false><<<grid, kFoldThreads, kMsSmem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(), \
+                                                                  c->w->d_vote_base.as<int32_t>(), cpc, mo, faces, cnt)
+  if (cpc < 32)
+    k_meanshift<3, true><<<grid, kFoldThreads, kMsSmem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(),
+                                                                     c->w->d_vote_base.as<int32_t>(), cpc, mo, faces, cnt);
+  else if (c->ms_variant == 2) CRF_MS(2); else if (c->ms_variant == 4) CRF_MS(4); else CRF_MS(3);
 #undef CRF_MS
   KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
   return CRF_OK;
@@ -722,9 +727,10 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->work_budget = std::min(c->work_budget, free_b / 2);
   }
   CU(cudaFuncSetAttribute(k_hp_reduce_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHpSmem));
-  CU(cudaFuncSetAttribute(k_meanshift<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
-  CU(cudaFuncSetAttribute(k_meanshift<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
-  CU(cudaFuncSetAttribute(k_meanshift<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+  CU(cudaFuncSetAttribute(k_meanshift<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+  CU(cudaFuncSetAttribute(k_meanshift<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+  CU(cudaFuncSetAttribute(k_meanshift<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+  CU(cudaFuncSetAttribute(k_meanshift<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
   if ((rc = c->d_counters.reserve(sizeof(unsigned long long) * CNT_NUM))) return rc;
   CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * CNT_NUM, c->w->stream));
   if ((rc = c->d_misc.reserve(4096))) return rc;

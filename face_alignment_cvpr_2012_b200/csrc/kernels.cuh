@@ -907,9 +907,9 @@ __device__ __forceinline__ void vote_terms(const DevVote q, bool first_pass, flo
 constexpr int kMsTile = 64;
 constexpr size_t kMsSmem = (size_t)2 * 3 * kMsTile * 33 * sizeof(float);  // dynamic shared memory of k_meanshift
 
-template <int MINB>
+template <int MINB, bool SPARSE>
 __global__ void __launch_bounds__(kFoldThreads, MINB) k_meanshift(const FaceDesc* __restrict__ fd, int nchains, const DevVote* __restrict__ votes, size_t vote_cap,
-                                                               const int32_t* __restrict__ vote_counts, const int32_t* __restrict__ vote_base, MeanShiftOpt o, crf_face_t* __restrict__ faces,
+                                                               const int32_t* __restrict__ vote_counts, const int32_t* __restrict__ vote_base, int cpc /* chains per CTA, <= 32 */, MeanShiftOpt o, crf_face_t* __restrict__ faces,
                                                             unsigned long long* counters) {
   extern __shared__ __align__(16) float s_dyn[];
   typedef float Tile[kMsTile][33];
@@ -920,15 +920,16 @@ __global__ void __launch_bounds__(kFoldThreads, MINB) k_meanshift(const FaceDesc
   __shared__ const DevVote* s_list[kFoldChains];
   __shared__ float s_mx[kFoldChains], s_my[kFoldChains];
   __shared__ unsigned long long s_tab[32];
-  __shared__ int s_maxn;
+  __shared__ int s_maxn, s_nact, s_act[kFoldChains];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * kFoldChains;
+  const int c0 = blockIdx.x * cpc;
   if (threadIdx.x < kFoldChains) {
     const int c = c0 + threadIdx.x;
-    const int cnt = c < nchains ? vote_counts[c] : 0;
+    const bool mine = threadIdx.x < cpc && c < nchains;
+    const int cnt = mine ? vote_counts[c] : 0;
     s_n[threadIdx.x] = max(cnt, 0);
-    s_active[threadIdx.x] = c < nchains && cnt >= 0;   // cnt < 0: face over the vote budget, left to the wide re-run
-    s_list[threadIdx.x] = c < nchains ? votes + (size_t)(c / kParts) * vote_cap + vote_base[c] : votes;
+    s_active[threadIdx.x] = mine && cnt >= 0;   // cnt < 0: face over the vote budget, left to the wide re-run
+    s_list[threadIdx.x] = mine ? votes + (size_t)(c / kParts) * vote_cap + vote_base[c] : votes;
     s_mx[threadIdx.x] = 0.f; s_my[threadIdx.x] = 0.f;
     s_tab[threadIdx.x] = c_expf.tab[threadIdx.x];
   }
@@ -940,14 +941,32 @@ __global__ void __launch_bounds__(kFoldThreads, MINB) k_meanshift(const FaceDesc
     if (warp == 0) {
       int m = s_active[lane] ? max(s_n[lane], 1) : 0;   // an empty chain still runs its (empty) passes
       m = __reduce_max_sync(0xffffffffu, m);
-      if (lane == 0) s_maxn = m;
+      // compact list of the chains that still have votes to weigh: few of them (small batches, late passes) are spread
+      // over all producer warps instead of leaving most of them idle
+      const unsigned live = __ballot_sync(0xffffffffu, s_active[lane] && s_n[lane] > 0);
+      if (s_active[lane] && s_n[lane] > 0) s_act[__popc(live & ((1u << lane) - 1u))] = lane;
+      if (lane == 0) { s_maxn = m; s_nact = __popc(live); }
     }
     __syncthreads();
     const int maxn = s_maxn;
     if (maxn == 0) break;
+    const int nact = s_nact;
     const int ntiles = (maxn + kMsTile - 1) / kMsTile;
     auto produce = [&](int tile) {
       const int b = tile & 1;
+      if (SPARSE) {   // few live chains per CTA: items = (live chain, 32-vote group), round-robin over the 8 producer warps
+        constexpr int G = kMsTile / 32;
+#pragma unroll 2
+        for (int it = warp - 1; it < nact * G; it += 8) {
+          const int j = s_act[it / G], h = it % G;
+          const int k = tile * kMsTile + h * 32 + lane;
+          if (k < s_n[j]) {
+            float w, wx, wy;
+            vote_terms(s_list[j][k], pass == 0, s_mx[j], s_my[j], lamda, s_tab, w, wx, wy);
+            s_w[b][h * 32 + lane][j] = w; s_x[b][h * 32 + lane][j] = wx; s_y[b][h * 32 + lane][j] = wy;
+          }
+        }
+      } else {
       DevVote q[4][kMsTile / 32];
       bool ok[4][kMsTile / 32];
 #pragma unroll
@@ -972,6 +991,7 @@ __global__ void __launch_bounds__(kFoldThreads, MINB) k_meanshift(const FaceDesc
           vote_terms(q[jj][h], pass == 0, cmx, cmy, lamda, s_tab, w, wx, wy);
           s_w[b][h * 32 + lane][j] = w; s_x[b][h * 32 + lane][j] = wx; s_y[b][h * 32 + lane][j] = wy;
         }
+      }
       }
     };
     float sw = 0.f, sx = 0.f, sy = 0.f;
@@ -1009,7 +1029,7 @@ __global__ void __launch_bounds__(kFoldThreads, MINB) k_meanshift(const FaceDesc
     }
     __syncthreads();
   }
-  if (warp == 0 && c0 + lane < nchains) {
+  if (warp == 0 && lane < cpc && c0 + lane < nchains) {
     const int c = c0 + lane, f = c / kParts, p = c - f * kParts;
     const int rx = __float2int_rn(mx), ry = __float2int_rn(my);  // Point_<int> = Point_<float>: cvRound
     crf_face_t* face = faces + f;
