@@ -71,21 +71,27 @@ static void build_gabor_bank(std::vector<float2> coef[5], int widths[5]) {
   }
 }
 
-// Coefficients of one scale for k_gabor_sym: first-half taps + centre, 7 orientations interleaved as (re, im) pairs,
-// 8 float2 per tap.  Verifies the exact even / odd symmetry the pair accumulation relies on.
-static bool build_gabor_sym(const std::vector<float2>& coef, int w, std::vector<float2>& out) {
-  const int nt = (w * w + 1) / 2;
-  out.assign((size_t)nt * 8, make_float2(0.f, 0.f));
+// Separable factors of one scale for k_gabor_sep: float2 hx[7][K], float2 hy[7][K], float g1[K], float dc
+// (same expressions, in double, as the oracle's create_gabor_kernel).
+static void build_gabor_sep(int nu, int w, std::vector<float>& out) {
+  const double sigma = 1.0 / 2.0 * M_PI, dF = std::sqrt(2.0);
+  const double k = (M_PI / 2) / std::pow(dF, (double)nu);
+  const int off = (w - 1) / 2;
+  out.assign((size_t)7 * w * 4 + w + 1, 0.f);
   for (int mu = 0; mu < 7; mu++) {
-    const float2* k = &coef[(size_t)mu * w * w];
-    for (int t = 0; t < nt; t++) {
-      const float2 a = k[t], b = k[w * w - 1 - t];
-      if (t < nt - 1 && (a.x != b.x || a.y != -b.y)) return false;
-      if (t == nt - 1 && a.y != 0.f) return false;
-      out[(size_t)t * 8 + mu] = a;
+    const double phi = M_PI * mu / 8;
+    const double ax = k * std::cos(phi), ay = k * std::sin(phi);
+    for (int i = 0; i < w; i++) {
+      const double x = (double)(i - off);
+      const double env = std::sqrt(k * k / (sigma * sigma)) * std::exp(-(x * x) * k * k / (2 * sigma * sigma));
+      out[((size_t)mu * w + i) * 2 + 0] = (float)(env * std::cos(ax * x));
+      out[((size_t)mu * w + i) * 2 + 1] = (float)(env * std::sin(ax * x));
+      out[(size_t)7 * w * 2 + ((size_t)mu * w + i) * 2 + 0] = (float)(env * std::cos(ay * x));
+      out[(size_t)7 * w * 2 + ((size_t)mu * w + i) * 2 + 1] = (float)(env * std::sin(ay * x));
+      out[(size_t)7 * w * 4 + i] = (float)env;
     }
   }
-  return true;
+  out[(size_t)7 * w * 4 + w] = (float)std::exp(-(sigma * sigma) / 2);
 }
 
 struct StageTimer {
@@ -119,7 +125,7 @@ struct crf_ctx {
   int hp_ntrees = 0, mp_ntrees_cfg = 0, num_channels = 38;
   PackedForest hp, mp;  // host copies (object-id maps for the stage API)
   // device model
-  Buf d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5], d_coef_sym[5];
+  Buf d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5], d_coef_sep[5];
   int gabor_width[5] = {0, 0, 0, 0, 0};
   ComposeTables ct{};
   // work buffers: two complete sets, so that consecutive chunks run on two streams and kernels bound by different
@@ -266,12 +272,12 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   const uint8_t* sc = c->w->d_scaled.as<uint8_t>();
   float* mag = c->w->d_mag.as<float>();
   uint32_t* mm = c->w->d_minmax.as<uint32_t>();
-  // heaviest scale first; 9x9 and larger: all orientations per thread with symmetric-pair accumulation
   const dim3 gsym((Hmax + 15) / 16, n);
-  k_gabor_sym<25><<<gsym, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sym[4].as<float4>(), 4, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
-  k_gabor_sym<19><<<gsym, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sym[3].as<float4>(), 3, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
-  k_gabor_sym<13><<<gsym, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sym[2].as<float4>(), 2, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
-  k_gabor_sym<9><<<gsym, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sym[1].as<float4>(), 1, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  // 9x9 .. 25x25 in separable form (heaviest first), 7x7 as the direct raster sum that equals cv2 bit for bit
+  k_gabor_sep<25><<<gsym, 256, GaborSepSmem<25>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[4].as<float>(), 4, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  k_gabor_sep<19><<<gsym, 256, GaborSepSmem<19>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[3].as<float>(), 3, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  k_gabor_sep<13><<<gsym, 256, GaborSepSmem<13>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[2].as<float>(), 2, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  k_gabor_sep<9><<<gsym, 256, GaborSepSmem<9>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[1].as<float>(), 1, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
   k_gabor_mag<7><<<grid, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef[0].as<float2>(), 0, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
   k_gabor_quant_integral<<<dim3(35, n), 128, 0, c->w->stream>>>(fd, mag, c->w->mag_fs, c->w->mag_ps, mm, c->w->d_stacks.as<stack_t>(), c->w->stack_fs, c->w->plane_stride, 1,
                                                              u8, c->w->u8_fs, dbg32);
@@ -628,7 +634,7 @@ void crf_ctx_destroy(crf_ctx* c) {
   cudaSetDevice(c->device);
   for (auto& w : c->ws) if (w.stream) cudaStreamSynchronize(w.stream);
   Buf* all[] = {&c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
-                &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_coef_sym[1], &c->d_coef_sym[2], &c->d_coef_sym[3], &c->d_coef_sym[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc};
+                &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_coef_sep[1], &c->d_coef_sep[2], &c->d_coef_sep[3], &c->d_coef_sep[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc};
   for (Buf* b : all) b->release();
   for (auto& w : c->ws) {
     for (Buf* b : w.all) b->release();
@@ -706,9 +712,9 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
       if (c->gabor_width[i] != expect[i]) return fail(CRF_ERR_STATE, "unexpected Gabor kernel width");
       if ((rc = upload(c->d_coef[i], coef[i], c->w->stream))) return rc;
       if (i > 0) {
-        std::vector<float2> sym;
-        if (!build_gabor_sym(coef[i], c->gabor_width[i], sym)) return fail(CRF_ERR_STATE, "Gabor kernel is not exactly even/odd");
-        if ((rc = upload(c->d_coef_sym[i], sym, c->w->stream))) return rc;
+        std::vector<float> sep;
+        build_gabor_sep(i, c->gabor_width[i], sep);
+        if ((rc = upload(c->d_coef_sep[i], sep, c->w->stream))) return rc;
       }
     }
   }
@@ -726,6 +732,10 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->work_budget = std::min(c->work_budget, free_b / 2);
   }
+  CU(cudaFuncSetAttribute(k_gabor_sep<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<25>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_sep<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<19>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_sep<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<13>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_sep<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<9>::bytes));
   CU(cudaFuncSetAttribute(k_hp_reduce_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHpSmem));
   CU(cudaFuncSetAttribute(k_meanshift<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
   CU(cudaFuncSetAttribute(k_meanshift<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));

@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(128) k_integral_from_u8(const uint8_t* __restr
 // ---------------------------------------------------------------------------------------------
 // a6, first half: the 35 complex Gabor responses (include/FeatureChannelFactory.hpp:253-270).
 // cv::filter2D = correlation, anchor centre, REFLECT_101, u8 -> f32; canonical accumulation =
-// raster order over the kernel; product and sum rounded separately for the 7x7 kernels (bit-identical to cv2),
-// one fused multiply-add per tap for the larger ones (where cv2 itself switches to a DFT path).  Then
+// raster order over the kernel; product and sum rounded separately (bit-identical to cv2 for the 7x7 kernels; the
+// larger kernels, where cv2 itself switches to a DFT path, go through k_gabor_sep).  Then
 // magnitude = sqrt(im*im + re*re).  One CTA = one 16-row band of one (face, orientation) at scale
 // NU (kernel size K); each thread owns 1 x 4 output strips, the band and its halo live in shared
 // memory as f32, coefficients are broadcast LDS.64.  Per-plane min/max via integer atomics
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256, 2) k_gabor_mag(const FaceDesc* __restrict
                                                       uint32_t* __restrict__ minmax) {
   using G = GaborGeom<K>;
   constexpr int KP = K + 1;            // coefficient row padded to an even tap count: two taps per LDS.128
-  constexpr bool FUSED = K >= 9;       // canonical accumulation (SURVEY A.4 / DESIGN.md): unfused for 7x7 (== cv2), fmaf beyond (cv2 is DFT there)
+  constexpr bool FUSED = false;        // 7x7 only: product and sum rounded separately == cv2's filter2D bit for bit (larger kernels: k_gabor_sep)
   __shared__ __align__(16) float tile[G::TH][G::PITCH];
   __shared__ __align__(16) float2 cf[K][KP];
   const FaceDesc d = fd[blockIdx.z];
@@ -285,113 +285,140 @@ __global__ void __launch_bounds__(256, 2) k_gabor_mag(const FaceDesc* __restrict
   }
 }
 
-// a6 for the 9x9 .. 25x25 kernels: all 7 orientations of one scale per thread, symmetric-pair accumulation.
-// The Gabor real part is exactly even and the imaginary part exactly odd under (x,y) -> (-x,-y) (checked on the host
-// when the bank is built), so the canonical sum for these sizes (cv2 itself takes a DFT path here) is
-//   re = fmaf(p(t) + p(mirror t), k_re(t), re),  im = fmaf(p(t) - p(mirror t), k_im(t), im)
-// over the first half of the kernel in raster order, then the centre tap for re.  The exact pixel sum / difference is
-// shared by the 7 orientations: 2 adds + 14 FFMA per (tap pair, pixel) instead of 28 FFMA.
-// One CTA = a 16-row band of one face; a thread owns a 1 x 4 strip and 56 accumulators.
-// coef: [ (K*K+1)/2 taps ][8] float2 (re, im) per orientation, slot 7 unused (keeps LDS.128 alignment).
+// a6 for the 9x9 .. 25x25 kernels in SEPARABLE form (the canonical arithmetic for these sizes):
+//   t1(x,y) e^{i(ax x + ay y)} - dc t1(x,y) = [g(x) e^{i ax x}] [g(y) e^{i ay y}] - dc g(x) g(y)
+// i.e. a complex row pass and a complex column pass per orientation plus one real Gaussian pair per scale: 6K + 2K/7
+// instead of K^2 multiply-adds per pixel and orientation.  Order (all __fmaf_rn, taps ascending):
+//   row pass on the REFLECT_101-padded rows: Rre, Rim (and Gr with g1);  column pass: re += Rre*hy_re; re += -Rim*hy_im;
+//   im += Rre*hy_im; im += Rim*hy_re; G += Gr*g1;  then re = fmaf(-dc, G, re).
+// One CTA = a 16-row band of one face, looping over the 7 orientations; the band + halo and the row-pass results
+// live in (dynamic) shared memory.  coef (per scale): float2 hx[7][K], float2 hy[7][K], float g1[K], float dc.
 // grid = (bands, faces), 256 threads.
 template <int K>
-__global__ void __launch_bounds__(256) k_gabor_sym(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
-                                                   const float4* __restrict__ coef, int nu, float* __restrict__ mag, size_t mag_face_stride,
+struct GaborSepSmem {
+  using G = GaborGeom<K>;
+  static constexpr int NCOEF = 7 * K * 2 * 2 + K + 1;   // floats
+  static constexpr size_t bytes = sizeof(float) * ((size_t)G::TH * G::PITCH + 2 * (size_t)G::TH * 128 + ((NCOEF + 3) & ~3));
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) k_gabor_sep(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
+                                                   const float* __restrict__ coef, int nu, float* __restrict__ mag, size_t mag_face_stride,
                                                    size_t mag_plane_stride, uint32_t* __restrict__ minmax) {
   using G = GaborGeom<K>;
-  constexpr int R = K / 2, NT = (K * K + 1) / 2;   // first-half taps + centre
-  __shared__ __align__(16) float tile[G::TH][G::PITCH];
-  __shared__ __align__(16) float4 cf[NT][4];        // [tap][(re0,im0,re1,im1), (re2..), (re4..), (re6,im6,-,-)]
+  constexpr int R = K / 2, TH = G::TH, PITCH = G::PITCH;
+  extern __shared__ __align__(16) float s_gs[];
+  float (*tile)[PITCH] = reinterpret_cast<float (*)[PITCH]>(s_gs);
+  float (*rre)[128] = reinterpret_cast<float (*)[128]>(s_gs + TH * PITCH);
+  float (*rim)[128] = rre + TH;
+  float* cf = s_gs + TH * PITCH + 2 * TH * 128;
+  const float2* hx = reinterpret_cast<const float2*>(cf);      // [7][K]
+  const float2* hy = hx + 7 * K;                               // [7][K]
+  const float* g1 = cf + 7 * K * 4;                            // [K]
   const FaceDesc d = fd[blockIdx.y];
   const int W = d.W, H = d.H;
   const int r0 = blockIdx.x * G::BAND;
   if (r0 >= H) return;
   const int tid = threadIdx.x;
   const uint8_t* __restrict__ g = scaled + blockIdx.y * scaled_face_stride;
-  for (int i = tid; i < NT * 4; i += 256) (&cf[0][0])[i] = coef[i];
-  for (int i = tid; i < G::TH * G::PITCH; i += 256) {
-    const int ty = i / G::PITCH, tx = i - ty * G::PITCH;
+  for (int i = tid; i < GaborSepSmem<K>::NCOEF; i += 256) cf[i] = coef[i];
+  for (int i = tid; i < TH * PITCH; i += 256) {
+    const int ty = i / PITCH, tx = i - ty * PITCH;
     const int sy = border101(r0 + ty - R, H), sx = border101(tx - R, W);
     tile[ty][tx] = (float)g[(size_t)sy * 128 + sx];
   }
   __syncthreads();
-  const int x0 = (tid & 31) * 4;
-  float vmin[7], vmax[7];
+  const float dc = cf[7 * K * 4 + K];
+  const int x0 = (tid & 31) * 4, rA = tid >> 5;
+  // ---- Gaussian: row pass into rre, column pass into registers
+  for (int it = tid; it < TH * 32; it += 256) {
+    const int r = it >> 5, xs = (it & 31) * 4;
+    float px[4 * G::NF4];
+    const float4* row = reinterpret_cast<const float4*>(&tile[r][xs]);
 #pragma unroll
-  for (int m = 0; m < 7; m++) { vmin[m] = __int_as_float(0x7f800000); vmax[m] = 0.f; }
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    const int r = (tid >> 5) + 8 * pass;
-    float re[7][4], im[7][4];
+    for (int q = 0; q < G::NF4; q++) { const float4 v = row[q]; px[4 * q] = v.x; px[4 * q + 1] = v.y; px[4 * q + 2] = v.z; px[4 * q + 3] = v.w; }
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int m = 0; m < 7; m++)
+    for (int i = 0; i < K; i++) {
+      const float c = g1[i];
 #pragma unroll
-      for (int o = 0; o < 4; o++) { re[m][o] = 0.f; im[m][o] = 0.f; }
-#pragma unroll 1
-    for (int j = 0; j <= R; j++) {
-      const float* top = &tile[r + j][x0];
-      const float* bot = &tile[r + K - 1 - j][x0];
-      const int ni = j < R ? K : R;   // the centre row contributes only the taps left of the centre
-      // sliding windows: wt = top[i .. i+3], wb = bot[K-1-i .. K-1-i+3]
-      float wt0 = top[0], wt1 = top[1], wt2 = top[2], wt3 = top[3];
-      float wb0 = bot[K - 1], wb1 = bot[K], wb2 = bot[K + 1], wb3 = bot[K + 2];
-      const float4* c4 = &cf[j * K][0];
-#pragma unroll 4
-      for (int i = 0; i < ni; i++) {
-        const float4 ca = c4[0], cb = c4[1], cc = c4[2], cd = c4[3];
-        c4 += 4;
-        const float s[4] = {wt0 + wb0, wt1 + wb1, wt2 + wb2, wt3 + wb3};
-        const float df[4] = {wt0 - wb0, wt1 - wb1, wt2 - wb2, wt3 - wb3};
-#pragma unroll
-        for (int o = 0; o < 4; o++) {
-          re[0][o] = __fmaf_rn(s[o], ca.x, re[0][o]); im[0][o] = __fmaf_rn(df[o], ca.y, im[0][o]);
-          re[1][o] = __fmaf_rn(s[o], ca.z, re[1][o]); im[1][o] = __fmaf_rn(df[o], ca.w, im[1][o]);
-          re[2][o] = __fmaf_rn(s[o], cb.x, re[2][o]); im[2][o] = __fmaf_rn(df[o], cb.y, im[2][o]);
-          re[3][o] = __fmaf_rn(s[o], cb.z, re[3][o]); im[3][o] = __fmaf_rn(df[o], cb.w, im[3][o]);
-          re[4][o] = __fmaf_rn(s[o], cc.x, re[4][o]); im[4][o] = __fmaf_rn(df[o], cc.y, im[4][o]);
-          re[5][o] = __fmaf_rn(s[o], cc.z, re[5][o]); im[5][o] = __fmaf_rn(df[o], cc.w, im[5][o]);
-          re[6][o] = __fmaf_rn(s[o], cd.x, re[6][o]); im[6][o] = __fmaf_rn(df[o], cd.y, im[6][o]);
-        }
-        // slide: top window moves right, bottom window moves left
-        wt0 = wt1; wt1 = wt2; wt2 = wt3; wt3 = top[i + 4];
-        wb3 = wb2; wb2 = wb1; wb1 = wb0; wb0 = bot[K - 2 - i];
-      }
+      for (int o = 0; o < 4; o++) a[o] = __fmaf_rn(px[o + i], c, a[o]);
     }
-    {  // centre tap (real part only: the imaginary coefficient is exactly 0)
-      const float4 ca = cf[NT - 1][0], cb = cf[NT - 1][1], cc = cf[NT - 1][2], cd = cf[NT - 1][3];
-      const float* mid = &tile[r + R][x0 + R];
+    *reinterpret_cast<float4*>(&rre[r][xs]) = make_float4(a[0], a[1], a[2], a[3]);
+  }
+  __syncthreads();
+  float Gs[2][4];
 #pragma unroll
-      for (int o = 0; o < 4; o++) {
-        const float p = mid[o];
-        re[0][o] = __fmaf_rn(p, ca.x, re[0][o]); re[1][o] = __fmaf_rn(p, ca.z, re[1][o]);
-        re[2][o] = __fmaf_rn(p, cb.x, re[2][o]); re[3][o] = __fmaf_rn(p, cb.z, re[3][o]);
-        re[4][o] = __fmaf_rn(p, cc.x, re[4][o]); re[5][o] = __fmaf_rn(p, cc.z, re[5][o]);
-        re[6][o] = __fmaf_rn(p, cd.x, re[6][o]);
-      }
-    }
-    if (r0 + r < H) {
+  for (int h = 0; h < 2; h++) {
 #pragma unroll
-      for (int m = 0; m < 7; m++) {
-        float v[4];
-#pragma unroll
-        for (int o = 0; o < 4; o++) {
-          v[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[m][o], im[m][o]), __fmul_rn(re[m][o], re[m][o])));
-          if (x0 + o < W) { vmin[m] = fminf(vmin[m], v[o]); vmax[m] = fmaxf(vmax[m], v[o]); }
-        }
-        float* mplane = mag + blockIdx.y * mag_face_stride + (size_t)(nu * 7 + m) * mag_plane_stride;
-        *reinterpret_cast<float4*>(&mplane[(size_t)(r0 + r) * 128 + x0]) = make_float4(v[0], v[1], v[2], v[3]);
-      }
+    for (int o = 0; o < 4; o++) Gs[h][o] = 0.f;
+#pragma unroll 5
+    for (int j = 0; j < K; j++) {
+      const float4 v = *reinterpret_cast<const float4*>(&rre[rA + 8 * h + j][x0]);
+      const float c = g1[j];
+      Gs[h][0] = __fmaf_rn(v.x, c, Gs[h][0]); Gs[h][1] = __fmaf_rn(v.y, c, Gs[h][1]);
+      Gs[h][2] = __fmaf_rn(v.z, c, Gs[h][2]); Gs[h][3] = __fmaf_rn(v.w, c, Gs[h][3]);
     }
   }
+  __syncthreads();
+  // ---- the 7 orientations
+#pragma unroll 1
+  for (int mu = 0; mu < 7; mu++) {
+    const float2* hxm = hx + mu * K;
+    const float2* hym = hy + mu * K;
+#pragma unroll 1
+    for (int it = tid; it < TH * 32; it += 256) {
+      const int r = it >> 5, xs = (it & 31) * 4;
+      float px[4 * G::NF4];
+      const float4* row = reinterpret_cast<const float4*>(&tile[r][xs]);
 #pragma unroll
-  for (int m = 0; m < 7; m++) {
-    const uint32_t umin = __reduce_min_sync(0xffffffffu, __float_as_uint(vmin[m]));
-    const uint32_t umax = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax[m]));
+      for (int q = 0; q < G::NF4; q++) { const float4 v = row[q]; px[4 * q] = v.x; px[4 * q + 1] = v.y; px[4 * q + 2] = v.z; px[4 * q + 3] = v.w; }
+      float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < K; i++) {
+        const float2 c = hxm[i];
+#pragma unroll
+        for (int o = 0; o < 4; o++) { a[o] = __fmaf_rn(px[o + i], c.x, a[o]); b[o] = __fmaf_rn(px[o + i], c.y, b[o]); }
+      }
+      *reinterpret_cast<float4*>(&rre[r][xs]) = make_float4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<float4*>(&rim[r][xs]) = make_float4(b[0], b[1], b[2], b[3]);
+    }
+    __syncthreads();
+    float vmin = __int_as_float(0x7f800000), vmax = 0.f;
+    float* mplane = mag + blockIdx.y * mag_face_stride + (size_t)(nu * 7 + mu) * mag_plane_stride;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      float re[4] = {0.f, 0.f, 0.f, 0.f}, im[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 5
+      for (int j = 0; j < K; j++) {
+        const float4 a = *reinterpret_cast<const float4*>(&rre[rA + 8 * h + j][x0]);
+        const float4 b = *reinterpret_cast<const float4*>(&rim[rA + 8 * h + j][x0]);
+        const float2 c = hym[j];
+        re[0] = __fmaf_rn(a.x, c.x, re[0]); re[0] = __fmaf_rn(-b.x, c.y, re[0]); im[0] = __fmaf_rn(a.x, c.y, im[0]); im[0] = __fmaf_rn(b.x, c.x, im[0]);
+        re[1] = __fmaf_rn(a.y, c.x, re[1]); re[1] = __fmaf_rn(-b.y, c.y, re[1]); im[1] = __fmaf_rn(a.y, c.y, im[1]); im[1] = __fmaf_rn(b.y, c.x, im[1]);
+        re[2] = __fmaf_rn(a.z, c.x, re[2]); re[2] = __fmaf_rn(-b.z, c.y, re[2]); im[2] = __fmaf_rn(a.z, c.y, im[2]); im[2] = __fmaf_rn(b.z, c.x, im[2]);
+        re[3] = __fmaf_rn(a.w, c.x, re[3]); re[3] = __fmaf_rn(-b.w, c.y, re[3]); im[3] = __fmaf_rn(a.w, c.y, im[3]); im[3] = __fmaf_rn(b.w, c.x, im[3]);
+      }
+      const int r = r0 + rA + 8 * h;
+      if (r < H) {
+        float m[4];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+          const float rr = __fmaf_rn(-dc, Gs[h][o], re[o]);
+          m[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[o], im[o]), __fmul_rn(rr, rr)));
+          if (x0 + o < W) { vmin = fminf(vmin, m[o]); vmax = fmaxf(vmax, m[o]); }
+        }
+        *reinterpret_cast<float4*>(&mplane[(size_t)r * 128 + x0]) = make_float4(m[0], m[1], m[2], m[3]);
+      }
+    }
+    const uint32_t umin = __reduce_min_sync(0xffffffffu, __float_as_uint(vmin));
+    const uint32_t umax = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
     if ((tid & 31) == 0) {
-      uint32_t* mm = minmax + ((size_t)blockIdx.y * 35 + nu * 7 + m) * 2;
+      uint32_t* mm = minmax + ((size_t)blockIdx.y * 35 + nu * 7 + mu) * 2;
       atomicMin(&mm[0], umin);
       atomicMax(&mm[1], umax);
     }
+    __syncthreads();   // rre / rim are rewritten by the next orientation
   }
 }
 

@@ -416,7 +416,14 @@ static void minmax3x3_u8(const Plane8& src, Plane8& mn, Plane8& mx) {
 }
 
 // FeatureChannelFactory.hpp:186-251  createKernel / initGaborKernels (A.4)
-struct GaborKernel { int width = 0; std::vector<float> re, im; };  // stored row-major [row j][col i]
+struct GaborKernel {
+  int width = 0;
+  std::vector<float> re, im;   // 2-D tables as createKernel builds them, row-major [row j][col i]
+  // separable factors of the same kernel (used for width >= 9, see gabor_response_separable):
+  //   t1(x,y) e^{i(ax x + ay y)} = [g(x) e^{i ax x}] [g(y) e^{i ay y}],  g(x) = sqrt(k^2/sigma^2) exp(-x^2 k^2 / (2 sigma^2))
+  std::vector<float> hx_re, hx_im, hy_re, hy_im, g1;
+  float dc = 0.f;              // exp(-sigma^2 / 2): the real part subtracts dc * t1(x,y)
+};
 static void create_gabor_kernel(int iMu, int iNu, double sigma, double dF, GaborKernel& out) {
   double F = dF;
   double k = (M_PI / 2) / std::pow(F, (double)iNu);
@@ -438,6 +445,16 @@ static void create_gabor_kernel(int iMu, int iNu, double sigma, double dF, Gabor
       out.re[(size_t)j * w + i] = (float)(dTemp1 * dTemp2);
       out.im[(size_t)j * w + i] = (float)(dTemp1 * dTemp3);
     }
+  out.hx_re.resize(w); out.hx_im.resize(w); out.hy_re.resize(w); out.hy_im.resize(w); out.g1.resize(w);
+  const double ax = k * std::cos(phi), ay = k * std::sin(phi);
+  for (int i = 0; i < w; i++) {
+    const double x = (double)(i - off_set);
+    const double env = std::sqrt(k * k / (sigma * sigma)) * std::exp(-(x * x) * k * k / (2 * sigma * sigma));
+    out.g1[i] = (float)env;
+    out.hx_re[i] = (float)(env * std::cos(ax * x)); out.hx_im[i] = (float)(env * std::sin(ax * x));
+    out.hy_re[i] = (float)(env * std::cos(ay * x)); out.hy_im[i] = (float)(env * std::sin(ay * x));
+  }
+  out.dc = (float)std::exp(-(sigma * sigma) / 2);
 }
 static const std::vector<GaborKernel>& gabor_bank() {
   static std::vector<GaborKernel> bank = [] {
@@ -461,11 +478,7 @@ static const std::vector<GaborKernel>& gabor_bank() {
 // match bit for bit, so the canonical form there is acc = fmaf(px, k, acc) (one rounding per tap, the
 // more accurate direct sum); its distance to cv2 is pinned statistically (+-1 LSB of the u8 plane).
 // Skipping exact-zero coefficients, as cv2 does, cannot change a value (x + 0*px == x).
-// parity: 0 = plain raster accumulation; +1 / -1 = the kernel is exactly even / odd under (x,y) -> (-x,-y)
-// (Gabor real / imaginary part) and, for kw >= 9, mirrored taps are accumulated as one fused multiply-add of the
-// exact pixel sum / difference:  acc = fmaf(p(t) +- p(mirror t), k(t), acc) over the first half of the kernel in
-// raster order, then the centre tap.
-static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int kw, PlaneF& dst, int parity = 0) {
+static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int kw, PlaneF& dst) {
   const int H = src.rows, W = src.cols, r = kw / 2;
   dst.rows = H; dst.cols = W; dst.d.resize((size_t)H * W);
   // padded float copy so the inner loop is branch-free (thread-local scratch: no malloc churn)
@@ -478,32 +491,6 @@ static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int 
     for (int x = 0; x < PW; x++) pad[(size_t)y * PW + x] = (float)src.at(sy, border101(x - r, W));
   }
   acc.resize((size_t)W);
-  if (kw >= 9 && parity != 0) {
-    const int centre = r * kw + r;
-    for (int t = 0; t < centre; t++) {   // the symmetry is a property of the coefficient tables; checked, not assumed
-      const float a = kern[(size_t)t], b = kern[(size_t)(kw * kw - 1 - t)];
-      if ((parity > 0 && a != b) || (parity < 0 && a != -b)) { std::fprintf(stderr, "gabor kernel is not %s\n", parity > 0 ? "even" : "odd"); std::abort(); }
-    }
-    for (int y = 0; y < H; y++) {
-      std::fill(acc.begin(), acc.end(), 0.f);
-      float* __restrict a = acc.data();
-      for (int t = 0; t < centre; t++) {
-        const int j = t / kw, i = t - j * kw;
-        const float* __restrict top = &pad[(size_t)(y + j) * PW + i];
-        const float* __restrict bot = &pad[(size_t)(y + kw - 1 - j) * PW + (kw - 1 - i)];
-        const float k = kern[(size_t)t];
-        if (parity > 0) for (int x = 0; x < W; x++) a[x] = std::fmaf(top[x] + bot[x], k, a[x]);
-        else            for (int x = 0; x < W; x++) a[x] = std::fmaf(top[x] - bot[x], k, a[x]);
-      }
-      if (parity > 0) {
-        const float* __restrict mid = &pad[(size_t)(y + r) * PW + r];
-        const float k = kern[(size_t)centre];
-        for (int x = 0; x < W; x++) a[x] = std::fmaf(mid[x], k, a[x]);
-      }
-      std::memcpy(&dst.d[(size_t)y * W], a, sizeof(float) * (size_t)W);
-    }
-    return;
-  }
   std::vector<int> tap_off; std::vector<float> tap_k;
   for (int j = 0; j < kw; j++)
     for (int i = 0; i < kw; i++) {
@@ -520,9 +507,54 @@ static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int 
     for (size_t t = 0; t < nt; t++) {
       const float* __restrict row = &pad[(size_t)y * PW + tap_off[t]];
       const float k = tap_k[t];
-      for (int x = 0; x < W; x++) a[x] = a[x] + row[x] * k;   // 7x7 (and any non-Gabor kernel): == cv2's filter2D bit for bit
+      for (int x = 0; x < W; x++) a[x] = a[x] + row[x] * k;   // == cv2's filter2D bit for bit for the 7x7 kernels
     }
     std::memcpy(&dst.d[(size_t)y * W], a, sizeof(float) * (size_t)W);
+  }
+}
+
+// Complex Gabor response for width >= 9 in separable form.  cv2 (2.4.9 and 4.13 alike) evaluates these sizes through a DFT,
+// so no direct sum is "the" reference arithmetic; the kernel is exactly (complex Gaussian-windowed exponential in x) x (the same
+// in y) minus dc x (separable Gaussian), which costs 6K instead of K^2 multiply-adds per pixel.  Canonical order, all f32 fmaf:
+//   row pass over the REFLECT_101-padded rows:  Rre = sum_i P(r, x+i) hx_re[i],  Rim likewise,  Gr = sum_i P(r, x+i) g1[i]
+//   column pass, j ascending:  re = fmaf(Rre, hy_re[j], re); re = fmaf(-Rim, hy_im[j], re);
+//                              im = fmaf(Rre, hy_im[j], im); im = fmaf( Rim, hy_re[j], im);  G = fmaf(Gr, g1[j], G)
+//   re = fmaf(-dc, G, re)
+// Its distance to cv2 is pinned statistically like every other form (+-1 LSB of the u8 plane, rate < 1e-3).
+static void gabor_response_separable(const Plane8& src, const GaborKernel& gk, PlaneF& re_out, PlaneF& im_out) {
+  const int H = src.rows, W = src.cols, K = gk.width, r = K / 2;
+  const int PW = W + 2 * r, PH = H + 2 * r;
+  static thread_local std::vector<float> pad, rre, rim, gr;
+  pad.resize((size_t)PW * PH); rre.resize((size_t)PH * W); rim.resize((size_t)PH * W); gr.resize((size_t)PH * W);
+  for (int y = 0; y < PH; y++) {
+    const int sy = border101(y - r, H);
+    for (int x = 0; x < PW; x++) pad[(size_t)y * PW + x] = (float)src.at(sy, border101(x - r, W));
+  }
+  for (int y = 0; y < PH; y++) {
+    float* __restrict a = &rre[(size_t)y * W]; float* __restrict b = &rim[(size_t)y * W]; float* __restrict g = &gr[(size_t)y * W];
+    for (int x = 0; x < W; x++) { a[x] = 0.f; b[x] = 0.f; g[x] = 0.f; }
+    for (int i = 0; i < K; i++) {
+      const float* __restrict p = &pad[(size_t)y * PW + i];
+      const float cr = gk.hx_re[i], ci = gk.hx_im[i], cg = gk.g1[i];
+      for (int x = 0; x < W; x++) { a[x] = std::fmaf(p[x], cr, a[x]); b[x] = std::fmaf(p[x], ci, b[x]); g[x] = std::fmaf(p[x], cg, g[x]); }
+    }
+  }
+  re_out.rows = im_out.rows = H; re_out.cols = im_out.cols = W;
+  re_out.d.resize((size_t)H * W); im_out.d.resize((size_t)H * W);
+  std::vector<float> G((size_t)W);
+  for (int y = 0; y < H; y++) {
+    float* __restrict re = &re_out.d[(size_t)y * W]; float* __restrict im = &im_out.d[(size_t)y * W];
+    for (int x = 0; x < W; x++) { re[x] = 0.f; im[x] = 0.f; G[x] = 0.f; }
+    for (int j = 0; j < K; j++) {
+      const float* __restrict a = &rre[(size_t)(y + j) * W]; const float* __restrict b = &rim[(size_t)(y + j) * W]; const float* __restrict g = &gr[(size_t)(y + j) * W];
+      const float cr = gk.hy_re[j], ci = gk.hy_im[j], cg = gk.g1[j];
+      for (int x = 0; x < W; x++) {
+        re[x] = std::fmaf(a[x], cr, re[x]); re[x] = std::fmaf(-b[x], ci, re[x]);
+        im[x] = std::fmaf(a[x], ci, im[x]); im[x] = std::fmaf(b[x], cr, im[x]);
+        G[x] = std::fmaf(g[x], cg, G[x]);
+      }
+    }
+    for (int x = 0; x < W; x++) re[x] = std::fmaf(-gk.dc, G[x], re[x]);
   }
 }
 
@@ -530,8 +562,12 @@ static void filter2d_f32(const Plane8& src, const std::vector<float>& kern, int 
 static void gabor_transform(const Plane8& src, const GaborKernel& gk, Plane8& out8) {
   static thread_local PlaneF r_mat, i_mat;
   static thread_local std::vector<float> mag;
-  filter2d_f32(src, gk.re, gk.width, r_mat, +1);
-  filter2d_f32(src, gk.im, gk.width, i_mat, -1);
+  if (gk.width >= 9) {
+    gabor_response_separable(src, gk, r_mat, i_mat);
+  } else {
+    filter2d_f32(src, gk.re, gk.width, r_mat);
+    filter2d_f32(src, gk.im, gk.width, i_mat);
+  }
   const size_t n = r_mat.d.size();
   mag.resize(n);
   double smin = 0, smax = 0;
