@@ -296,9 +296,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "kernels": [
                 {"kernel": "k_traverse (head-pose forest)", "bound": "hbm", "ms_per_step": hp_ms,
                  "achieved": (48 * work["hp_node_tests"] + 4 * work["hp_traversals"]) / (hp_ms * 1e-3) / 1e9 if hp_ms > 0 else 0.0, "unit": "GB/s"},
-                {"kernel": "k_gabor_sym<9..25> + k_gabor_mag<7> + quantise/integral", "bound": "fp32 issue (non-tensor FFMA)", "ms_per_step": gabor_ms,
+                {"kernel": "k_gabor_sep<9..25> + k_gabor_mag<7> + quantise/integral", "bound": "fp32 issue (non-tensor FFMA)", "ms_per_step": gabor_ms,
                  "achieved": gabor_flops / (gabor_ms * 1e-3) / 1e12 if gabor_ms > 0 else 0.0, "peak": fp32_peak, "unit": "TFLOP/s",
-                 "note": "achieved = direct-form FLOPs (35 980 per pixel, SURVEY 8d) / time; the symmetric-pair kernel executes 0.57 instructions per direct-form MAC"},
+                 "note": "achieved = direct-form FLOPs (35 980 per pixel, SURVEY 8d) / time; the separable form needs 6K instead of K^2 multiply-adds per pixel and orientation, so this can exceed the FFMA peak"},
             ],
             "work_per_step": {k: work[k] for k in ("hp_node_tests", "ffd_node_tests", "hp_traversals", "ffd_traversals", "votes", "vote_passes")},
         }
