@@ -126,7 +126,7 @@ def load_models(need_gpu: bool, need_oracle: bool):
         import tempfile
         from face_alignment_cvpr_2012_b200 import synthetic_model as sm
         d = tempfile.mkdtemp(prefix="crf_synth_")
-        hp, ffd = sm.write_model(d, seed=7, hp_depth=15, ffd_depth=16, leaf_prob=0.06)
+        hp, ffd = sm.write_model(d, seed=7, hp_depth=12, ffd_depth=13, leaf_prob=0.1)   # ~0.5 M nodes: tens of seconds to write and parse
         tag = "random-init forests of the shipped shape (staged/model.crfb200 absent)"
         if need_gpu:
             import face_alignment_cvpr_2012_b200 as crf

@@ -7,6 +7,7 @@ say so in the returned `data` tag.
 """
 from __future__ import annotations
 
+import os
 from pathlib import Path
 
 import numpy as np
@@ -16,6 +17,8 @@ STAGED = ROOT / "staged"
 
 
 def staged_model_path() -> Path | None:
+    if os.environ.get("CRF_NO_STAGED"):   # exercise the fallbacks (seeded random forests, procedural faces)
+        return None
     p = STAGED / "model.crfb200"
     return p if p.exists() else None
 
@@ -26,7 +29,7 @@ def load_lfw(dir_: Path | None = None):
     import cv2
     dir_ = Path(dir_) if dir_ else STAGED / "imgs"
     idx = dir_ / "index_random_subset.txt"
-    if not idx.exists():
+    if not idx.exists() or os.environ.get("CRF_NO_STAGED"):
         return []
     out = []
     for line in idx.read_text().split("\n"):
