@@ -48,6 +48,13 @@ struct alignas(32) DevSlot {
 };
 static_assert(sizeof(DevSlot) == 32, "slot must be one 32-byte sector");
 
+// Compact 16-byte form of the same node (two per 32-byte sector, so both children of a node share a sector): the
+// reciprocals are dropped and the two integer means are recomputed with a float reciprocal + exact fix-up.
+//   r1 = x1 | y1<<5 | w1<<10 | h1<<15 | ch<<20 | leaf<<26      r2 = x2 | y2<<5 | w2<<10 | h2<<15 | (thr+256)<<20
+//   child = slot of the left child (leaf: forest-global leaf index)     areas = area1 | area2<<16
+struct alignas(16) DevSlot16 { uint32_t r1, r2; int32_t child; uint32_t areas; };
+static_assert(sizeof(DevSlot16) == 16, "compact slot is 16 bytes");
+
 // MPLeaf (include/MPSample.hpp:137-159) with the vote predicate of src/face_utils.cpp:285-290 folded
 // into `mask` (bit i: part i votes) for the options of the context.
 struct alignas(16) DevMpLeaf {   // 48 bytes: three 128-bit loads
@@ -59,6 +66,7 @@ static_assert(sizeof(DevMpLeaf) == 48, "leaf record is three 16-byte words");
 
 struct PackedForest {
   std::vector<DevSlot> slots;
+  std::vector<DevSlot16> slots16;    // same slots, compact form
   std::vector<int32_t> roots;        // slot of the root of tree t (forest-major for the jungle)
   std::vector<int32_t> forest_base;  // jungle: first tree of pose forest f in `roots`
   std::vector<int32_t> forest_ntrees;

@@ -125,7 +125,7 @@ struct crf_ctx {
   int hp_ntrees = 0, mp_ntrees_cfg = 0, num_channels = 38;
   PackedForest hp, mp;  // host copies (object-id maps for the stage API)
   // device model
-  Buf d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5], d_coef_sep[5];
+  Buf d_hp_slots16, d_mp_slots16, d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5], d_coef_sep[5];
   int gabor_width[5] = {0, 0, 0, 0, 0};
   ComposeTables ct{};
   // work buffers: two complete sets, so that consecutive chunks run on two streams and kernels bound by different
@@ -293,12 +293,12 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   a.fd = fd; a.stacks = c->w->d_stacks.as<stack_t>(); a.stack_face_stride = c->w->stack_fs; a.plane_stride = c->w->plane_stride;
   a.stride = stride;
   if (hp) {
-    a.slots = c->d_hp_slots.as<DevSlot>(); a.roots = roots; a.ntrees = ntrees;
+    a.slots = c->d_hp_slots.as<DevSlot>(); a.slots16 = c->d_hp_slots16.as<DevSlot16>(); a.roots = roots; a.ntrees = ntrees;
     a.leaf_out = c->w->d_hp_leaf.as<int32_t>(); a.leaf_face_stride = c->w->hp_leaf_fs;
     a.cnt_tests = CNT_HP_TESTS; a.cnt_trav = CNT_HP_TRAV;
     if (hp_values) a.leaf_value = c->d_hp_m.as<float>();
   } else {
-    a.slots = c->d_mp_slots.as<DevSlot>();
+    a.slots = c->d_mp_slots.as<DevSlot>(); a.slots16 = c->d_mp_slots16.as<DevSlot16>();
     a.face_roots = c->w->d_face_roots.as<int32_t>(); a.face_ntrees = c->w->d_face_ntrees.as<int32_t>();
     a.leaf_out = c->w->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->w->ffd_leaf_fs;
     a.cnt_tests = CNT_FFD_TESTS; a.cnt_trav = CNT_FFD_TRAV;
@@ -309,8 +309,10 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   const size_t smem = (size_t)32 * smem_trees * 4;
   // variant = LW (32 or 8) | MODE << 8 | NW (5 or 10) << 16; CRF_TRAVERSE_VARIANT overrides for experiments
   // defaults from tools/traverse_variants.py on B200: one warp per tree for the 15-tree head-pose forest, 10 warps for 20 trees;
-  // rows of 32 x-adjacent patches at dense strides, 8 x 4 blocks at sparse ones; 256-bit slot loads
-  const int variant = c->traverse_variant ? c->traverse_variant : ((stride >= 3 ? 8 : 32) | (2 << 8) | ((hp && stride < 3 ? 15 : 10) << 16));
+  // rows of 32 x-adjacent patches and the compact 16-byte slots at dense strides; 8 x 4 blocks and 256-bit loads of the wide
+  // slots at sparse ones
+  const int variant = c->traverse_variant ? c->traverse_variant
+                                           : (stride >= 3 ? (8 | (2 << 8) | (10 << 16)) : (32 | (4 << 8) | ((hp ? 15 : 10) << 16)));
   const int LW = variant & 0xff, MODE = (variant >> 8) & 0xff, NW = (variant >> 16) & 0xff;
   const int tiles = LW != 8 ? ((nx + 31) / 32) * ny : ((nx + 7) / 8) * ((ny + 3) / 4);
   const dim3 grid(tiles, n);
@@ -321,6 +323,11 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
     launched = true;                                                                                       \
   }
   bool launched = false;
+  if (MODE == 4 && LW == 32) {   // compact 16-byte slots
+    const dim3 g16(((nx + 31) / 32) * ny, n);
+    if (NW == 10) { if (c->counting) k_traverse16<10, true><<<g16, 320, smem, c->w->stream>>>(a); else k_traverse16<10, false><<<g16, 320, smem, c->w->stream>>>(a); launched = true; }
+    if (NW == 15) { if (c->counting) k_traverse16<15, true><<<g16, 480, smem, c->w->stream>>>(a); else k_traverse16<15, false><<<g16, 480, smem, c->w->stream>>>(a); launched = true; }
+  }
   CRF_TRAV(5, 32, 0) CRF_TRAV(5, 32, 1) CRF_TRAV(5, 32, 2) CRF_TRAV(5, 32, 3)
   CRF_TRAV(5, 8, 0) CRF_TRAV(5, 8, 1) CRF_TRAV(5, 8, 2) CRF_TRAV(5, 8, 3)
   CRF_TRAV(10, 32, 0) CRF_TRAV(10, 32, 2) CRF_TRAV(10, 8, 2) CRF_TRAV(10, 8, 3)
@@ -633,7 +640,7 @@ void crf_ctx_destroy(crf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   for (auto& w : c->ws) if (w.stream) cudaStreamSynchronize(w.stream);
-  Buf* all[] = {&c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
+  Buf* all[] = {&c->d_hp_slots16, &c->d_mp_slots16, &c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
                 &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_coef_sep[1], &c->d_coef_sep[2], &c->d_coef_sep[3], &c->d_coef_sep[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc};
   for (Buf* b : all) b->release();
   for (auto& w : c->ws) {
@@ -682,6 +689,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   c->mp_ntrees_cfg = m->m.mp_ntrees_cfg;
   c->num_channels = m->m.num_channels;
   if (c->hp_ntrees > kMaxList || c->mp_ntrees_cfg > kMaxList || c->mp_ntrees_cfg < 1) return fail(CRF_ERR_UNSUPPORTED, "forest size outside 1..128 trees");
+  if ((rc = upload(c->d_hp_slots16, c->hp.slots16, c->w->stream)) || (rc = upload(c->d_mp_slots16, c->mp.slots16, c->w->stream))) return rc;
   if ((rc = upload(c->d_hp_slots, c->hp.slots, c->w->stream)) || (rc = upload(c->d_hp_roots, c->hp.roots, c->w->stream)) || (rc = upload(c->d_hp_m, c->hp.hp_m, c->w->stream)) ||
       (rc = upload(c->d_mp_slots, c->mp.slots, c->w->stream)) || (rc = upload(c->d_mp_roots, c->mp.roots, c->w->stream)) ||
       (rc = upload(c->d_mp_mask, c->mp.mp_mask, c->w->stream)) || (rc = upload(c->d_mp_leaf, c->mp.mp_leaf, c->w->stream)))

@@ -469,6 +469,7 @@ struct TraverseArgs {
   const stack_t* stacks;
   size_t stack_face_stride, plane_stride;
   const DevSlot* slots;
+  const DevSlot16* slots16;      // compact form of the same slots (k_traverse16)
   const int32_t* roots;        // shared tree list (head pose) or nullptr
   const int32_t* face_roots;   // [face][kMaxList] composed lists (FFD) or nullptr
   const int32_t* face_ntrees;  // [face] or nullptr
@@ -578,6 +579,69 @@ __global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
     if (lane == 0 && tests) atomicAdd(&a.counters[a.cnt_tests], (unsigned long long)tests);
     n_active = __popc(__ballot_sync(0xffffffffu, active));
     if (threadIdx.x == 0) atomicAdd(&a.counters[a.cnt_trav], (unsigned long long)n_active * nt);
+  }
+}
+
+// Exact floor(s / area) for s <= 255 * area < 2^18 without a stored reciprocal: float estimate, then a +-1 fix-up.
+__device__ __forceinline__ int mean_exact(uint32_t s, uint32_t area) {
+  int q = (int)(__uint2float_rn(s) * __frcp_rn(__uint2float_rn(area)));
+  const int r = (int)s - q * (int)area;
+  q += (r >= (int)area) ? 1 : 0;
+  q -= (r < 0) ? 1 : 0;
+  return q;
+}
+
+// k_traverse on the compact 16-byte slots: half the bytes per node fetch (the 256-bit fetch of the wide slot returns
+// 1 KB per warp to the register file, as much as the eight corner loads together).
+template <int NW, bool COUNT>
+__global__ void __launch_bounds__(NW * 32) k_traverse16(TraverseArgs a) {
+  extern __shared__ int32_t s_leaf[];  // [32][nt]
+  const int f = blockIdx.y;
+  const FaceDesc d = a.fd[f];
+  const int nx = (d.W - kPatch + a.stride - 1) / a.stride, ny = (d.H - kPatch + a.stride - 1) / a.stride;
+  const int nxb = (nx + 31) >> 5;
+  const int tile = blockIdx.x;
+  if (nx <= 0 || ny <= 0 || tile >= nxb * ny) return;
+  const int iy = tile / nxb, ixb = tile - iy * nxb;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ix = ixb * 32 + lane;
+  const bool active = ix < nx;
+  const int nt = a.face_ntrees ? a.face_ntrees[f] : a.ntrees;
+  const int32_t* roots = a.face_roots ? a.face_roots + (size_t)f * kMaxList : a.roots;
+  const stack_t* __restrict__ origin = a.stacks + f * a.stack_face_stride + (size_t)(iy * a.stride) * kRowStride + (active ? ix : 0) * a.stride;
+  const DevSlot16* __restrict__ slots = a.slots16;
+  unsigned tests = 0;
+  for (int t = warp; t < nt; t += NW) {
+    int cur = roots[t];
+    int leaf = -1;
+    if (active) {
+      for (;;) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(slots + cur));   // r1, r2, child, areas
+        if ((q.x >> 26) & 1u) { leaf = a.leaf_value ? __float_as_int(__ldg(a.leaf_value + q.z)) : (int)q.z; break; }
+        const stack_t* __restrict__ p = origin + (size_t)((q.x >> 20) & 0x3f) * a.plane_stride;
+        const uint32_t a1 = ((q.x >> 5) & 31) * kRowStride + (q.x & 31), w1 = (q.x >> 10) & 31, e1 = a1 + ((q.x >> 15) & 31) * kRowStride;
+        const uint32_t a2 = ((q.y >> 5) & 31) * kRowStride + (q.y & 31), w2 = (q.y >> 10) & 31, e2 = a2 + ((q.y >> 15) & 31) * kRowStride;
+        const uint32_t A1 = __ldg(p + a1), B1 = __ldg(p + a1 + w1), C1 = __ldg(p + e1), D1 = __ldg(p + e1 + w1);
+        const uint32_t A2 = __ldg(p + a2), B2 = __ldg(p + a2 + w2), C2 = __ldg(p + e2), D2 = __ldg(p + e2 + w2);
+        const int m1 = mean_exact(D1 - B1 - C1 + A1, q.w & 0xffff), m2 = mean_exact(D2 - B2 - C2 + A2, q.w >> 16);
+        const int thr = (int)((q.y >> 20) & 0x3ff) - 256;
+        cur = (int)q.z + ((m1 - m2) > thr ? 1 : 0);  // go left iff mean1 - mean2 <= threshold
+        if (COUNT) tests++;
+      }
+    }
+    s_leaf[lane * nt + t] = leaf;
+  }
+  __syncthreads();
+  const int npatch_tile = min(32, nx - ixb * 32);
+  int32_t* out = a.leaf_out + f * a.leaf_face_stride;
+  for (int i = threadIdx.x; i < npatch_tile * nt; i += NW * 32) {
+    const int l = i / nt, t = i - l * nt;
+    out[((size_t)(ixb * 32 + l) * ny + iy) * nt + t] = s_leaf[i];
+  }
+  if (COUNT) {
+    tests = __reduce_add_sync(0xffffffffu, tests);
+    if (lane == 0 && tests) atomicAdd(&a.counters[a.cnt_tests], (unsigned long long)tests);
+    if (threadIdx.x == 0) atomicAdd(&a.counters[a.cnt_trav], (unsigned long long)npatch_tile * nt);
   }
 }
 

@@ -109,6 +109,16 @@ int pack_forests(const std::vector<const FlatForest*>& forests, ForestKind kind,
           s.child = pair;
         }
         out.slots[slot_of[ni]] = s;
+        DevSlot16 c{};
+        c.child = s.child;
+        if (n.leaf >= 0) c.r1 = 1u << 26;
+        else {
+          c.r1 = (uint32_t)n.r1[0] | (uint32_t)n.r1[1] << 5 | (uint32_t)n.r1[2] << 10 | (uint32_t)n.r1[3] << 15 | (uint32_t)n.channel << 20;
+          c.r2 = (uint32_t)n.r2[0] | (uint32_t)n.r2[1] << 5 | (uint32_t)n.r2[2] << 10 | (uint32_t)n.r2[3] << 15 | (uint32_t)(n.threshold + 256) << 20;
+          c.areas = (uint32_t)n.r1[2] * n.r1[3] | ((uint32_t)n.r2[2] * n.r2[3]) << 16;
+        }
+        if (out.slots16.size() < out.slots.size()) out.slots16.resize(out.slots.size());
+        out.slots16[slot_of[ni]] = c;
       }
     }
   }

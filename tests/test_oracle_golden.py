@@ -73,6 +73,11 @@ def test_node_test_integer_division_equivalence():
         m = (1 << 31) // area + 1
         mg = ((s << 1) * m) >> 32
         assert np.array_equal(q, fl) and np.array_equal(q, mg), area
+        # k_traverse16's reciprocal-free form: float estimate + one exact fix-up step
+        est = (s.astype(np.float32) * (np.float32(1) / np.float32(area))).astype(np.int64)
+        r = s - est * area
+        est = est + (r >= area) - (r < 0)
+        assert np.array_equal(q, est), area
 
 
 def test_meanshift_empty_and_single(O):
