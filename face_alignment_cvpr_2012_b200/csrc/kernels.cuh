@@ -302,11 +302,12 @@ struct GaborSepSmem {
 };
 
 template <int K>
-__global__ void __launch_bounds__(256) k_gabor_sep(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
-                                                   const float* __restrict__ coef, int nu, float* __restrict__ mag, size_t mag_face_stride,
-                                                   size_t mag_plane_stride, uint32_t* __restrict__ minmax) {
+__global__ void __launch_bounds__(256, 3) k_gabor_sep(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
+                                                      const float* __restrict__ coef, int nu, float* __restrict__ mag, size_t mag_face_stride,
+                                                      size_t mag_plane_stride, uint32_t* __restrict__ minmax) {
   using G = GaborGeom<K>;
-  constexpr int R = K / 2, TH = G::TH, PITCH = G::PITCH;
+  constexpr int R = K / 2, TH = G::TH, PITCH = G::PITCH, HT = TH / 2;   // TH = 16 + K - 1 is even
+  static_assert(TH % 2 == 0, "row pass pairs rows r and r + TH/2");
   extern __shared__ __align__(16) float s_gs[];
   float (*tile)[PITCH] = reinterpret_cast<float (*)[PITCH]>(s_gs);
   float (*rre)[128] = reinterpret_cast<float (*)[128]>(s_gs + TH * PITCH);
@@ -329,35 +330,44 @@ __global__ void __launch_bounds__(256) k_gabor_sep(const FaceDesc* __restrict__ 
   }
   __syncthreads();
   const float dc = cf[7 * K * 4 + K];
-  const int x0 = (tid & 31) * 4, rA = tid >> 5;
+  // Shared-memory traffic is what bounds this kernel, so every coefficient fetched serves two rows: the row pass works on
+  // rows (r, r + TH/2) together, the column pass on two vertically adjacent outputs (which also share the row-pass
+  // values they read).  Column-pass thread: outputs (2q, 2q + 1) x 4 columns, q = warp.
+  const int x0 = (tid & 31) * 4, q2 = (tid >> 5) * 2;
+
   // ---- Gaussian: row pass into rre, column pass into registers
-  for (int it = tid; it < TH * 32; it += 256) {
+  for (int it = tid; it < HT * 32; it += 256) {
     const int r = it >> 5, xs = (it & 31) * 4;
-    float px[4 * G::NF4];
-    const float4* row = reinterpret_cast<const float4*>(&tile[r][xs]);
+    float px[2][4 * G::NF4];
 #pragma unroll
-    for (int q = 0; q < G::NF4; q++) { const float4 v = row[q]; px[4 * q] = v.x; px[4 * q + 1] = v.y; px[4 * q + 2] = v.z; px[4 * q + 3] = v.w; }
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int h = 0; h < 2; h++) {
+      const float4* row = reinterpret_cast<const float4*>(&tile[r + h * HT][xs]);
+#pragma unroll
+      for (int q = 0; q < G::NF4; q++) { const float4 v = row[q]; px[h][4 * q] = v.x; px[h][4 * q + 1] = v.y; px[h][4 * q + 2] = v.z; px[h][4 * q + 3] = v.w; }
+    }
+    float a[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
     for (int i = 0; i < K; i++) {
       const float c = g1[i];
 #pragma unroll
-      for (int o = 0; o < 4; o++) a[o] = __fmaf_rn(px[o + i], c, a[o]);
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int o = 0; o < 4; o++) a[h][o] = __fmaf_rn(px[h][o + i], c, a[h][o]);
     }
-    *reinterpret_cast<float4*>(&rre[r][xs]) = make_float4(a[0], a[1], a[2], a[3]);
+#pragma unroll
+    for (int h = 0; h < 2; h++) *reinterpret_cast<float4*>(&rre[r + h * HT][xs]) = make_float4(a[h][0], a[h][1], a[h][2], a[h][3]);
   }
   __syncthreads();
-  float Gs[2][4];
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-#pragma unroll
-    for (int o = 0; o < 4; o++) Gs[h][o] = 0.f;
-#pragma unroll 5
-    for (int j = 0; j < K; j++) {
-      const float4 v = *reinterpret_cast<const float4*>(&rre[rA + 8 * h + j][x0]);
-      const float c = g1[j];
-      Gs[h][0] = __fmaf_rn(v.x, c, Gs[h][0]); Gs[h][1] = __fmaf_rn(v.y, c, Gs[h][1]);
-      Gs[h][2] = __fmaf_rn(v.z, c, Gs[h][2]); Gs[h][3] = __fmaf_rn(v.w, c, Gs[h][3]);
+  float Gs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  {
+    float cprev = 0.f;
+#pragma unroll 2
+    for (int t = 0; t <= K; t++) {   // row-pass row q2 + t feeds output q2 (tap t) and output q2 + 1 (tap t - 1)
+      const float4 v = *reinterpret_cast<const float4*>(&rre[q2 + t][x0]);
+      const float c = t < K ? g1[t] : 0.f;
+      if (t < K) { Gs[0][0] = __fmaf_rn(v.x, c, Gs[0][0]); Gs[0][1] = __fmaf_rn(v.y, c, Gs[0][1]); Gs[0][2] = __fmaf_rn(v.z, c, Gs[0][2]); Gs[0][3] = __fmaf_rn(v.w, c, Gs[0][3]); }
+      if (t > 0) { Gs[1][0] = __fmaf_rn(v.x, cprev, Gs[1][0]); Gs[1][1] = __fmaf_rn(v.y, cprev, Gs[1][1]); Gs[1][2] = __fmaf_rn(v.z, cprev, Gs[1][2]); Gs[1][3] = __fmaf_rn(v.w, cprev, Gs[1][3]); }
+      cprev = c;
     }
   }
   __syncthreads();
@@ -367,45 +377,68 @@ __global__ void __launch_bounds__(256) k_gabor_sep(const FaceDesc* __restrict__ 
     const float2* hxm = hx + mu * K;
     const float2* hym = hy + mu * K;
 #pragma unroll 1
-    for (int it = tid; it < TH * 32; it += 256) {
+    for (int it = tid; it < HT * 32; it += 256) {
       const int r = it >> 5, xs = (it & 31) * 4;
-      float px[4 * G::NF4];
-      const float4* row = reinterpret_cast<const float4*>(&tile[r][xs]);
+      float px[2][4 * G::NF4];
 #pragma unroll
-      for (int q = 0; q < G::NF4; q++) { const float4 v = row[q]; px[4 * q] = v.x; px[4 * q + 1] = v.y; px[4 * q + 2] = v.z; px[4 * q + 3] = v.w; }
-      float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int h = 0; h < 2; h++) {
+        const float4* row = reinterpret_cast<const float4*>(&tile[r + h * HT][xs]);
+#pragma unroll
+        for (int q = 0; q < G::NF4; q++) { const float4 v = row[q]; px[h][4 * q] = v.x; px[h][4 * q + 1] = v.y; px[h][4 * q + 2] = v.z; px[h][4 * q + 3] = v.w; }
+      }
+      float a[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, b[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
       for (int i = 0; i < K; i++) {
         const float2 c = hxm[i];
 #pragma unroll
-        for (int o = 0; o < 4; o++) { a[o] = __fmaf_rn(px[o + i], c.x, a[o]); b[o] = __fmaf_rn(px[o + i], c.y, b[o]); }
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int o = 0; o < 4; o++) { a[h][o] = __fmaf_rn(px[h][o + i], c.x, a[h][o]); b[h][o] = __fmaf_rn(px[h][o + i], c.y, b[h][o]); }
       }
-      *reinterpret_cast<float4*>(&rre[r][xs]) = make_float4(a[0], a[1], a[2], a[3]);
-      *reinterpret_cast<float4*>(&rim[r][xs]) = make_float4(b[0], b[1], b[2], b[3]);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        *reinterpret_cast<float4*>(&rre[r + h * HT][xs]) = make_float4(a[h][0], a[h][1], a[h][2], a[h][3]);
+        *reinterpret_cast<float4*>(&rim[r + h * HT][xs]) = make_float4(b[h][0], b[h][1], b[h][2], b[h][3]);
+      }
     }
     __syncthreads();
+    float re[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, im[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    {
+      float2 cprev = make_float2(0.f, 0.f);
+#pragma unroll 2
+      for (int t = 0; t <= K; t++) {
+        const float4 a = *reinterpret_cast<const float4*>(&rre[q2 + t][x0]);
+        const float4 b = *reinterpret_cast<const float4*>(&rim[q2 + t][x0]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        const float2 c = t < K ? hym[t] : make_float2(0.f, 0.f);
+        if (t < K) {
+#pragma unroll
+          for (int o = 0; o < 4; o++) {
+            re[0][o] = __fmaf_rn(av[o], c.x, re[0][o]); re[0][o] = __fmaf_rn(-bv[o], c.y, re[0][o]);
+            im[0][o] = __fmaf_rn(av[o], c.y, im[0][o]); im[0][o] = __fmaf_rn(bv[o], c.x, im[0][o]);
+          }
+        }
+        if (t > 0) {
+#pragma unroll
+          for (int o = 0; o < 4; o++) {
+            re[1][o] = __fmaf_rn(av[o], cprev.x, re[1][o]); re[1][o] = __fmaf_rn(-bv[o], cprev.y, re[1][o]);
+            im[1][o] = __fmaf_rn(av[o], cprev.y, im[1][o]); im[1][o] = __fmaf_rn(bv[o], cprev.x, im[1][o]);
+          }
+        }
+        cprev = c;
+      }
+    }
     float vmin = __int_as_float(0x7f800000), vmax = 0.f;
     float* mplane = mag + blockIdx.y * mag_face_stride + (size_t)(nu * 7 + mu) * mag_plane_stride;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      float re[4] = {0.f, 0.f, 0.f, 0.f}, im[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 5
-      for (int j = 0; j < K; j++) {
-        const float4 a = *reinterpret_cast<const float4*>(&rre[rA + 8 * h + j][x0]);
-        const float4 b = *reinterpret_cast<const float4*>(&rim[rA + 8 * h + j][x0]);
-        const float2 c = hym[j];
-        re[0] = __fmaf_rn(a.x, c.x, re[0]); re[0] = __fmaf_rn(-b.x, c.y, re[0]); im[0] = __fmaf_rn(a.x, c.y, im[0]); im[0] = __fmaf_rn(b.x, c.x, im[0]);
-        re[1] = __fmaf_rn(a.y, c.x, re[1]); re[1] = __fmaf_rn(-b.y, c.y, re[1]); im[1] = __fmaf_rn(a.y, c.y, im[1]); im[1] = __fmaf_rn(b.y, c.x, im[1]);
-        re[2] = __fmaf_rn(a.z, c.x, re[2]); re[2] = __fmaf_rn(-b.z, c.y, re[2]); im[2] = __fmaf_rn(a.z, c.y, im[2]); im[2] = __fmaf_rn(b.z, c.x, im[2]);
-        re[3] = __fmaf_rn(a.w, c.x, re[3]); re[3] = __fmaf_rn(-b.w, c.y, re[3]); im[3] = __fmaf_rn(a.w, c.y, im[3]); im[3] = __fmaf_rn(b.w, c.x, im[3]);
-      }
-      const int r = r0 + rA + 8 * h;
+      const int r = r0 + q2 + h;
       if (r < H) {
         float m[4];
 #pragma unroll
         for (int o = 0; o < 4; o++) {
-          const float rr = __fmaf_rn(-dc, Gs[h][o], re[o]);
-          m[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[o], im[o]), __fmul_rn(rr, rr)));
+          const float rr = __fmaf_rn(-dc, Gs[h][o], re[h][o]);
+          m[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[h][o], im[h][o]), __fmul_rn(rr, rr)));
           if (x0 + o < W) { vmin = fminf(vmin, m[o]); vmax = fmaxf(vmax, m[o]); }
         }
         *reinterpret_cast<float4*>(&mplane[(size_t)r * 128 + x0]) = make_float4(m[0], m[1], m[2], m[3]);
