@@ -8,6 +8,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.cuh"
@@ -121,6 +122,8 @@ struct crf_ctx {
   int device = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned staging for ROI-mode uploads
+  size_t h_stage_bytes[2] = {0, 0};
   crf_options_t opt{};
   int hp_ntrees = 0, mp_ntrees_cfg = 0, num_channels = 38;
   PackedForest hp, mp;  // host copies (object-id maps for the stage API)
@@ -460,18 +463,36 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
   }
   // chunks of consecutive faces; a chunk's frames are the distinct frames its faces name
   const int chunk = pick_chunk(c, Hmax_first, headpose_only);
-  struct Chunk { int f0, f1, Hmax; std::vector<int> frames; };
+  // Two upload modes per chunk.  Frame mode: the distinct frames of the chunk go up whole (crops, dense boxes).  ROI mode:
+  // when the boxes cover well under the frames' area (a few faces in a 1080p / 4K frame), only the box pixels travel — packed
+  // row by row into a pinned staging buffer on the host while the GPU works on the previous chunk, then one H2D copy.
+  struct Chunk { int f0, f1, Hmax; bool roi; size_t bytes; std::vector<int> frames; };
   std::vector<Chunk> chunks;
+  std::vector<crf_rect_t> src_box((size_t)n);   // where the pixels are in the caller's frame (ROI mode rewrites the descriptor)
   for (int f0 = 0; f0 < n; f0 += chunk) {
-    Chunk ch; ch.f0 = f0; ch.f1 = std::min(n, f0 + chunk); ch.Hmax = 0;
+    Chunk ch; ch.f0 = f0; ch.f1 = std::min(n, f0 + chunk); ch.Hmax = 0; ch.roi = false; ch.bytes = 0;
+    std::unordered_map<int, int> slot_of;
+    size_t roi_bytes = 0;
     for (int i = f0; i < ch.f1; i++) {
       const int im = image_of_box ? image_of_box[i] : i;
       if (im < 0 || im >= n_images) return fail(CRF_ERR_ARG, "image index out of range");
-      int slot = -1;
-      for (size_t k = ch.frames.size(); k-- > 0;) if (ch.frames[k] == im) { slot = (int)k; break; }
-      if (slot < 0) { slot = (int)ch.frames.size(); ch.frames.push_back(im); }
+      auto it = slot_of.find(im);
+      int slot;
+      if (it == slot_of.end()) { slot = (int)ch.frames.size(); ch.frames.push_back(im); slot_of.emplace(im, slot); }
+      else slot = it->second;
       descs[i].img_off = (size_t)slot * img_bytes;
+      src_box[i] = boxes[i];
+      roi_bytes += ((size_t)boxes[i].width * boxes[i].height * 3 + 15) & ~(size_t)15;
       ch.Hmax = std::max(ch.Hmax, descs[i].H);
+    }
+    ch.bytes = ch.frames.size() * img_bytes;
+    if (roi_bytes * 10 < ch.bytes * 6) {
+      ch.roi = true; ch.bytes = roi_bytes;
+      size_t off = 0;
+      for (int i = f0; i < ch.f1; i++) {
+        descs[i].img_off = off; descs[i].img_step = (size_t)boxes[i].width * 3; descs[i].bx = 0; descs[i].by = 0;
+        off += ((size_t)boxes[i].width * boxes[i].height * 3 + 15) & ~(size_t)15;
+      }
     }
     chunks.push_back(std::move(ch));
   }
@@ -483,9 +504,20 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
   CU(cudaMemcpyAsync(c->d_fd.p, descs.data(), (size_t)n * sizeof(FaceDesc), cudaMemcpyHostToDevice, s0));
   CU(cudaMemsetAsync(c->d_faces.p, 0, (size_t)n * sizeof(crf_face_t), s0));
   c->cnt.h2d_bytes += (size_t)n * sizeof(FaceDesc);
-  size_t max_frames = 0; int Hmax_all = 0, max_faces = 0;
-  for (auto& ch : chunks) { max_frames = std::max(max_frames, ch.frames.size()); Hmax_all = std::max(Hmax_all, ch.Hmax); max_faces = std::max(max_faces, ch.f1 - ch.f0); }
-  for (int b = 0; b < 2; b++) if ((rc = c->d_imgs[b].reserve(max_frames * img_bytes))) return rc;
+  size_t max_bytes = 0, max_roi = 0; int Hmax_all = 0, max_faces = 0;
+  for (auto& ch : chunks) {
+    max_bytes = std::max(max_bytes, ch.bytes); if (ch.roi) max_roi = std::max(max_roi, ch.bytes);
+    Hmax_all = std::max(Hmax_all, ch.Hmax); max_faces = std::max(max_faces, ch.f1 - ch.f0);
+  }
+  for (int b = 0; b < 2; b++) {
+    if ((rc = c->d_imgs[b].reserve(max_bytes))) return rc;
+    if (max_roi > c->h_stage_bytes[b]) {
+      if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]);
+      c->h_stage[b] = nullptr; c->h_stage_bytes[b] = 0;
+      CU(cudaHostAlloc((void**)&c->h_stage[b], max_roi + max_roi / 4, cudaHostAllocDefault));
+      c->h_stage_bytes[b] = max_roi + max_roi / 4;
+    }
+  }
   Plan p; p.n = max_faces; p.Hmax = Hmax_all; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
   p.need_ffd = !headpose_only;
   const int nsets = chunks.size() > 1 ? c->nstreams : 1;
@@ -494,6 +526,21 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
   auto copy_chunk = [&](size_t k) -> int {
     const Chunk& ch = chunks[k];
     const int b = (int)(k & 1);
+    if (ch.roi) {
+      if (k >= 2) CU(cudaEventSynchronize(c->ev_copied[b]));   // the staging buffer's previous upload has left the host
+      uint8_t* st = c->h_stage[b];
+      for (int i = ch.f0; i < ch.f1; i++) {
+        const crf_rect_t& bx = src_box[i];
+        const uint8_t* src = images[image_of_box ? image_of_box[i] : i] + (size_t)bx.y * step + (size_t)bx.x * 3;
+        uint8_t* dst = st + descs[i].img_off;
+        const size_t rowb = (size_t)bx.width * 3;
+        for (int r = 0; r < bx.height; r++) std::memcpy(dst + (size_t)r * rowb, src + (size_t)r * step, rowb);
+      }
+      CU(cudaMemcpyAsync(c->d_imgs[b].p, st, ch.bytes, cudaMemcpyHostToDevice, c->copy_stream));
+      c->cnt.h2d_bytes += ch.bytes;
+      CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+      return CRF_OK;
+    }
     // consecutive frames that are also consecutive in host memory go in one copy
     size_t i = 0;
     while (i < ch.frames.size()) {
@@ -650,6 +697,7 @@ void crf_ctx_destroy(crf_ctx* c) {
   c->timer.destroy();
   for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (int i = 0; i < 2; i++) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
   delete c;
 }
 
