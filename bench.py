@@ -302,17 +302,20 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             ],
             "work_per_step": {k: work[k] for k in ("hp_node_tests", "ffd_node_tests", "hp_traversals", "ffd_traversals", "votes", "vote_passes")},
         }
-        # host-side p50 latency of single-face calls (default strides of the reference: 4 / 3)
+        # host-side p50 latency of single-face crf_analyze_crops calls: at the strides of this workload (comparable with the
+        # CPU sample's p50) and at the reference's default strides 4 / 3
         try:
+            def p50_single(c):
+                lat, one = [], np.zeros(1, crf.FACE_DTYPE)
+                for i in range(40):
+                    t0 = time.perf_counter()
+                    c.analyze_crops_ptr(h_crops.data_ptr() + i * CROP * CROP * 3, 1, CROP, CROP, one)
+                    lat.append((time.perf_counter() - t0) * 1e3)
+                return float(np.median(lat[8:]))
+            line["p50_ms_per_face"] = p50_single(ctx)
             ctx_lat = crf.Context(gm, local_rank, crf._options(None))
-            lat = []
-            one = np.zeros(1, crf.FACE_DTYPE)
-            for i in range(40):
-                t0 = time.perf_counter()
-                ctx_lat.analyze_crops_ptr(h_crops.data_ptr() + i * CROP * CROP * 3, 1, CROP, CROP, one)
-                lat.append((time.perf_counter() - t0) * 1e3)
-            line["p50_ms_per_face"] = float(np.median(lat[8:]))
-            line["config"]["p50"] = "single-face crf_analyze_crops calls, reference default strides 4/3, host buffers"
+            line["p50_ms_per_face_default_strides"] = p50_single(ctx_lat)
+            line["config"]["p50"] = "single-face crf_analyze_crops calls with host buffers: stride 1 (this workload) / reference default strides 4,3"
             ctx_lat.close()
         except Exception as e:  # noqa: BLE001
             line["p50_error"] = str(e)

@@ -72,7 +72,36 @@ class MeanShiftOption:  # include/MeanShift.hpp:16-25
 
 
 @dataclass
-class FaceForestOptions:  # include/FaceForest.hpp:60-68 (face-detector fields omitted: boxes are given)
+class FaceDetectionOption:  # include/FaceForest.hpp:21-31
+    min_feature_size: int = 30
+    min_neighbors: int = 1
+    search_scale_factor: float = 1.3
+    path_face_cascade: str = ""
+
+
+def intersect(r1, r2):
+    """src/face_utils.cpp:325-347."""
+    x = r2[0] if r1[0] < r2[0] else r1[0]
+    y = r2[1] if r1[1] < r2[1] else r1[1]
+    w = (r1[0] + r1[2] if r1[0] + r1[2] < r2[0] + r2[2] else r2[0] + r2[2]) - x
+    h = (r1[1] + r1[3] if r1[1] + r1[3] < r2[1] + r2[3] else r2[1] + r2[3]) - y
+    return (0, 0, 0, 0) if w <= 0 or h <= 0 else (x, y, w, h)
+
+
+def enlarge_detections(boxes, rows: int, cols: int) -> list:
+    """The box post-processing of FaceForest::detectFace (src/FaceForest.cpp:147-157): Haar boxes are too tight, so each
+    grows by 5 % of its width on both sides and by 2 x 15 % of its width downwards, clipped to the image."""
+    out = []
+    for (x, y, w, h) in boxes:
+        offset_x = int(w * 0.05)
+        offset_y = int(w * 0.15)
+        out.append(intersect((int(x) - offset_x, int(y), int(w) + offset_x * 2, int(h) + offset_y * 2), (0, 0, cols, rows)))
+    return out
+
+
+@dataclass
+class FaceForestOptions:  # include/FaceForest.hpp:60-68
+    fd_option: FaceDetectionOption = field(default_factory=FaceDetectionOption)
     head_pose_forest_param: ForestParam = field(default_factory=ForestParam)
     mp_forest_param: ForestParam = field(default_factory=ForestParam)
     pose_option: HeadPoseEstimatorOption = field(default_factory=HeadPoseEstimatorOption)
@@ -322,6 +351,15 @@ class FaceForest:
                                   o.mp_forest_param.ntrees or 20)
             self.model = model
             self.ctx = Context(model, self.option.device, _options(self.option))
+            self.m_face_cascade = None
+            if self.option.fd_option.path_face_cascade:   # src/FaceForest.cpp:23-28; the cascade itself stays on the CPU
+                import cv2
+                self.m_face_cascade = cv2.CascadeClassifier(self.option.fd_option.path_face_cascade)
+                if self.m_face_cascade.empty():
+                    import sys
+                    print(f"(!) Error loading face detection model: {self.option.fd_option.path_face_cascade}", file=sys.stderr)
+                    self.model = None; self.ctx = None
+                    return
         except CrfError as e:  # src/FaceForest.cpp:31-36: ERROR(...) and leave is_inizialized false
             import sys
             print(f"(!) Error loading forest: {e}", file=sys.stderr)
@@ -342,10 +380,23 @@ class FaceForest:
             return face
         return f
 
-    def analyzeImage(self, img: np.ndarray, faces_bboxes, faces: list | None = None) -> list:
-        """src/FaceForest.cpp:161-181 with the detectFace() boxes given by the caller."""
+    @staticmethod
+    def detectFace(img: np.ndarray, face_cascade, fd_option: FaceDetectionOption) -> list:
+        """src/FaceForest.cpp:136-159: cv::CascadeClassifier::detectMultiScale on the host (OpenCV, as in the reference) +
+        the box enlargement.  Not part of the GPU hot path: its boxes feed analyzeFace."""
+        mfs = (fd_option.min_feature_size, fd_option.min_feature_size)
+        det = face_cascade.detectMultiScale(img, scaleFactor=fd_option.search_scale_factor, minNeighbors=fd_option.min_neighbors, flags=0, minSize=mfs)
+        return enlarge_detections([tuple(int(v) for v in b) for b in det], img.shape[0], img.shape[1])
+
+    def analyzeImage(self, img: np.ndarray, faces_bboxes=None, faces: list | None = None) -> list:
+        """src/FaceForest.cpp:161-181.  With faces_bboxes=None the Haar cascade of fd_option runs first (host), as in the
+        reference; otherwise the caller's boxes are used.  All faces of the frame go through the GPU in one launch."""
         if not self.is_inizialized:
             raise AssertionError("CV_Assert(is_inizialized)")  # src/FaceForest.cpp:167
+        if faces_bboxes is None:
+            if self.m_face_cascade is None:
+                raise AssertionError("no face cascade loaded: pass boxes or set fd_option.path_face_cascade")
+            faces_bboxes = self.detectFace(img, self.m_face_cascade, self.option.fd_option)
         out = self._to_faces(self.ctx.analyze_faces(img, list(faces_bboxes)), faces_bboxes)
         if faces is not None:
             faces.clear(); faces.extend(out)

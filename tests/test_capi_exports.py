@@ -64,3 +64,11 @@ def test_cpp_compat_header_builds_and_mirrors_error_behaviour(crf, synth_dirs, t
     hp, ffd = synth_dirs
     r = subprocess.run([str(exe), hp, ffd], capture_output=True, text=True)
     assert r.returncode == 0 and "compat_smoke ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_detectface_box_postprocessing(crf):
+    """FaceForest::detectFace's enlargement (src/FaceForest.cpp:147-157) and intersect (src/face_utils.cpp:325-347)."""
+    assert crf.enlarge_detections([(100, 50, 100, 100)], 480, 640) == [(95, 50, 110, 130)]
+    assert crf.enlarge_detections([(2, 400, 101, 101)], 480, 640) == [(0, 400, 108, 80)]       # clipped left and bottom
+    assert crf.enlarge_detections([(600, 10, 60, 60)], 480, 640) == [(597, 10, 43, 78)]       # clipped right
+    assert crf.intersect((700, 0, 10, 10), (0, 0, 640, 480)) == (0, 0, 0, 0)

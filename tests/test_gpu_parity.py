@@ -441,3 +441,29 @@ def test_eval_ffd_driver(crf, staged_models, lfw_faces, lfw_golden, gpu, tmp_pat
         iod = np.linalg.norm((gt[0] + gt[1]) / 2 - (gt[6] + gt[7]) / 2)
         want = np.linalg.norm(gt - lfw_golden["recs"][k]["ffd"], axis=1) / iod
         assert np.allclose(e, want, rtol=1e-5, atol=1e-6)
+
+
+def test_analyze_image_with_host_haar_detector(crf, staged_models, lfw_faces, gpu):
+    """FaceForest::analyzeImage as the reference runs it: Haar cascade on the host (cv2), enlarged boxes, GPU pipeline."""
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    xml = wl.STAGED / "haarcascade_frontalface_alt.xml"
+    if not xml.exists():
+        pytest.skip("Haar cascade not staged")
+    opt = crf.FaceForestOptions()
+    opt.fd_option.path_face_cascade = str(xml)
+    ff = crf.FaceForest(opt, model=staged_models[0])
+    assert ff.is_inizialized
+    found = 0
+    for f in lfw_faces[:8]:
+        faces = ff.analyzeImage(f["img"])
+        for face in faces:
+            x, y, w, h = face.bbox
+            ax, ay, aw, ah = f["box"]
+            inter = max(0, min(x + w, ax + aw) - max(x, ax)) * max(0, min(y + h, ay + ah) - max(y, ay))
+            if inter > 0.5 * aw * ah:   # the detection that matches the annotated face: landmarks must land near the annotation
+                found += 1
+                pred = face.ffd_cordinates + np.array([x, y])
+                gt = f["parts"] + np.array([ax, ay])
+                iod = np.linalg.norm((gt[0] + gt[1]) / 2.0 - (gt[6] + gt[7]) / 2.0)
+                assert np.mean(np.linalg.norm(pred - gt, axis=1)) / iod < 0.25
+    assert found >= 6

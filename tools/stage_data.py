@@ -31,7 +31,8 @@ def main() -> int:
     print(f"packed image: {(out / 'model.crfb200').stat().st_size / 1e6:.1f} MB, reloads in {time.time() - t:.2f}s")
     for p in sorted((REF / "imgs").iterdir()):
         shutil.copy(p, out / "imgs" / p.name)
-    print("staged", len(list((out / "imgs").iterdir())), "files under staged/imgs")
+    shutil.copy(REF / "haarcascade_frontalface_alt.xml", out / "haarcascade_frontalface_alt.xml")
+    print("staged", len(list((out / "imgs").iterdir())), "files under staged/imgs + the Haar cascade (host-side detectFace)")
     return 0
 
 
