@@ -355,14 +355,14 @@ static int launch_meanshift(crf_ctx* c, const FaceDesc* fd, int nchains, crf_fac
   Span s(c, CRF_STAGE_MEANSHIFT);
   MeanShiftOpt mo{c->opt.ms_kernel_size, c->opt.ms_max_iterations, c->opt.ms_stopping_criteria};
   // 32 chains share a fold warp when there are enough chains to fill the GPU; small batches spread over more CTAs
-  const int cpc = nchains >= 8192 ? 32 : (nchains >= 2048 ? 16 : 8);
+  const int cpc = nchains >= 8192 ? 32 : std::max(1, std::min(8, nchains / 296));   // small batches: up to two CTAs per SM before chains share one
   const dim3 grid((nchains + cpc - 1) / cpc);
   unsigned long long* cnt = c->counting ? c->d_counters.as<unsigned long long>() : nullptr;
 #define CRF_MS(MINB)                                                                                                                                    \
-  k_meanshift<MINB, false><<<grid, kFoldThreads, kMsSmem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(), \
+  k_meanshift<MINB, false><<<grid, kFoldThreads, MsGeom<false>::smem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(), \
                                                                   c->w->d_vote_base.as<int32_t>(), cpc, mo, faces, cnt)
   if (cpc < 32)
-    k_meanshift<3, true><<<grid, kFoldThreads, kMsSmem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(),
+    k_meanshift<3, true><<<grid, kFoldThreads, MsGeom<true>::smem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(),
                                                                      c->w->d_vote_base.as<int32_t>(), cpc, mo, faces, cnt);
   else if (c->ms_variant == 2) CRF_MS(2); else if (c->ms_variant == 4) CRF_MS(4); else CRF_MS(3);
 #undef CRF_MS
@@ -793,10 +793,10 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   CU(cudaFuncSetAttribute(k_gabor_sep<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<13>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_sep<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<9>::bytes));
   CU(cudaFuncSetAttribute(k_hp_reduce_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHpSmem));
-  CU(cudaFuncSetAttribute(k_meanshift<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
-  CU(cudaFuncSetAttribute(k_meanshift<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
-  CU(cudaFuncSetAttribute(k_meanshift<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
-  CU(cudaFuncSetAttribute(k_meanshift<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+  CU(cudaFuncSetAttribute(k_meanshift<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsGeom<false>::smem));
+  CU(cudaFuncSetAttribute(k_meanshift<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsGeom<false>::smem));
+  CU(cudaFuncSetAttribute(k_meanshift<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsGeom<false>::smem));
+  CU(cudaFuncSetAttribute(k_meanshift<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsGeom<true>::smem));
   if ((rc = c->d_counters.reserve(sizeof(unsigned long long) * CNT_NUM))) return rc;
   CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * CNT_NUM, c->w->stream));
   if ((rc = c->d_misc.reserve(4096))) return rc;

@@ -1028,15 +1028,22 @@ __device__ __forceinline__ void vote_terms(const DevVote q, bool first_pass, flo
   wy = q.y * w;
 }
 
-constexpr int kMsTile = 64;
-constexpr size_t kMsSmem = (size_t)2 * 3 * kMsTile * 33 * sizeof(float);  // dynamic shared memory of k_meanshift
+// Dense CTAs: 32 chains, tiles of 64 votes.  Sparse CTAs (small batches): at most 8 chains and tiles of 256 votes, so a
+// chain's pass takes a quarter of the barrier-separated steps.
+template <bool SPARSE> struct MsGeom {
+  static constexpr int TILE = SPARSE ? 256 : 64;
+  static constexpr int PITCH = SPARSE ? 9 : 33;     // odd pitches: conflict-free for producers (lanes = votes) and the fold (lanes = chains)
+  static constexpr int MAX_CPC = SPARSE ? 8 : 32;
+  static constexpr size_t smem = (size_t)2 * 3 * TILE * PITCH * sizeof(float);   // dynamic shared memory of k_meanshift
+};
 
 template <int MINB, bool SPARSE>
 __global__ void __launch_bounds__(kFoldThreads, MINB) k_meanshift(const FaceDesc* __restrict__ fd, int nchains, const DevVote* __restrict__ votes, size_t vote_cap,
                                                                const int32_t* __restrict__ vote_counts, const int32_t* __restrict__ vote_base, int cpc /* chains per CTA, <= 32 */, MeanShiftOpt o, crf_face_t* __restrict__ faces,
                                                             unsigned long long* counters) {
   extern __shared__ __align__(16) float s_dyn[];
-  typedef float Tile[kMsTile][33];
+  constexpr int kMsTile = MsGeom<SPARSE>::TILE;
+  typedef float Tile[kMsTile][MsGeom<SPARSE>::PITCH];
   Tile* s_w = reinterpret_cast<Tile*>(s_dyn);   // [2]
   Tile* s_x = s_w + 2;
   Tile* s_y = s_w + 4;
@@ -1125,12 +1132,13 @@ __global__ void __launch_bounds__(kFoldThreads, MINB) k_meanshift(const FaceDesc
       if (warp == 0) {
         const int b = tile & 1;
         const int kmax = s_active[lane] ? min(kMsTile, s_n[lane] - tile * kMsTile) : 0;
+        const int jl = lane < MsGeom<SPARSE>::MAX_CPC ? lane : 0;   // lanes beyond the CTA's chains fold nothing (kmax = 0)
 #pragma unroll 8
         for (int k = 0; k < kMsTile; k++) {   // branch-free: adding +0 is exact (the sums never hold -0)
           const bool valid = k < kmax;
-          sx += valid ? s_x[b][k][lane] : 0.f;
-          sy += valid ? s_y[b][k][lane] : 0.f;
-          sw += valid ? s_w[b][k][lane] : 0.f;
+          sx += valid ? s_x[b][k][jl] : 0.f;
+          sy += valid ? s_y[b][k][jl] : 0.f;
+          sw += valid ? s_w[b][k][jl] : 0.f;
         }
       } else if (tile + 1 < ntiles) {
         produce(tile + 1);
