@@ -8,6 +8,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -226,6 +227,24 @@ static int ensure(crf_ctx* c, const Plan& p) {
   }
   if (p.want_u8 && (rc = c->w->d_u8planes.reserve(n * c->w->u8_fs))) return rc;
   return CRF_OK;
+}
+
+// Host-side row packing of face boxes into pinned staging, split over a few threads (memcpy-bound).
+template <class F>
+static void parallel_for(int n, size_t bytes, F&& fn) {
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int nt = (int)std::min<size_t>(std::min<unsigned>(hw, 8u), std::max<size_t>(1, bytes >> 21));   // one thread per ~2 MB, at most 8
+  if (nt <= 1 || n < 2) { for (int i = 0; i < n; i++) fn(i); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([&, t] { for (int i = (int)((long long)n * t / nt), e = (int)((long long)n * (t + 1) / nt); i < e; i++) fn(i); });
+  for (auto& x : th) x.join();
+}
+
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
 }
 
 // src/FaceForest.cpp:199-204 (scale, scaled size) + the argument checks of the path.
@@ -466,6 +485,8 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
   // Two upload modes per chunk.  Frame mode: the distinct frames of the chunk go up whole (crops, dense boxes).  ROI mode:
   // when the boxes cover well under the frames' area (a few faces in a 1080p / 4K frame), only the box pixels travel — packed
   // row by row into a pinned staging buffer on the host while the GPU works on the previous chunk, then one H2D copy.
+  // Pageable sources always go through the staging buffer (a threaded pack + pinned H2D beats the driver's pageable copy).
+  const bool src_pinned = is_pinned_host(images[image_of_box ? image_of_box[0] : 0]);
   struct Chunk { int f0, f1, Hmax; bool roi; size_t bytes; std::vector<int> frames; };
   std::vector<Chunk> chunks;
   std::vector<crf_rect_t> src_box((size_t)n);   // where the pixels are in the caller's frame (ROI mode rewrites the descriptor)
@@ -486,7 +507,7 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
       ch.Hmax = std::max(ch.Hmax, descs[i].H);
     }
     ch.bytes = ch.frames.size() * img_bytes;
-    if (roi_bytes * 10 < ch.bytes * 6) {
+    if (roi_bytes * 10 < ch.bytes * 6 || (!src_pinned && roi_bytes <= ch.bytes + ch.bytes / 4)) {
       ch.roi = true; ch.bytes = roi_bytes;
       size_t off = 0;
       for (int i = f0; i < ch.f1; i++) {
@@ -529,13 +550,15 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
     if (ch.roi) {
       if (k >= 2) CU(cudaEventSynchronize(c->ev_copied[b]));   // the staging buffer's previous upload has left the host
       uint8_t* st = c->h_stage[b];
-      for (int i = ch.f0; i < ch.f1; i++) {
+      parallel_for(ch.f1 - ch.f0, ch.bytes, [&](int k2) {
+        const int i = ch.f0 + k2;
         const crf_rect_t& bx = src_box[i];
         const uint8_t* src = images[image_of_box ? image_of_box[i] : i] + (size_t)bx.y * step + (size_t)bx.x * 3;
         uint8_t* dst = st + descs[i].img_off;
         const size_t rowb = (size_t)bx.width * 3;
-        for (int r = 0; r < bx.height; r++) std::memcpy(dst + (size_t)r * rowb, src + (size_t)r * step, rowb);
-      }
+        if (rowb == step) std::memcpy(dst, src, rowb * bx.height);
+        else for (int r = 0; r < bx.height; r++) std::memcpy(dst + (size_t)r * rowb, src + (size_t)r * step, rowb);
+      });
       CU(cudaMemcpyAsync(c->d_imgs[b].p, st, ch.bytes, cudaMemcpyHostToDevice, c->copy_stream));
       c->cnt.h2d_bytes += ch.bytes;
       CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
