@@ -815,6 +815,11 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   CU(cudaFuncSetAttribute(k_gabor_sep<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<19>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_sep<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<13>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_sep<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<9>::bytes));
+  if (const char* v = std::getenv("CRF_CARVEOUT")) {   // experiment: shared-memory carveout (percent) of the traversal kernels
+    const int pct = (int)std::strtol(v, nullptr, 0);
+    CU(cudaFuncSetAttribute(k_traverse16<10, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    CU(cudaFuncSetAttribute(k_traverse16<15, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  }
   CU(cudaFuncSetAttribute(k_hp_reduce_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHpSmem));
   CU(cudaFuncSetAttribute(k_meanshift<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsGeom<false>::smem));
   CU(cudaFuncSetAttribute(k_meanshift<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsGeom<false>::smem));

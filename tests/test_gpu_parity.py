@@ -467,3 +467,25 @@ def test_analyze_image_with_host_haar_detector(crf, staged_models, lfw_faces, gp
                 iod = np.linalg.norm((gt[0] + gt[1]) / 2.0 - (gt[6] + gt[7]) / 2.0)
                 assert np.mean(np.linalg.norm(pred - gt, axis=1)) / iod < 0.25
     assert found >= 6
+
+
+def test_pinned_and_pageable_sources_agree(crf, synth_models, gpu):
+    """The host entry point takes two upload routes: whole frames straight from pinned memory, or box pixels packed into the
+    library's pinned staging (pageable callers, sparse boxes).  Same records either way."""
+    import ctypes as C
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, _ = synth_models
+    crops, _ = wl.make_crops(70, seed=5)
+    ctx = crf.Context(gm, 0, crf._options(None, max_chunk=32))
+    pageable = ctx.analyze_crops(crops)
+    p = C.c_void_p()
+    crf.capi.check(crf.lib().crf_host_alloc(C.byref(p), crops.nbytes))
+    try:
+        C.memmove(p, crops.ctypes.data, crops.nbytes)
+        out = np.zeros(len(crops), crf.FACE_DTYPE)
+        ctx.analyze_crops_ptr(p.value, len(crops), 100, 100, out)
+        assert out.tobytes() == pageable.tobytes()
+        h2d = ctx.counters()["h2d_bytes"]
+        assert h2d >= 2 * crops.nbytes
+    finally:
+        crf.lib().crf_host_free(p)
