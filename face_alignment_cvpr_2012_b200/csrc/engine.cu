@@ -349,6 +349,8 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
     const dim3 g16(((nx + 31) / 32) * ny, n);
     if (NW == 10) { if (c->counting) k_traverse16<10, true><<<g16, 320, smem, c->w->stream>>>(a); else k_traverse16<10, false><<<g16, 320, smem, c->w->stream>>>(a); launched = true; }
     if (NW == 15) { if (c->counting) k_traverse16<15, true><<<g16, 480, smem, c->w->stream>>>(a); else k_traverse16<15, false><<<g16, 480, smem, c->w->stream>>>(a); launched = true; }
+    if (NW == 20) { if (c->counting) k_traverse16<20, true><<<g16, 640, smem, c->w->stream>>>(a); else k_traverse16<20, false><<<g16, 640, smem, c->w->stream>>>(a); launched = true; }
+    if (NW == 7) { if (c->counting) k_traverse16<7, true><<<g16, 224, smem, c->w->stream>>>(a); else k_traverse16<7, false><<<g16, 224, smem, c->w->stream>>>(a); launched = true; }
   }
   CRF_TRAV(5, 32, 0) CRF_TRAV(5, 32, 1) CRF_TRAV(5, 32, 2) CRF_TRAV(5, 32, 3)
   CRF_TRAV(5, 8, 0) CRF_TRAV(5, 8, 1) CRF_TRAV(5, 8, 2) CRF_TRAV(5, 8, 3)
