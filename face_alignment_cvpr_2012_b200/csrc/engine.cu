@@ -273,7 +273,8 @@ static int launch_resize(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, const 
   return CRF_OK;
 }
 
-static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool minmax_planes, bool want_u8) {
+static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, int extra /* 0: features {0,1,2}; 1: FC_MIN_MAX; 2: FC_NORM */, bool want_u8) {
+  const bool minmax_planes = extra != 0;
   uint8_t* u8 = want_u8 ? c->w->d_u8planes.as<uint8_t>() : nullptr;
   uint32_t* dbg32 = want_u8 ? c->w->d_int32.as<uint32_t>() : nullptr;   // full 32-bit integrals, stage API only
   {
@@ -281,7 +282,8 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
     PlainPlanes pp{};
     int nw;
     if (!minmax_planes) { nw = 3; pp.which[0] = 0; pp.plane[0] = 0; pp.which[1] = 1; pp.plane[1] = 36; pp.which[2] = 2; pp.plane[2] = 37; }
-    else { nw = 2; pp.which[0] = 3; pp.plane[0] = 0; pp.which[1] = 4; pp.plane[1] = 1; }
+    else if (extra == 1) { nw = 2; pp.which[0] = 3; pp.plane[0] = 0; pp.which[1] = 4; pp.plane[1] = 1; }
+    else { nw = 1; pp.which[0] = 5; pp.plane[0] = 0; }
     k_plain_channels<<<dim3(nw, n), 128, 0, c->w->stream>>>(fd, c->w->d_scaled.as<uint8_t>(), c->w->scaled_fs, c->w->d_stacks.as<stack_t>(), c->w->stack_fs,
                                                          c->w->plane_stride, u8, c->w->u8_fs, dbg32, pp);
     KCHECK(); count_launch(c, CRF_STAGE_PLAIN);
@@ -415,7 +417,7 @@ static int run_faces(crf_ctx* c, const FaceDesc* d_fd, int n, int Hmax, const ui
   int rc;
   if ((rc = launch_resize(c, d_fd, n, Hmax, d_imgs))) return rc;
   if (imgs_consumed) CU(cudaEventRecord(imgs_consumed, c->w->stream));
-  if ((rc = launch_channels(c, d_fd, n, Hmax, false, false))) return rc;
+  if ((rc = launch_channels(c, d_fd, n, Hmax, 0, false))) return rc;
   if ((rc = launch_traverse(c, d_fd, n, Hmax, true, c->opt.hp_stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees, true))) return rc;
   if ((rc = launch_hp_reduce(c, d_fd, n, c->opt.hp_stride, !headpose_only, tree_cap, d_faces))) return rc;
   if (headpose_only) return CRF_OK;
@@ -996,7 +998,7 @@ int crf_stage_channels(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t*
   CU(cudaSetDevice(c->device));
   int rc = stage_upload_scaled(c, scaled, W, H, 38, true, true, false, false, 1, 4, 3);
   if (rc) return rc;
-  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, false, true))) return rc;
+  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, 0, true))) return rc;
   return stage_download_planes(c, 38, W, H, planes_u8, integrals);
 }
 
@@ -1006,8 +1008,18 @@ int crf_stage_minmax(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* p
   CU(cudaSetDevice(c->device));
   int rc = stage_upload_scaled(c, scaled, W, H, 38, false, true, false, false, 1, 4, 3);
   if (rc) return rc;
-  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, true, true))) return rc;
+  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, 1, true))) return rc;
   return stage_download_planes(c, 2, W, H, planes_u8, integrals);
+}
+
+int crf_stage_norm(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* plane_u8, uint32_t* integral) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!scaled) return fail(CRF_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = stage_upload_scaled(c, scaled, W, H, 38, false, true, false, false, 1, 4, 3);
+  if (rc) return rc;
+  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, 2, true))) return rc;
+  return stage_download_planes(c, 1, W, H, plane_u8, integral);
 }
 
 // planes -> integral stack of one synthetic face

@@ -120,7 +120,7 @@ __device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, stack_t*
 
 // a5 + a7 (+ a7b): FC_GRAY, FC_SOBEL (d/dy then d/dx, 8U-saturated), FC_MIN_MAX
 // (include/FeatureChannelFactory.hpp:46-57, :120-165).  grid = (nwhich, faces), 128 threads.
-// which: 0 gray, 1 Sobel dy, 2 Sobel dx, 3 erode, 4 dilate.  plane_of[which] = output plane index.
+// which: 0 gray, 1 Sobel dy, 2 Sobel dx, 3 erode, 4 dilate, 5 equalizeHist (FC_NORM, :58-70).  plane_of[which] = output plane index.
 struct PlainPlanes { int which[5]; int plane[5]; };
 
 __global__ void __launch_bounds__(128) k_plain_channels(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
@@ -134,31 +134,57 @@ __global__ void __launch_bounds__(128) k_plain_channels(const FaceDesc* __restri
   uint8_t* u8o = u8planes ? u8planes + blockIdx.y * u8_face_stride + (size_t)plane * W * H : nullptr;
   uint32_t* o32 = dbg32 ? dbg32 + blockIdx.y * stack_face_stride + (size_t)plane * plane_stride : nullptr;
   auto G = [&](int y, int x) -> int { return g[(size_t)y * 128 + x]; };
-  if (which == 0) {
-    integral_plane([&](int r, int c) -> uint32_t { return G(r, c); }, W, H, out, u8o, o32);
-  } else if (which == 1 || which == 2) {
-    const bool is_dx = which == 2;
-    integral_plane([&](int r, int c) -> uint32_t {
-      const int ym = border101(r - 1, H), yp = border101(r + 1, H), xm = border101(c - 1, W), xp = border101(c + 1, W);
-      int v;
-      if (is_dx) v = (G(ym, xp) + 2 * G(r, xp) + G(yp, xp)) - (G(ym, xm) + 2 * G(r, xm) + G(yp, xm));
-      else v = (G(yp, xm) + 2 * G(yp, c) + G(yp, xp)) - (G(ym, xm) + 2 * G(ym, c) + G(ym, xp));
-      return (uint32_t)min(max(v, 0), 255);
-    }, W, H, out, u8o, o32);
-  } else {
-    const bool is_max = which == 4;
-    integral_plane([&](int r, int c) -> uint32_t {
-      int lo = 255, hi = 0;
-      for (int j = -1; j <= 1; j++)
-        for (int i = -1; i <= 1; i++) {
-          const int yy = r + j, xx = c + i;
-          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-          const int v = G(yy, xx);
-          lo = min(lo, v); hi = max(hi, v);
+  __shared__ int s_hist[256];
+  __shared__ uint8_t s_lut[256];
+  if (which == 5) {
+    // cv::equalizeHist: histogram in shared memory, the 256-entry LUT by one thread (sequential cumulative sum, f32 scale)
+    for (int i = threadIdx.x; i < 256; i += 128) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < W * H; i += 128) atomicAdd(&s_hist[G(i / W, i % W)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int i = 0;
+      while (i < 256 && !s_hist[i]) ++i;
+      const int total = W * H;
+      if (i < 256 && s_hist[i] == total) {
+        for (int k = 0; k < 256; k++) s_lut[k] = (uint8_t)i;
+      } else {
+        for (int k = 0; k <= i && k < 256; k++) s_lut[k] = 0;
+        const float scale = __fdiv_rn(255.f, (float)(total - s_hist[i]));
+        int sum = 0;
+        for (++i; i < 256; ++i) {
+          sum += s_hist[i];
+          s_lut[i] = (uint8_t)min(max(__float2int_rn(__fmul_rn((float)sum, scale)), 0), 255);
         }
-      return (uint32_t)(is_max ? hi : lo);
-    }, W, H, out, u8o, o32);
+      }
+    }
+    __syncthreads();
   }
+  // one pixel function for every kind (a single instance of the integral's shared-memory band)
+  integral_plane([&](int r, int c) -> uint32_t {
+    switch (which) {
+      case 0: return (uint32_t)G(r, c);
+      case 1: case 2: {
+        const int ym = border101(r - 1, H), yp = border101(r + 1, H), xm = border101(c - 1, W), xp = border101(c + 1, W);
+        int v;
+        if (which == 2) v = (G(ym, xp) + 2 * G(r, xp) + G(yp, xp)) - (G(ym, xm) + 2 * G(r, xm) + G(yp, xm));   // d/dx
+        else v = (G(yp, xm) + 2 * G(yp, c) + G(yp, xp)) - (G(ym, xm) + 2 * G(ym, c) + G(ym, xp));              // d/dy
+        return (uint32_t)min(max(v, 0), 255);
+      }
+      case 5: return s_lut[G(r, c)];
+      default: {
+        int lo = 255, hi = 0;
+        for (int j = -1; j <= 1; j++)
+          for (int i = -1; i <= 1; i++) {
+            const int yy = r + j, xx = c + i;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const int v = G(yy, xx);
+            lo = min(lo, v); hi = max(hi, v);
+          }
+        return (uint32_t)(which == 4 ? hi : lo);
+      }
+    }
+  }, W, H, out, u8o, o32);
 }
 
 // Integral of caller-supplied dense u8 planes [C][H][W] (stage API: synthetic channels).

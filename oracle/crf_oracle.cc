@@ -415,6 +415,28 @@ static void minmax3x3_u8(const Plane8& src, Plane8& mn, Plane8& mx) {
     }
 }
 
+// FeatureChannelFactory.hpp:58-70  cv::equalizeHist (FC_NORM): histogram, first non-empty bin i0, scale = 255 / (N - hist[i0]) in f32,
+// lut[i] = cvRound(cumulative(i0 < j <= i) * scale), lut[i0] = 0; a constant image maps to itself.
+static void equalize_hist_u8(const Plane8& src, Plane8& dst) {
+  dst.rows = src.rows; dst.cols = src.cols; dst.d.assign(src.d.size(), 0);
+  int hist[256] = {0};
+  for (uint8_t v : src.d) hist[v]++;
+  int i = 0;
+  while (i < 256 && !hist[i]) ++i;
+  const int total = (int)src.d.size();
+  if (i == 256) return;
+  if (hist[i] == total) { std::fill(dst.d.begin(), dst.d.end(), (uint8_t)i); return; }
+  uint8_t lut[256] = {0};
+  const float scale = (256 - 1.f) / (total - hist[i]);
+  int sum = 0;
+  for (lut[i++] = 0; i < 256; ++i) {
+    sum += hist[i];
+    long v = std::lrintf(sum * scale);
+    lut[i] = (uint8_t)std::min<long>(std::max<long>(v, 0), 255);
+  }
+  for (size_t p = 0; p < src.d.size(); p++) dst.d[p] = lut[src.d[p]];
+}
+
 // FeatureChannelFactory.hpp:186-251  createKernel / initGaborKernels (A.4)
 struct GaborKernel {
   int width = 0;
@@ -677,7 +699,13 @@ struct ImageSample {
         planes8.push_back(a); planes8.push_back(b);
         break;
       }
-      default: break;  // FC_CANNY / FC_NORM: out of scope
+      case 5: {                                                                // FC_NORM
+        Plane8 a;
+        equalize_hist_u8(img, a);
+        planes8.push_back(a);
+        break;
+      }
+      default: break;  // FC_CANNY: out of scope
     }
   }
   // src/ImageSample.cpp:30-64, integral branch (A.6)
@@ -1173,6 +1201,7 @@ int orc_num_planes(int features_mask) {
   if (features_mask & 2) n += 35;
   if (features_mask & 4) n += 2;
   if (features_mask & 8) n += 2;
+  if (features_mask & 32) n += 1;
   return n;
 }
 

@@ -54,6 +54,9 @@ def main():
     d["sobel_dx"] = cv2.Sobel(img, cv2.CV_8U, 1, 0)
     k3 = np.ones((3, 3), np.uint8)
     d["erode"] = cv2.erode(img, k3); d["dilate"] = cv2.dilate(img, k3)
+    d["equalize"] = cv2.equalizeHist(img)
+    lowc = (img // 4 + 90).astype(np.uint8)
+    d["equalize_src2"] = lowc; d["equalize2"] = cv2.equalizeHist(lowc)
     bank = O.gabor_bank()
     for idx in range(7):
         d[f"f2d_re_{idx}"] = cv2.filter2D(img, cv2.CV_32F, bank[idx][0]); d[f"f2d_im_{idx}"] = cv2.filter2D(img, cv2.CV_32F, bank[idx][1])

@@ -87,6 +87,16 @@ def test_channels_golden_plane(sctx, cv2_golden):
     assert np.abs(d).max() <= 1 and (d != 0).mean() < 1e-3
 
 
+def test_norm_channel(O, sctx, cv2_golden):
+    """FC_NORM (cv::equalizeHist + integral) against cv2's own output and the oracle, incl. a constant image."""
+    for src, ref in ((cv2_golden["plane"], cv2_golden["equalize"]), (cv2_golden["equalize_src2"], cv2_golden["equalize2"])):
+        p, integ = sctx.stage_channels(src, norm=True)
+        assert np.array_equal(p[0], ref)
+        assert np.array_equal(integ[0], O.channels(src, features_mask=0b100000)[1][0].astype(np.uint32))
+    p, _ = sctx.stage_channels(np.full((64, 125), 200, np.uint8), norm=True)
+    assert (p[0] == 200).all()
+
+
 def test_channels_degenerate_images(O, sctx):
     for img in (np.zeros((125, 125), np.uint8), np.full((125, 125), 255, np.uint8), np.tile(np.arange(125, dtype=np.uint8), (125, 1))):
         planes, integ = sctx.stage_channels(img)

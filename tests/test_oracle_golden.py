@@ -37,6 +37,17 @@ def test_plain_channels(O, cv2_golden):
     assert np.array_equal(mm[0], cv2_golden["erode"]) and np.array_equal(mm[1], cv2_golden["dilate"])
 
 
+def test_equalize_hist(O, cv2_golden):
+    """FC_NORM = cv::equalizeHist (include/FeatureChannelFactory.hpp:58-70)."""
+    p, _ = O.channels(cv2_golden["plane"], features_mask=0b100000)
+    assert np.array_equal(p[0], cv2_golden["equalize"])
+    p, _ = O.channels(cv2_golden["equalize_src2"], features_mask=0b100000)
+    assert np.array_equal(p[0], cv2_golden["equalize2"])
+    const = np.full((40, 125), 77, np.uint8)
+    p, _ = O.channels(const, features_mask=0b100000)
+    assert (p[0] == 77).all()
+
+
 def test_gabor_7x7_filter2d_bit_exact(O, cv2_golden):
     img = cv2_golden["plane"]
     for idx in range(7):
