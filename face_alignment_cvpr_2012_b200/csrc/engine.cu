@@ -333,12 +333,12 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   const size_t smem = (size_t)32 * smem_trees * 4;
   // variant = LW (32 or 8) | MODE << 8 | NW (5 or 10) << 16; CRF_TRAVERSE_VARIANT overrides for experiments
   // defaults from tools/traverse_variants.py on B200: one warp per tree for the 15-tree head-pose forest, 10 warps for 20 trees;
-  // rows of 32 x-adjacent patches and the compact 16-byte slots at dense strides; 8 x 4 blocks and 256-bit loads of the wide
+  // rows of 32 x-adjacent patches and the compact 16-byte slots at dense strides; 16 x 2 blocks and 256-bit loads of the wide
   // slots at sparse ones
   const int variant = c->traverse_variant ? c->traverse_variant
-                                           : (stride >= 3 ? (8 | (2 << 8) | (10 << 16)) : (32 | (4 << 8) | ((hp ? 15 : 10) << 16)));
+                                           : (stride >= 3 ? (16 | (2 << 8) | (15 << 16)) : (32 | (4 << 8) | ((hp ? 15 : 10) << 16)));
   const int LW = variant & 0xff, MODE = (variant >> 8) & 0xff, NW = (variant >> 16) & 0xff;
-  const int tiles = LW != 8 ? ((nx + 31) / 32) * ny : ((nx + 7) / 8) * ((ny + 3) / 4);
+  const int tiles = ((nx + LW - 1) / LW) * ((ny + 32 / LW - 1) / (32 / LW));
   const dim3 grid(tiles, n);
 #define CRF_TRAV(NW_, LW_, MODE_)                                                                          \
   if (NW == NW_ && LW == LW_ && MODE == MODE_) {                                                           \
@@ -357,7 +357,7 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   CRF_TRAV(5, 32, 0) CRF_TRAV(5, 32, 1) CRF_TRAV(5, 32, 2) CRF_TRAV(5, 32, 3)
   CRF_TRAV(5, 8, 0) CRF_TRAV(5, 8, 1) CRF_TRAV(5, 8, 2) CRF_TRAV(5, 8, 3)
   CRF_TRAV(10, 32, 0) CRF_TRAV(10, 32, 2) CRF_TRAV(10, 8, 2) CRF_TRAV(10, 8, 3)
-  CRF_TRAV(15, 32, 2) CRF_TRAV(20, 32, 2) CRF_TRAV(4, 32, 2) CRF_TRAV(8, 32, 2)
+  CRF_TRAV(15, 32, 2) CRF_TRAV(20, 32, 2) CRF_TRAV(4, 32, 2) CRF_TRAV(8, 32, 2) CRF_TRAV(10, 16, 2) CRF_TRAV(15, 16, 2)
 #undef CRF_TRAV
   if (!launched) return fail(CRF_ERR_ARG, "unknown CRF_TRAVERSE_VARIANT");
   KCHECK(); count_launch(c, stage);
