@@ -29,7 +29,7 @@ extern "C" {
 #define CRF_NUM_POSE_FORESTS 5    /* poseT hard-codes 5 bins               src/FaceForest.cpp:216-222 */
 #define CRF_NUM_HEADPOSE_CLASSES 5/* NUM_HEADPOSE_CLASSES                  include/Constants.hpp:66   */
 #define CRF_MAX_SCALED_H 521      /* f32 integral exactness limit (sums < 2^24), SURVEY H7           */
-#define CRF_ROW_STRIDE 128        /* u32 words per integral row on the device                         */
+#define CRF_ROW_STRIDE 128        /* elements per integral row on the device                          */
 
 typedef enum {
   CRF_OK = 0,
@@ -59,8 +59,8 @@ typedef struct {
   int   ms_kernel_size;        /* 10 */
   int   ms_max_iterations;     /* 7 */
   float ms_stopping_criteria;  /* 0.05 */
-  int   max_chunk;             /* faces resident per device chunk; 0 = library default */
-  int   max_scaled_h;          /* tallest scaled face the context is sized for; 0 = 192 */
+  int   max_chunk;             /* faces per launch; 0 = as many as fit min(64 GB, half the free memory), at most 4096 */
+  int   max_scaled_h;          /* ignored: work buffers grow on demand (kept for ABI stability) */
 } crf_options_t;
 
 /* Face (include/FaceForest.hpp:70-75) plus the intermediate results the parity tests need. */
@@ -75,7 +75,8 @@ typedef struct {
   int   ffd[CRF_NUM_PARTS][2];       /* ffd_cordinates after *= 1/scale (src/FaceForest.cpp:256-257): bbox-relative original pixels */
   int   ms_iters[CRF_NUM_PARTS];     /* MeanShift iterations executed */
   int   n_votes[CRF_NUM_PARTS];      /* votes per part (src/face_utils.cpp:289-298) */
-  int   flags;                       /* bit0: composition clamped (reference would index out of bounds) */
+  int   flags;                       /* bit0: composition clamped (reference would index out of bounds); bits 1-2 are internal
+                                        (face re-run with worst-case capacities) and never set in returned records */
 } crf_face_t;
 
 typedef struct {
