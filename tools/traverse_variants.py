@@ -17,7 +17,7 @@ fs = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 gm = crf.Model(packed=str(wl.staged_model_path()))
 crops, _ = wl.make_crops(n)
 ref = None
-variants = [(10, 32, 2), (10, 16, 2), (15, 16, 2), (10, 8, 2)]
+variants = [(10, 32, 2), (10, 32, 4), (15, 32, 4)]
 for nw, lw, mode in variants:
     os.environ["CRF_TRAVERSE_VARIANT"] = str(lw | (mode << 8) | (nw << 16))
     ctx = crf.Context(gm, 0, crf._options(None, hp_stride=hs, ffd_stride=fs))
