@@ -55,6 +55,27 @@ static_assert(sizeof(DevSlot) == 32, "slot must be one 32-byte sector");
 struct alignas(16) DevSlot16 { uint32_t r1, r2; int32_t child; uint32_t areas; };
 static_assert(sizeof(DevSlot16) == 16, "compact slot is 16 bytes");
 
+// Window form of the same node for the dense (stride-1) traversal that gathers from SHARED memory (k_traverse_win):
+// a CTA keeps the 38 x 38-sample window of all planes that an 8 x 8 tile of patches can touch (rectangles of the model
+// end at offset <= kWinExtent inside the patch) as [plane][ring row][kWinCols] u32, rows addressed modulo kWinRows so that
+// stepping the tile down by 8 patches re-loads only 8 rows.  Everything a node test needs is pre-multiplied into byte
+// offsets of that layout; leaves loop onto themselves (child = own slot, zero rectangles, threshold 32767) so a finished
+// walk can keep executing the same instruction stream as its neighbour.
+constexpr int kWinTile = 8;                    // patches per tile side
+constexpr int kWinExtent = 30;                 // largest x + w / y + h the window covers
+constexpr int kWinRows = kWinTile + kWinExtent;     // 38 ring rows
+constexpr int kWinCols = 40;                   // 38 columns used; 40 = 160-byte rows, pitch == 8 (mod 32 banks)
+constexpr int kWinRowBytes = kWinCols * 4;
+constexpr int kWinPlaneBytes = kWinRows * kWinRowBytes;   // 6080
+struct alignas(32) DevSlotW {
+  uint32_t px1, px2;   // ch * kWinPlaneBytes + x * 4
+  uint32_t yh1, yh2;   // y * kWinRowBytes | (h * kWinRowBytes) << 16
+  uint32_t m1, m2;     // magic_for_area; leaf: m2 = forest-global leaf index
+  int32_t child;       // internal: slot of the left child; leaf: own slot
+  uint32_t tw;         // (uint16)thr | (w1 * 4) << 16 | (w2 * 4) << 24 | leaf << 31
+};
+static_assert(sizeof(DevSlotW) == 32, "window slot is one 32-byte sector");
+
 // MPLeaf (include/MPSample.hpp:137-159) with the vote predicate of src/face_utils.cpp:285-290 folded
 // into `mask` (bit i: part i votes) for the options of the context.
 struct alignas(16) DevMpLeaf {   // 48 bytes: three 128-bit loads
@@ -67,6 +88,8 @@ static_assert(sizeof(DevMpLeaf) == 48, "leaf record is three 16-byte words");
 struct PackedForest {
   std::vector<DevSlot> slots;
   std::vector<DevSlot16> slots16;    // same slots, compact form
+  std::vector<DevSlotW> slotsw;      // same slots, window form (valid when max_extent <= kWinExtent)
+  int max_extent = 0;                // largest x + w or y + h over all rectangles
   std::vector<int32_t> roots;        // slot of the root of tree t (forest-major for the jungle)
   std::vector<int32_t> forest_base;  // jungle: first tree of pose forest f in `roots`
   std::vector<int32_t> forest_ntrees;

@@ -129,7 +129,7 @@ struct crf_ctx {
   int hp_ntrees = 0, mp_ntrees_cfg = 0, num_channels = 38;
   PackedForest hp, mp;  // host copies (object-id maps for the stage API)
   // device model
-  Buf d_hp_slots16, d_mp_slots16, d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5], d_coef_sep[5];
+  Buf d_hp_slotsw, d_mp_slotsw, d_hp_slots16, d_mp_slots16, d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5], d_coef_sep[5];
   int gabor_width[5] = {0, 0, 0, 0, 0};
   ComposeTables ct{};
   // work buffers: two complete sets, so that consecutive chunks run on two streams and kernels bound by different
@@ -147,6 +147,8 @@ struct crf_ctx {
   crf_counters_t cnt{};
   bool counting = false;
   int traverse_variant = 0;  // 0 = pick by stride (see launch_traverse)
+  int sm_count = 148;
+  int win_hp = 0, win_ffd = 0;   // k_traverse_win variants (0 = default)
   // 1 = consecutive chunks run back to back on one stream (default: measured faster — co-resident Gabor CTAs shrink the L1
   // the gathers live on, and two chunks' stacks thrash L2); 2 = alternate chunks between two streams / work sets
   int nstreams = 1;
@@ -317,12 +319,12 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   a.fd = fd; a.stacks = c->w->d_stacks.as<stack_t>(); a.stack_face_stride = c->w->stack_fs; a.plane_stride = c->w->plane_stride;
   a.stride = stride;
   if (hp) {
-    a.slots = c->d_hp_slots.as<DevSlot>(); a.slots16 = c->d_hp_slots16.as<DevSlot16>(); a.roots = roots; a.ntrees = ntrees;
+    a.slots = c->d_hp_slots.as<DevSlot>(); a.slots16 = c->d_hp_slots16.as<DevSlot16>(); a.slotsw = c->d_hp_slotsw.as<DevSlotW>(); a.roots = roots; a.ntrees = ntrees;
     a.leaf_out = c->w->d_hp_leaf.as<int32_t>(); a.leaf_face_stride = c->w->hp_leaf_fs;
     a.cnt_tests = CNT_HP_TESTS; a.cnt_trav = CNT_HP_TRAV;
     if (hp_values) a.leaf_value = c->d_hp_m.as<float>();
   } else {
-    a.slots = c->d_mp_slots.as<DevSlot>(); a.slots16 = c->d_mp_slots16.as<DevSlot16>();
+    a.slots = c->d_mp_slots.as<DevSlot>(); a.slots16 = c->d_mp_slots16.as<DevSlot16>(); a.slotsw = c->d_mp_slotsw.as<DevSlotW>();
     a.face_roots = c->w->d_face_roots.as<int32_t>(); a.face_ntrees = c->w->d_face_ntrees.as<int32_t>();
     a.leaf_out = c->w->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->w->ffd_leaf_fs;
     a.cnt_tests = CNT_FFD_TESTS; a.cnt_trav = CNT_FFD_TRAV;
@@ -330,6 +332,33 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   a.counters = c->counting ? c->d_counters.as<unsigned long long>() : nullptr;
   const int nx = patches_1d(125, stride), ny = patches_1d(Hmax, stride);
   if (nx <= 0 || ny <= 0) return CRF_OK;
+  // Dense grids: gather from a shared-memory window instead of L1/L2 (k_traverse_win) when the model's rectangles fit the
+  // window and there are enough (face, tile column) items to keep every SM's persistent CTA busy.
+  // CRF_TRAVERSE_VARIANT=0x100001 forces it, any other non-zero value selects one of the global-gather variants below.
+  {
+    const int ncols = (patches_1d(125, 1) + kWinTile - 1) / kWinTile;
+    const bool fits = stride == 1 && (hp ? c->hp.max_extent : c->mp.max_extent) <= kWinExtent && c->num_channels <= kWinMaxPlanes;
+    const bool forced = c->traverse_variant == 0x100001;
+    if (forced && !fits) return fail(CRF_ERR_ARG, "CRF_TRAVERSE_VARIANT=0x100001 needs stride 1 and rectangles inside the window");
+    if (fits && (forced || (c->traverse_variant == 0 && (long long)n * ncols >= 2LL * c->sm_count))) {
+      const int nitems = n * ncols, grid = std::min(nitems, c->sm_count);
+      // (warps per CTA) | (walks per lane) << 8; CRF_WIN_HP / CRF_WIN_FFD override for experiments
+      const int wv = hp ? (c->win_hp ? c->win_hp : (30 | 1 << 8)) : (c->win_ffd ? c->win_ffd : (20 | 2 << 8));
+      bool ok = false;
+#define CRF_WIN(NW_, WK_)                                                                                                   \
+      if (wv == (NW_ | WK_ << 8)) {                                                                                          \
+        auto kf = c->counting ? k_traverse_win<NW_, WK_, true> : k_traverse_win<NW_, WK_, false>;                            \
+        CU(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmemBytes));                            \
+        kf<<<grid, NW_ * 32, kWinSmemBytes, c->w->stream>>>(a, nitems, ncols, c->num_channels);                              \
+        ok = true;                                                                                                           \
+      }
+      CRF_WIN(15, 2) CRF_WIN(20, 2) CRF_WIN(10, 2) CRF_WIN(30, 1) CRF_WIN(32, 1) CRF_WIN(20, 1) CRF_WIN(24, 1) CRF_WIN(28, 1) CRF_WIN(16, 1)
+#undef CRF_WIN
+      if (!ok) return fail(CRF_ERR_ARG, "unknown CRF_WIN_HP / CRF_WIN_FFD variant");
+      KCHECK(); count_launch(c, stage);
+      return CRF_OK;
+    }
+  }
   const size_t smem = (size_t)32 * smem_trees * 4;
   // variant = LW (32 or 8) | MODE << 8 | NW (5 or 10) << 16; CRF_TRAVERSE_VARIANT overrides for experiments
   // defaults from tools/traverse_variants.py on B200: one warp per tree for the 15-tree head-pose forest, 10 warps for 20 trees;
@@ -714,7 +743,7 @@ void crf_ctx_destroy(crf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   for (auto& w : c->ws) if (w.stream) cudaStreamSynchronize(w.stream);
-  Buf* all[] = {&c->d_hp_slots16, &c->d_mp_slots16, &c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
+  Buf* all[] = {&c->d_hp_slotsw, &c->d_mp_slotsw, &c->d_hp_slots16, &c->d_mp_slots16, &c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
                 &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_coef_sep[1], &c->d_coef_sep[2], &c->d_coef_sep[3], &c->d_coef_sep[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc};
   for (Buf* b : all) b->release();
   for (auto& w : c->ws) {
@@ -742,6 +771,8 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if (opt) c->opt = *opt; else crf_options_default(&c->opt);
   if (c->opt.hp_stride < 1 || c->opt.ffd_stride < 1) return fail(CRF_ERR_ARG, "strides must be >= 1");
   if (const char* v = std::getenv("CRF_TRAVERSE_VARIANT")) c->traverse_variant = (int)std::strtol(v, nullptr, 0);
+  if (const char* v = std::getenv("CRF_WIN_HP")) c->win_hp = (int)std::strtol(v, nullptr, 0);
+  if (const char* v = std::getenv("CRF_WIN_FFD")) c->win_ffd = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_MS_VARIANT")) c->ms_variant = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_STREAMS")) c->nstreams = std::strtol(v, nullptr, 0) == 2 ? 2 : 1;
   for (auto& w : c->ws) CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
@@ -765,6 +796,8 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   c->num_channels = m->m.num_channels;
   if (c->hp_ntrees > kMaxList || c->mp_ntrees_cfg > kMaxList || c->mp_ntrees_cfg < 1) return fail(CRF_ERR_UNSUPPORTED, "forest size outside 1..128 trees");
   if ((rc = upload(c->d_hp_slots16, c->hp.slots16, c->w->stream)) || (rc = upload(c->d_mp_slots16, c->mp.slots16, c->w->stream))) return rc;
+  if ((rc = upload(c->d_hp_slotsw, c->hp.slotsw, c->w->stream)) || (rc = upload(c->d_mp_slotsw, c->mp.slotsw, c->w->stream))) return rc;
+  CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   if ((rc = upload(c->d_hp_slots, c->hp.slots, c->w->stream)) || (rc = upload(c->d_hp_roots, c->hp.roots, c->w->stream)) || (rc = upload(c->d_hp_m, c->hp.hp_m, c->w->stream)) ||
       (rc = upload(c->d_mp_slots, c->mp.slots, c->w->stream)) || (rc = upload(c->d_mp_roots, c->mp.roots, c->w->stream)) ||
       (rc = upload(c->d_mp_mask, c->mp.mp_mask, c->w->stream)) || (rc = upload(c->d_mp_leaf, c->mp.mp_leaf, c->w->stream)))

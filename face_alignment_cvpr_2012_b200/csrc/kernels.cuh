@@ -529,6 +529,7 @@ struct TraverseArgs {
   size_t stack_face_stride, plane_stride;
   const DevSlot* slots;
   const DevSlot16* slots16;      // compact form of the same slots (k_traverse16)
+  const DevSlotW* slotsw;        // window form of the same slots (k_traverse_win)
   const int32_t* roots;        // shared tree list (head pose) or nullptr
   const int32_t* face_roots;   // [face][kMaxList] composed lists (FFD) or nullptr
   const int32_t* face_ntrees;  // [face] or nullptr
@@ -701,6 +702,171 @@ __global__ void __launch_bounds__(NW * 32) k_traverse16(TraverseArgs a) {
     tests = __reduce_add_sync(0xffffffffu, tests);
     if (lane == 0 && tests) atomicAdd(&a.counters[a.cnt_tests], (unsigned long long)tests);
     if (threadIdx.x == 0) atomicAdd(&a.counters[a.cnt_trav], (unsigned long long)npatch_tile * nt);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Dense (stride 1) traversal with the corner gathers served from SHARED memory.
+// The global-gather kernels above are bound by the L1 data pipe and the L2 (16.5 G sector misses per
+// 4096 faces, 5.5 kB/clk of L2 traffic, 131-137 instructions per node visit).  Here a persistent CTA
+// owns a column of 8 x 8-patch tiles of one face and keeps, for ALL planes, the 38 x 38 samples the
+// tile can touch (device_forest.h: DevSlotW) in 231 040 bytes of shared memory, as a ring over rows:
+// the first tile of a column loads 38 rows, each further tile only the 8 new ones (coalesced 160-byte
+// row pieces, 16-byte vectors).  Warp = tree, lane = an 8 x 4 block of patches, two walks per lane
+// (rows ly and ly + 4) in one instruction stream; row pitch 40 words == 8 (mod 32) makes the 32 lanes
+// of a converged warp hit 32 different banks.  Only the 32-byte node records still come from L1/L2.
+// Used when stride == 1, the model's rectangles end at <= kWinExtent, and the batch fills the GPU.
+// grid = persistent CTAs; item = (face, tile column); NW warps.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWinSmemBytes = kWinPlaneBytes * 38;   // sized for the 38 planes of the shipped feature set
+constexpr int kWinMaxPlanes = 38;
+#ifndef CRF_WIN_PREFETCH
+#define CRF_WIN_PREFETCH 1
+#endif
+constexpr bool WIN_PREFETCH = CRF_WIN_PREFETCH != 0;
+
+// Predicated shared load: a walk parked on its leaf issues no request (its lane-private address would only add bank
+// conflicts to the live lanes of the warp).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr, uint32_t live) {
+  uint32_t v;   // left undefined for a parked walk: its node test is never used
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}" : "=r"(v) : "r"(addr), "r"(live));
+  return v;
+}
+
+__device__ __forceinline__ void ldg_slotw(const DevSlotW* p, uint4& q0, uint4& q1) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(p));
+}
+
+// One node test of a walk.  col = shared address of the lane's patch column, row = byte offset of the lane's patch
+// row inside the ring.  q0 = px1, px2, yh1, yh2; q1 = m1, m2, child, tw.  Returns the next slot.
+__device__ __forceinline__ int win_step(const DevSlotW* __restrict__ slots, uint32_t col, uint32_t row, const uint4 q0, const uint4 q1, uint32_t live) {
+  constexpr uint32_t kRing = kWinPlaneBytes;
+  uint32_t ra1 = row + (q0.z & 0xffffu); ra1 = min(ra1, ra1 - kRing);
+  uint32_t rc1 = ra1 + (q0.z >> 16);     rc1 = min(rc1, rc1 - kRing);
+  uint32_t ra2 = row + (q0.w & 0xffffu); ra2 = min(ra2, ra2 - kRing);
+  uint32_t rc2 = ra2 + (q0.w >> 16);     rc2 = min(rc2, rc2 - kRing);
+  const uint32_t ca1 = col + q0.x, cb1 = ca1 + ((q1.w >> 16) & 0xffu);
+  const uint32_t ca2 = col + q0.y, cb2 = ca2 + ((q1.w >> 24) & 0x7fu);
+  const uint32_t A1 = lds_u32(ca1 + ra1, live), B1 = lds_u32(cb1 + ra1, live), C1 = lds_u32(ca1 + rc1, live), D1 = lds_u32(cb1 + rc1, live);
+  const uint32_t A2 = lds_u32(ca2 + ra2, live), B2 = lds_u32(cb2 + ra2, live), C2 = lds_u32(ca2 + rc2, live), D2 = lds_u32(cb2 + rc2, live);
+  const int m1 = (int)__umulhi((D1 - B1 - C1 + A1) << 1, q1.x), m2 = (int)__umulhi((D2 - B2 - C2 + A2) << 1, q1.y);
+  const int thr = (int)(short)(q1.w & 0xffffu);
+  return (int)q1.z + ((m1 - m2) > thr ? 1 : 0);   // go left iff mean1 - mean2 <= threshold
+}
+
+template <int NW, int WALKS, bool COUNT>
+__global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int nitems, int ncols, int nplanes) {
+  static_assert(WALKS == 1 || WALKS == 2, "one or two walks per lane");
+  extern __shared__ __align__(16) uint8_t s_win[];
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_win);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lx = lane & 7, ly = lane >> 3;
+  const DevSlotW* __restrict__ slots = a.slotsw;
+  unsigned tests = 0;
+  unsigned long long trav = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int f = item / ncols, ixb = item - f * ncols;
+    const FaceDesc d = a.fd[f];
+    const int nx = d.W - kPatch, ny = d.H - kPatch;   // stride 1
+    const int x0 = ixb * kWinTile;
+    if (nx <= 0 || ny <= 0 || x0 >= nx) continue;
+    const int nrows = d.H + 1;
+    const stack_t* __restrict__ src = a.stacks + f * a.stack_face_stride + x0;
+    const int nt = a.face_ntrees ? a.face_ntrees[f] : a.ntrees;
+    const int32_t* roots = a.face_roots ? a.face_roots + (size_t)f * kMaxList : a.roots;
+    int32_t* out = a.leaf_out + f * a.leaf_face_stride;
+    const bool vx = x0 + lx < nx;
+    const int ntile_y = (ny + kWinTile - 1) / kWinTile;
+    for (int iyb = 0; iyb < ntile_y; iyb++) {
+      const int y0 = iyb * kWinTile;
+      // rows of this tile's window that are not in the ring yet
+      const int rbeg = iyb == 0 ? 0 : y0 + kWinExtent, rend = min(y0 + kWinRows, nrows);
+      const int nvec = max(rend - rbeg, 0) * nplanes * (kWinCols / 4);
+      __syncthreads();   // every walk of the previous tile is done with the rows about to be replaced
+#pragma unroll 4
+      for (int i = threadIdx.x; i < nvec; i += NW * 32) {
+        const int c = i % (kWinCols / 4), pr = i / (kWinCols / 4);
+        const int p = pr % nplanes, r = rbeg + pr / nplanes;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)p * a.plane_stride + (size_t)r * kRowStride) + c);
+        const uint32_t dst = s_base + p * kWinPlaneBytes + (r % kWinRows) * kWinRowBytes + c * 16;
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+      __syncthreads();
+      if (WIN_PREFETCH) {
+        // the stacks of a launch (2.4 MB per face) do not stay in L2: pull the rows of the next tile step (or the first window
+        // of the next item) towards L2 while this tile's walks run, one 32-byte sector per request
+        const stack_t* psrc = src;
+        int pbeg = y0 + kWinTile + kWinExtent, pend = min(y0 + kWinTile + kWinRows, nrows);
+        if (iyb + 1 >= ntile_y) {
+          const int nitem = item + gridDim.x;
+          pbeg = pend = 0;
+          if (nitem < nitems) {
+            const int nf = nitem / ncols;
+            psrc = a.stacks + nf * a.stack_face_stride + (nitem - nf * ncols) * kWinTile;
+            pend = min(kWinRows, a.fd[nf].H + 1);
+          }
+        }
+        const int nsec = max(pend - pbeg, 0) * nplanes * (kWinCols / 8);
+        for (int i = threadIdx.x; i < nsec; i += NW * 32) {
+          const int c = i % (kWinCols / 8), pr = i / (kWinCols / 8);
+          const int p = pr % nplanes, r = pbeg + pr / nplanes;
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(psrc + (size_t)p * a.plane_stride + (size_t)r * kRowStride + c * 8));
+        }
+      }
+      const int r0 = y0 % kWinRows;
+      const uint32_t col = s_base + lx * 4;
+      if (WALKS == 2) {
+        int ra = r0 + ly, rb = r0 + ly + 4;
+        ra -= ra >= kWinRows ? kWinRows : 0;
+        rb -= rb >= kWinRows ? kWinRows : 0;
+        const uint32_t rowA = ra * kWinRowBytes, rowB = rb * kWinRowBytes;
+        const bool vA = vx && y0 + ly < ny, vB = vx && y0 + ly + 4 < ny;
+        for (int t = warp; t < nt; t += NW) {
+          uint4 a0, a1, b0, b1;
+          ldg_slotw(slots + roots[t], a0, a1);
+          b0 = a0; b1 = a1;
+          for (;;) {
+            const bool la = (int)a1.w < 0, lb = (int)b1.w < 0;
+            if (la && lb) break;
+            const int ca = win_step(slots, col, rowA, a0, a1, la ? 0u : 1u), cb = win_step(slots, col, rowB, b0, b1, lb ? 0u : 1u);
+            if (COUNT) tests += (vA && !la ? 1 : 0) + (vB && !lb ? 1 : 0);
+            if (!la) ldg_slotw(slots + ca, a0, a1);
+            if (!lb) ldg_slotw(slots + cb, b0, b1);
+          }
+          int va = (int)a1.y, vb = (int)b1.y;
+          if (a.leaf_value) { va = __float_as_int(__ldg(a.leaf_value + va)); vb = __float_as_int(__ldg(a.leaf_value + vb)); }
+          if (vA) out[((size_t)(x0 + lx) * ny + (y0 + ly)) * nt + t] = va;
+          if (vB) out[((size_t)(x0 + lx) * ny + (y0 + ly + 4)) * nt + t] = vb;
+        }
+      } else {
+        // one walk per lane: a task is (tree, upper / lower half of the tile), so twice as many independent warps
+        for (int k = warp; k < 2 * nt; k += NW) {
+          const int t = k >> 1, py = ly + 4 * (k & 1);
+          int ra = r0 + py;
+          ra -= ra >= kWinRows ? kWinRows : 0;
+          const uint32_t rowA = ra * kWinRowBytes;
+          const bool vA = vx && y0 + py < ny;
+          uint4 a0, a1;
+          ldg_slotw(slots + roots[t], a0, a1);
+          while ((int)a1.w >= 0) {
+            const int ca = win_step(slots, col, rowA, a0, a1, 1u);
+            if (COUNT) tests += vA ? 1 : 0;
+            ldg_slotw(slots + ca, a0, a1);
+          }
+          int va = (int)a1.y;
+          if (a.leaf_value) va = __float_as_int(__ldg(a.leaf_value + va));
+          if (vA) out[((size_t)(x0 + lx) * ny + (y0 + py)) * nt + t] = va;
+        }
+      }
+      if (COUNT && threadIdx.x == 0) trav += (unsigned long long)min(kWinTile, nx - x0) * min(kWinTile, ny - y0) * nt;
+    }
+  }
+  if (COUNT) {
+    tests = __reduce_add_sync(0xffffffffu, tests);
+    if (lane == 0 && tests) atomicAdd(&a.counters[a.cnt_tests], (unsigned long long)tests);
+    if (threadIdx.x == 0 && trav) atomicAdd(&a.counters[a.cnt_trav], trav);
   }
 }
 

@@ -119,6 +119,23 @@ int pack_forests(const std::vector<const FlatForest*>& forests, ForestKind kind,
         }
         if (out.slots16.size() < out.slots.size()) out.slots16.resize(out.slots.size());
         out.slots16[slot_of[ni]] = c;
+        DevSlotW w{};
+        if (n.leaf >= 0) {
+          w.m2 = (uint32_t)s.child;
+          w.child = slot_of[ni];
+          w.tw = 0x7fffu | 1u << 31;
+        } else {
+          w.px1 = (uint32_t)n.channel * kWinPlaneBytes + n.r1[0] * 4u;
+          w.px2 = (uint32_t)n.channel * kWinPlaneBytes + n.r2[0] * 4u;
+          w.yh1 = (uint32_t)n.r1[1] * kWinRowBytes | ((uint32_t)n.r1[3] * kWinRowBytes) << 16;
+          w.yh2 = (uint32_t)n.r2[1] * kWinRowBytes | ((uint32_t)n.r2[3] * kWinRowBytes) << 16;
+          w.m1 = s.m1; w.m2 = s.m2;
+          w.child = s.child;
+          w.tw = (uint32_t)(uint16_t)n.threshold | (n.r1[2] * 4u) << 16 | (n.r2[2] * 4u) << 24;
+          for (const uint8_t* r : {n.r1, n.r2}) out.max_extent = std::max(out.max_extent, std::max(r[0] + r[2], r[1] + r[3]));
+        }
+        if (out.slotsw.size() < out.slots.size()) out.slotsw.resize(out.slots.size());
+        out.slotsw[slot_of[ni]] = w;
       }
     }
   }

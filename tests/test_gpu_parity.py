@@ -118,6 +118,43 @@ def test_forest_leaf_ids_synthetic_model(O, sctx, synth_models, stride, H, W):
     s.close()
 
 
+@pytest.mark.parametrize("H,W,nt", [(125, 125, 20), (148, 124, 20), (33, 125, 7), (40, 125, 23), (200, 125, 20), (32, 125, 20), (70, 124, 41)])
+def test_window_traversal_forced(O, crf, gpu, synth_models, monkeypatch, H, W, nt):
+    """k_traverse_win (shared-memory window, ring rows, two walks per lane) on one ragged face: partial tiles right and
+    below, heights that need 1..22 tile steps, tree lists shorter / longer than the warps of a CTA, and the counters."""
+    gm, om = synth_models
+    monkeypatch.setenv("CRF_TRAVERSE_VARIANT", "0x100001")
+    ctx = crf.Context(gm, 0)
+    ctx.set_profiling(False, True)
+    rng = np.random.default_rng(H * 7 + nt)
+    for smooth in (True, False):
+        planes = _planes(rng, 38, H, W, smooth=smooth)
+        s = O.Sample(planes=planes)
+        ctx.reset_counters()
+        ids_o, _, _, vis_hp = om.eval_hp(s, 1)
+        assert np.array_equal(ctx.stage_eval_forest(planes, 1), ids_o)
+        fi = rng.integers(0, 5, nt); ti = rng.integers(0, 20, nt)
+        e = om.eval_ffd(s, fi, ti, 1)
+        assert np.array_equal(ctx.stage_eval_forest(planes, 1, fi, ti), e["leaf_ids"])
+        c = ctx.counters()
+        assert c["hp_traversals"] == ids_o.size and c["ffd_traversals"] == e["leaf_ids"].size
+        assert c["hp_node_tests"] == vis_hp - ids_o.size and c["ffd_node_tests"] == e["visits"] - e["leaf_ids"].size
+        s.close()
+    ctx.close()
+
+
+def test_window_and_gather_traversals_agree_in_batches(crf, gpu, synth_models, monkeypatch):
+    """Whole pipeline at stride 1 on 80 crops: the default (window kernel, persistent CTAs over (face, column) items) against
+    the global-gather kernels forced through CRF_TRAVERSE_VARIANT; records must be byte-identical."""
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, _ = synth_models
+    crops, _ = wl.make_crops(80, seed=77)
+    got = crf.Context(gm, 0, crf._options(None, hp_stride=1, ffd_stride=1)).analyze_crops(crops)
+    monkeypatch.setenv("CRF_TRAVERSE_VARIANT", hex(32 | (4 << 8) | (10 << 16)))
+    ref = crf.Context(gm, 0, crf._options(None, hp_stride=1, ffd_stride=1)).analyze_crops(crops)
+    assert got.tobytes() == ref.tobytes()
+
+
 def test_forest_large_rectangles(crf, O, gpu, tmp_path):
     """Rectangles up to 30x30 (area 900): the modulo-2^16 integral layout needs up to 4 strips per rectangle."""
     from face_alignment_cvpr_2012_b200 import synthetic_model as sm
@@ -389,7 +426,8 @@ def test_full_size_properties(crf, staged_models, gpu):
     crops = base[perm]
     ctx = crf.Context(gm, 0, crf._options(None, hp_stride=1, ffd_stride=1, max_chunk=256))
     got = ctx.analyze_crops(crops)
-    ref = crf.Context(gm, 0, crf._options(None, hp_stride=1, ffd_stride=1, max_chunk=37)).analyze_crops(base)
+    # chunks of 16 faces stay below the window kernel's batch threshold: the reference records come from the global-gather traversal
+    ref = crf.Context(gm, 0, crf._options(None, hp_stride=1, ffd_stride=1, max_chunk=16)).analyze_crops(base)
     assert got.tobytes() == ref[perm].tobytes()
     d_crops = torch.from_numpy(crops).cuda()
     d_out = torch.empty(4096 * crf.FACE_DTYPE.itemsize, dtype=torch.uint8, device="cuda")

@@ -1,0 +1,18 @@
+#!/usr/bin/env python
+"""Sweep of the k_traverse_win launch shapes (warps per CTA | walks per lane << 8) through CRF_WIN_HP / CRF_WIN_FFD.
+usage: win_variants.py [faces=2048]   (development aid; prints the traversal stage times of each variant)"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+n = sys.argv[1] if len(sys.argv) > 1 else "2048"
+for hp, ffd in [("30|1", "20|2")]:
+    env = dict(os.environ)
+    f = lambda s: str(int(s.split("|")[0]) | int(s.split("|")[1]) << 8)
+    env["CRF_WIN_HP"], env["CRF_WIN_FFD"] = f(hp), f(ffd)
+    r = subprocess.run([sys.executable, str(ROOT / "tools" / "stage_times.py"), n, "1", "1"], env=env, capture_output=True, text=True)
+    line = (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1]
+    i = line.find("'hp_traverse'")
+    print(f"hp {hp:5s} ffd {ffd:5s}:", line[i:i + 80] if i >= 0 else line[-200:], flush=True)
