@@ -12,7 +12,7 @@ reduction are the only torch.distributed calls.
            the library's stream, max over ranks.
 `e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers (crf_analyze_crops):
            pinned host crops -> H2D -> path -> D2H of the crf_face_t results, every step.
-`roofline`: the dominant gather kernel (FFD forest traversal): algorithmic bytes (48 B per node
+`roofline`: the dominant gather kernel (FFD forest traversal, k_traverse_win): algorithmic bytes (48 B per node
            test + 4 B per leaf written) / its CUDA-event duration inside the timed region, against the measured
            HBM copy peak.
 `cpu_baseline` / `--impl reference`: the reference's ThreadPool CPU path (oracle/crf_oracle.cc restatement — the
@@ -287,14 +287,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_traverse (FFD forest, stride 1)", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "roofline": {"kernel": "k_traverse_win<20,2> (FFD forest, stride 1, shared-memory window)", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
                          "alg_bytes_per_launch": alg_bytes / launches_ffd, "launches_per_step": launches_ffd, "ms_per_step": ffd_ms,
-                         "note": "gather working set (integral stacks of the faces in flight + 55 MB of node records) is L2-resident, so the HBM-equivalent "
-                                 "fraction can exceed 1; see profiles/ for dram bytes and L2 throughput"},
+                         "note": "the gathers are served from a shared-memory window of the integral stack (node records from L1/L2), so the HBM-equivalent "
+                                 "fraction exceeds 1; the limiter is the L1/shared data pipe (LSU wavefronts 76 % of peak, profiles/r1g_*.csv)"},
             "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "kernels": [
-                {"kernel": "k_traverse (head-pose forest)", "bound": "hbm", "ms_per_step": hp_ms,
+                {"kernel": "k_traverse_win<30,1> (head-pose forest)", "bound": "hbm", "ms_per_step": hp_ms,
                  "achieved": (48 * work["hp_node_tests"] + 4 * work["hp_traversals"]) / (hp_ms * 1e-3) / 1e9 if hp_ms > 0 else 0.0, "unit": "GB/s"},
                 {"kernel": "k_gabor_sep<9..25> + k_gabor_mag<7> + quantise/integral", "bound": "fp32 issue (non-tensor FFMA)", "ms_per_step": gabor_ms,
                  "achieved": gabor_flops / (gabor_ms * 1e-3) / 1e12 if gabor_ms > 0 else 0.0, "peak": fp32_peak, "unit": "TFLOP/s",
