@@ -62,7 +62,7 @@ EXPORTS = [
     "crf_model_info", "crf_model_tree_dump", "crf_model_free", "crf_device_count", "crf_ctx_create", "crf_ctx_destroy",
     "crf_ctx_set_profiling", "crf_ctx_stage_ms", "crf_ctx_counters", "crf_ctx_reset_counters", "crf_ctx_stream", "crf_host_alloc",
     "crf_host_free", "crf_analyze_faces", "crf_analyze_batch", "crf_analyze_crops", "crf_headpose_crops", "crf_analyze_crops_device",
-    "crf_stage_gray_resize", "crf_stage_channels", "crf_stage_minmax", "crf_stage_norm", "crf_stage_eval_forest", "crf_stage_headpose",
+    "crf_stage_gray_resize", "crf_stage_channels", "crf_stage_minmax", "crf_stage_norm", "crf_stage_canny", "crf_stage_eval_forest", "crf_stage_headpose",
     "crf_stage_compose", "crf_stage_votes_meanshift", "crf_stage_meanshift",
 ]
 
@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.crf_stage_channels.argtypes = [vp, u8p, C.c_int, C.c_int, u8p, C.POINTER(C.c_uint32)]
     L.crf_stage_minmax.argtypes = [vp, u8p, C.c_int, C.c_int, u8p, C.POINTER(C.c_uint32)]
     L.crf_stage_norm.argtypes = [vp, u8p, C.c_int, C.c_int, u8p, C.POINTER(C.c_uint32)]
+    L.crf_stage_canny.argtypes = [vp, u8p, C.c_int, C.c_int, u8p, C.POINTER(C.c_uint32)]
     L.crf_stage_eval_forest.argtypes = [vp, C.c_int, i32p, i32p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.crf_stage_headpose.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, i32p, i32p, i32p, i32p, i32p, i32p]
     L.crf_stage_compose.argtypes = [vp, C.c_float, C.c_float, i32p, i32p, i32p, i32p, i32p, i32p]

@@ -275,7 +275,7 @@ static int launch_resize(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, const 
   return CRF_OK;
 }
 
-static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, int extra /* 0: features {0,1,2}; 1: FC_MIN_MAX; 2: FC_NORM */, bool want_u8) {
+static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, int extra /* 0: features {0,1,2}; 1: FC_MIN_MAX; 2: FC_NORM; 3: FC_CANNY */, bool want_u8) {
   const bool minmax_planes = extra != 0;
   uint8_t* u8 = want_u8 ? c->w->d_u8planes.as<uint8_t>() : nullptr;
   uint32_t* dbg32 = want_u8 ? c->w->d_int32.as<uint32_t>() : nullptr;   // full 32-bit integrals, stage API only
@@ -285,8 +285,10 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, int 
     int nw;
     if (!minmax_planes) { nw = 3; pp.which[0] = 0; pp.plane[0] = 0; pp.which[1] = 1; pp.plane[1] = 36; pp.which[2] = 2; pp.plane[2] = 37; }
     else if (extra == 1) { nw = 2; pp.which[0] = 3; pp.plane[0] = 0; pp.which[1] = 4; pp.plane[1] = 1; }
-    else { nw = 1; pp.which[0] = 5; pp.plane[0] = 0; }
-    k_plain_channels<<<dim3(nw, n), 128, 0, c->w->stream>>>(fd, c->w->d_scaled.as<uint8_t>(), c->w->scaled_fs, c->w->d_stacks.as<stack_t>(), c->w->stack_fs,
+    else if (extra == 2) { nw = 1; pp.which[0] = 5; pp.plane[0] = 0; }
+    else { nw = 1; pp.which[0] = 6; pp.plane[0] = 0; }
+    const size_t smem = extra == 3 ? (size_t)(Hmax + 2) * 127 * 3 : 0;   // FC_CANNY: u16 magnitudes + u8 map of the padded face
+    k_plain_channels<<<dim3(nw, n), 128, smem, c->w->stream>>>(fd, c->w->d_scaled.as<uint8_t>(), c->w->scaled_fs, c->w->d_stacks.as<stack_t>(), c->w->stack_fs,
                                                          c->w->plane_stride, u8, c->w->u8_fs, dbg32, pp);
     KCHECK(); count_launch(c, CRF_STAGE_PLAIN);
   }
@@ -857,6 +859,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
     CU(cudaFuncSetAttribute(k_traverse16<10, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     CU(cudaFuncSetAttribute(k_traverse16<15, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
   }
+  CU(cudaFuncSetAttribute(k_plain_channels, cudaFuncAttributeMaxDynamicSharedMemorySize, (CRF_MAX_SCALED_H + 2) * 127 * 3));
   CU(cudaFuncSetAttribute(k_hp_reduce_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHpSmem));
   CU(cudaFuncSetAttribute(k_meanshift<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsGeom<false>::smem));
   CU(cudaFuncSetAttribute(k_meanshift<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsGeom<false>::smem));
@@ -1052,6 +1055,16 @@ int crf_stage_norm(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* pla
   int rc = stage_upload_scaled(c, scaled, W, H, 38, false, true, false, false, 1, 4, 3);
   if (rc) return rc;
   if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, 2, true))) return rc;
+  return stage_download_planes(c, 1, W, H, plane_u8, integral);
+}
+
+int crf_stage_canny(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* plane_u8, uint32_t* integral) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!scaled) return fail(CRF_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = stage_upload_scaled(c, scaled, W, H, 38, false, true, false, false, 1, 4, 3);
+  if (rc) return rc;
+  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, 3, true))) return rc;
   return stage_download_planes(c, 1, W, H, plane_u8, integral);
 }
 

@@ -136,6 +136,53 @@ __global__ void __launch_bounds__(128) k_plain_channels(const FaceDesc* __restri
   auto G = [&](int y, int x) -> int { return g[(size_t)y * 128 + x]; };
   __shared__ int s_hist[256];
   __shared__ uint8_t s_lut[256];
+  extern __shared__ __align__(16) uint8_t s_canny[];   // which == 6 only: magnitudes u16 [(H+2)(W+2)] + edge map u8 [(H+2)(W+2)]
+  const int P = W + 2;
+  uint16_t* s_mag = reinterpret_cast<uint16_t*>(s_canny);
+  uint8_t* s_map = s_canny + (size_t)(H + 2) * P * 2;
+  if (which == 6) {
+    // cv::Canny(img, out, -1, 5) (include/FeatureChannelFactory.hpp:166-179), aperture 3, L1 gradient; OpenCV's canny.cpp
+    // restated: 16-bit Sobel with BORDER_REPLICATE, |dx| + |dy|, directional non-maximum suppression, then hysteresis as a
+    // monotone relaxation (candidate next to an edge becomes an edge) iterated to its fixed point, which is the flood fill's.
+    auto GR = [&](int y, int x) -> int { return g[(size_t)min(max(y, 0), H - 1) * 128 + min(max(x, 0), W - 1)]; };
+    auto grad = [&](int y, int x, int& gx, int& gy) {
+      const int a = GR(y - 1, x - 1), b = GR(y - 1, x), c2 = GR(y - 1, x + 1), d2 = GR(y, x - 1), f = GR(y, x + 1), g2 = GR(y + 1, x - 1), h = GR(y + 1, x), i2 = GR(y + 1, x + 1);
+      gx = (c2 + 2 * f + i2) - (a + 2 * d2 + g2);
+      gy = (g2 + 2 * h + i2) - (a + 2 * b + c2);
+    };
+    for (int i = threadIdx.x; i < (H + 2) * P; i += 128) { s_mag[i] = 0; s_map[i] = 1; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < W * H; i += 128) {
+      const int y = i / W, x = i - y * W;
+      int gx, gy; grad(y, x, gx, gy);
+      s_mag[(y + 1) * P + x + 1] = (uint16_t)(abs(gx) + abs(gy));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < W * H; i += 128) {
+      const int y = i / W, x = i - y * W, c = (y + 1) * P + x + 1;
+      int xs, ys; grad(y, x, xs, ys);
+      const int m = s_mag[c];
+      const int ax = abs(xs), ay = abs(ys) << 15, tg22x = ax * 13573;   // TG22 = (int)(tan(22.5 deg) * 2^15 + 0.5)
+      bool ok;
+      if (ay < tg22x) ok = m > s_mag[c - 1] && m >= s_mag[c + 1];
+      else if (ay > tg22x + (ax << 16)) ok = m > s_mag[c - P] && m >= s_mag[c + P];
+      else { const int sg = (xs ^ ys) < 0 ? -1 : 1; ok = m > s_mag[c - P - sg] && m > s_mag[c + P + sg]; }
+      // low threshold -1: every magnitude (>= 0) passes `m > low`
+      if (ok) s_map[c] = m > 5 ? 2 : 0;
+    }
+    __syncthreads();
+    for (;;) {
+      int changed = 0;
+      for (int i = threadIdx.x; i < W * H; i += 128) {
+        const int y = i / W, x = i - y * W, c = (y + 1) * P + x + 1;
+        if (s_map[c] != 0) continue;
+        const bool near = s_map[c - P - 1] == 2 || s_map[c - P] == 2 || s_map[c - P + 1] == 2 || s_map[c - 1] == 2 || s_map[c + 1] == 2 ||
+                          s_map[c + P - 1] == 2 || s_map[c + P] == 2 || s_map[c + P + 1] == 2;
+        if (near) { s_map[c] = 2; changed = 1; }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+  }
   if (which == 5) {
     // cv::equalizeHist: histogram in shared memory, the 256-entry LUT by one thread (sequential cumulative sum, f32 scale)
     for (int i = threadIdx.x; i < 256; i += 128) s_hist[i] = 0;
@@ -172,6 +219,7 @@ __global__ void __launch_bounds__(128) k_plain_channels(const FaceDesc* __restri
         return (uint32_t)min(max(v, 0), 255);
       }
       case 5: return s_lut[G(r, c)];
+      case 6: return s_map[(r + 1) * P + c + 1] == 2 ? 255u : 0u;
       default: {
         int lo = 255, hi = 0;
         for (int j = -1; j <= 1; j++)

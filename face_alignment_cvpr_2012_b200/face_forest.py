@@ -273,13 +273,14 @@ class Context:
                                                     capi.ptr(buf, C.c_uint8), C.byref(W), C.byref(H)))
         return buf[: W.value * H.value].reshape(H.value, W.value).copy()
 
-    def stage_channels(self, scaled: np.ndarray, minmax: bool = False, norm: bool = False):
-        """features {0,1,2} (38 planes), or FC_MIN_MAX (2 planes), or FC_NORM (1 plane)."""
+    def stage_channels(self, scaled: np.ndarray, minmax: bool = False, norm: bool = False, canny: bool = False):
+        """features {0,1,2} (38 planes), or FC_MIN_MAX (2 planes), or FC_NORM (1 plane), or FC_CANNY (1 plane)."""
         scaled = np.ascontiguousarray(scaled, np.uint8)
         H, W = scaled.shape
-        n = 1 if norm else 2 if minmax else 38
+        n = 1 if (norm or canny) else 2 if minmax else 38
         planes = np.zeros((n, H, W), np.uint8); integ = np.zeros((n, H + 1, W + 1), np.uint32)
-        fn = capi.lib().crf_stage_norm if norm else capi.lib().crf_stage_minmax if minmax else capi.lib().crf_stage_channels
+        L = capi.lib()
+        fn = L.crf_stage_canny if canny else L.crf_stage_norm if norm else L.crf_stage_minmax if minmax else L.crf_stage_channels
         capi.check(fn(self.h, capi.ptr(scaled, C.c_uint8), W, H, capi.ptr(planes, C.c_uint8), capi.ptr(integ, C.c_uint32)))
         return planes, integ
 

@@ -156,6 +156,8 @@ int crf_stage_channels(crf_ctx* ctx, const uint8_t* scaled, int W, int H, uint8_
 int crf_stage_minmax(crf_ctx* ctx, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals);
 /* FC_NORM (include/FeatureChannelFactory.hpp:58-70): cv::equalizeHist; plane [H][W], integral [H+1][W+1]. */
 int crf_stage_norm(crf_ctx* ctx, const uint8_t* scaled, int W, int H, uint8_t* plane_u8, uint32_t* integral);
+/* FC_CANNY (include/FeatureChannelFactory.hpp:166-179): cv::Canny(img, out, -1, 5); plane [H][W] (0 / 255), integral [H+1][W+1]. */
+int crf_stage_canny(crf_ctx* ctx, const uint8_t* scaled, int W, int H, uint8_t* plane_u8, uint32_t* integral);
 /* Forest<S>::evaluateMT over the dense grid of getHeadPoseVotesMT / getFacialFeaturesVotesMT.
  * Channel data comes from caller-supplied u8 planes [C][H][W] (C <= 64) so that synthetic
  * channels can be used.  which = -1: head-pose forest (tree_forest/tree_index ignored);

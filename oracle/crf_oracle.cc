@@ -437,6 +437,57 @@ static void equalize_hist_u8(const Plane8& src, Plane8& dst) {
   for (size_t p = 0; p < src.d.size(); p++) dst.d[p] = lut[src.d[p]];
 }
 
+// FeatureChannelFactory.hpp:166-179  cv::Canny(img, canny_img, -1, 5) (FC_CANNY): aperture 3, L1 gradient magnitude,
+// thresholds low = -1 / high = 5 (every local maximum of the gradient is a candidate; those above 5 seed the hysteresis).
+// Restates OpenCV's canny.cpp: 16-bit Sobel with BORDER_REPLICATE, magnitude |dx| + |dy| with a zero border, non-maximum
+// suppression in the three direction classes (TG22 = tan(22.5 deg) in 15-bit fixed point) with its asymmetric > / >=
+// comparisons, then 8-connected hysteresis from the strong pixels.  Pinned bit-exactly against cv2 4.13
+// (tests/test_oracle_golden.py::test_canny_matches_cv2).
+static void canny_u8(const Plane8& src, Plane8& dst, int low = -1, int high = 5) {
+  const int H = src.rows, W = src.cols, P = W + 2;
+  dst.rows = H; dst.cols = W; dst.d.assign(src.d.size(), 0);
+  auto px = [&](int y, int x) { return (int)src.at(std::min(std::max(y, 0), H - 1), std::min(std::max(x, 0), W - 1)); };
+  std::vector<int> dx((size_t)H * W), dy((size_t)H * W), mag((size_t)(H + 2) * P, 0);
+  std::vector<uint8_t> mp((size_t)(H + 2) * P, 1);   // 1 = not an edge, 0 = candidate, 2 = edge
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const int gx = (px(y - 1, x + 1) + 2 * px(y, x + 1) + px(y + 1, x + 1)) - (px(y - 1, x - 1) + 2 * px(y, x - 1) + px(y + 1, x - 1));
+      const int gy = (px(y + 1, x - 1) + 2 * px(y + 1, x) + px(y + 1, x + 1)) - (px(y - 1, x - 1) + 2 * px(y - 1, x) + px(y - 1, x + 1));
+      dx[(size_t)y * W + x] = gx; dy[(size_t)y * W + x] = gy;
+      mag[(size_t)(y + 1) * P + x + 1] = std::abs(gx) + std::abs(gy);
+    }
+  const int TG22 = (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5);
+  std::vector<int> stack;
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const size_t c = (size_t)(y + 1) * P + x + 1;
+      const int m = mag[c];
+      bool ok = false;
+      if (m > low) {
+        const int xs = dx[(size_t)y * W + x], ys = dy[(size_t)y * W + x];
+        const int ax = std::abs(xs), ay = std::abs(ys) << 15;
+        const int tg22x = ax * TG22;
+        if (ay < tg22x) ok = m > mag[c - 1] && m >= mag[c + 1];
+        else {
+          const int tg67x = tg22x + (ax << 16);
+          if (ay > tg67x) ok = m > mag[c - P] && m >= mag[c + P];
+          else { const int sg = (xs ^ ys) < 0 ? -1 : 1; ok = m > mag[c - P - sg] && m > mag[c + P + sg]; }
+        }
+      }
+      if (ok) { mp[c] = m > high ? 2 : 0; if (m > high) stack.push_back((int)c); }
+    }
+  while (!stack.empty()) {
+    const int c = stack.back(); stack.pop_back();
+    for (int j = -1; j <= 1; j++)
+      for (int i = -1; i <= 1; i++) {
+        const int q = c + j * P + i;
+        if (mp[q] == 0) { mp[q] = 2; stack.push_back(q); }
+      }
+  }
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) dst.at(y, x) = mp[(size_t)(y + 1) * P + x + 1] == 2 ? 255 : 0;
+}
+
 // FeatureChannelFactory.hpp:186-251  createKernel / initGaborKernels (A.4)
 struct GaborKernel {
   int width = 0;
@@ -705,7 +756,13 @@ struct ImageSample {
         planes8.push_back(a);
         break;
       }
-      default: break;  // FC_CANNY: out of scope
+      case 4: {                                                                // FC_CANNY
+        Plane8 a;
+        canny_u8(img, a);
+        planes8.push_back(a);
+        break;
+      }
+      default: break;
     }
   }
   // src/ImageSample.cpp:30-64, integral branch (A.6)
@@ -1201,6 +1258,7 @@ int orc_num_planes(int features_mask) {
   if (features_mask & 2) n += 35;
   if (features_mask & 4) n += 2;
   if (features_mask & 8) n += 2;
+  if (features_mask & 16) n += 1;
   if (features_mask & 32) n += 1;
   return n;
 }

@@ -2,7 +2,7 @@
 """Generates the committed golden fixtures (run in the build container, where cv2 4.13 and /root/reference exist).
 
   cv2_stages.npz   inputs + cv2 4.13 outputs of the OpenCV-defined stages of the path:
-                   cvtColor(BGR2GRAY), resize(INTER_LINEAR), integral, Sobel(8U), erode/dilate 3x3,
+                   cvtColor(BGR2GRAY), resize(INTER_LINEAR), integral, Sobel(8U), erode/dilate 3x3, equalizeHist, Canny(-1, 5),
                    filter2D with the 7x7 Gabor kernels (bit-exact by construction of the canonical arithmetic),
                    and the whole Gabor plane (magnitude -> normalize -> x255 -> u8) of cv2 for all 35 kernels
                    (+-1 LSB statistical pin for kernels >= 9x9, where cv2 takes its DFT path).
@@ -57,6 +57,10 @@ def main():
     d["equalize"] = cv2.equalizeHist(img)
     lowc = (img // 4 + 90).astype(np.uint8)
     d["equalize_src2"] = lowc; d["equalize2"] = cv2.equalizeHist(lowc)
+    # FC_CANNY (include/FeatureChannelFactory.hpp:169): cv::Canny(img, out, -1, 5) on a blurred and on a raw noise plane
+    d["canny"] = cv2.Canny(img, -1, 5)
+    raw = np.random.default_rng(4).integers(0, 256, (64, 124), dtype=np.uint8)
+    d["canny_src2"] = raw; d["canny2"] = cv2.Canny(raw, -1, 5)
     bank = O.gabor_bank()
     for idx in range(7):
         d[f"f2d_re_{idx}"] = cv2.filter2D(img, cv2.CV_32F, bank[idx][0]); d[f"f2d_im_{idx}"] = cv2.filter2D(img, cv2.CV_32F, bank[idx][1])

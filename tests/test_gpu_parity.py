@@ -97,6 +97,20 @@ def test_norm_channel(O, sctx, cv2_golden):
     assert (p[0] == 200).all()
 
 
+@pytest.mark.parametrize("H,W", [(125, 125), (148, 124), (40, 125), (521, 125)])
+def test_canny_channel(O, sctx, cv2_golden, H, W):
+    """FC_CANNY as a stage (crf_stage_canny): bit-exact vs the oracle, and vs cv2 on the golden plane."""
+    import cv2
+    rng = np.random.default_rng(H + W)
+    for img in (cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), 2.0), rng.integers(0, 256, (H, W), dtype=np.uint8),
+                np.zeros((H, W), np.uint8), np.tile(np.arange(W, dtype=np.uint8), (H, 1))):
+        planes, integ = sctx.stage_channels(img, canny=True)
+        op, oi = O.channels(img, features_mask=16)
+        assert np.array_equal(planes, op) and np.array_equal(integ, oi.astype(np.uint32))
+    planes, _ = sctx.stage_channels(cv2_golden["plane"], canny=True)
+    assert np.array_equal(planes[0], cv2_golden["canny"])
+
+
 def test_channels_degenerate_images(O, sctx):
     for img in (np.zeros((125, 125), np.uint8), np.full((125, 125), 255, np.uint8), np.tile(np.arange(125, dtype=np.uint8), (125, 1))):
         planes, integ = sctx.stage_channels(img)

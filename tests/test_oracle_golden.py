@@ -91,6 +91,17 @@ def test_node_test_integer_division_equivalence():
         assert np.array_equal(q, est), area
 
 
+def test_canny_matches_cv2(O, cv2_golden):
+    """FC_CANNY: the restated cv::Canny(img, out, -1, 5) against cv2 4.13, bit for bit (planes are 0 / 255)."""
+    for src, want in ((cv2_golden["plane"], cv2_golden["canny"]), (cv2_golden["canny_src2"], cv2_golden["canny2"])):
+        planes, integ = O.channels(src, features_mask=16)
+        assert planes.shape[0] == 1 and np.array_equal(planes[0], want)
+        assert np.array_equal(integ[0][1:, 1:], np.cumsum(np.cumsum(want.astype(np.float64), 0), 1).astype(np.float32))
+    # sorted feature order: gray (0), canny (4), norm (5)
+    planes, _ = O.channels(cv2_golden["plane"], features_mask=1 | 16 | 32)
+    assert planes.shape[0] == 3 and np.array_equal(planes[1], cv2_golden["canny"]) and np.array_equal(planes[2], cv2_golden["equalize"])
+
+
 def test_meanshift_empty_and_single(O):
     mean, rnd, it = O.meanshift(np.zeros((0, 3), np.float32))
     assert mean.tolist() == [0, 0] and it == 1
