@@ -41,6 +41,9 @@ CROP = 100
 WORKLOAD = "C2: batch of 4096 synthetic 100x100 face crops per GPU, head-pose forest + FFD forest, dense stride-1 patches"
 
 
+print_line = print   # replaced in main() by a writer on the original stdout
+
+
 def ncu_traffic(faces: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the FFD traversal launch from the committed `ncu --set full`
     capture of this workload (profiles/r1_traffic.json, written by tools/ncu_traffic.py), scaled to the faces per launch."""
@@ -172,7 +175,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference needs OpenCV 2.4 + Boost (absent): oracle/crf_oracle.cc restates its ThreadPool CPU path; ms_per_step extrapolates the sample to 4096 faces",
     }
-    print(json.dumps(line))
+    print_line(json.dumps(line))
     return 0
 
 
@@ -323,7 +326,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             v, cores, n, p50 = cpu_sample(om, crops, args.cpu_seconds, 64)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "p50_ms_per_face": p50,
                                     "sample": f"first {n} crops of the same batch (stride 1), one face at a time, ThreadPool over {cores} host threads per face"}
-        print(json.dumps(line))
+        print_line(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -342,6 +345,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: library banners written to fd 1 meanwhile (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    global print_line
+    print_line = lambda line: (out.write(line + "\n"), out.flush())  # noqa: E731
     if args.impl == "reference":
         return run_reference(args, rank, world)
     return run_b200(args, rank, world, local_rank)
