@@ -149,6 +149,8 @@ struct crf_ctx {
   int traverse_variant = 0;  // 0 = pick by stride (see launch_traverse)
   int sm_count = 148;
   int win_hp = 0, win_ffd = 0;   // k_traverse_win variants (0 = default)
+  int win_tex = 1;               // node records of k_traverse_win through the texture pipe (CRF_WIN_TEX=0: 256-bit global loads)
+  cudaTextureObject_t tex_hp = 0, tex_mp = 0;
   // 1 = consecutive chunks run back to back on one stream (default: measured faster — co-resident Gabor CTAs shrink the L1
   // the gathers live on, and two chunks' stacks thrash L2); 2 = alternate chunks between two streams / work sets
   int nstreams = 1;
@@ -321,12 +323,12 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   a.fd = fd; a.stacks = c->w->d_stacks.as<stack_t>(); a.stack_face_stride = c->w->stack_fs; a.plane_stride = c->w->plane_stride;
   a.stride = stride;
   if (hp) {
-    a.slots = c->d_hp_slots.as<DevSlot>(); a.slots16 = c->d_hp_slots16.as<DevSlot16>(); a.slotsw = c->d_hp_slotsw.as<DevSlotW>(); a.roots = roots; a.ntrees = ntrees;
+    a.slots = c->d_hp_slots.as<DevSlot>(); a.slots16 = c->d_hp_slots16.as<DevSlot16>(); a.slotsw = c->d_hp_slotsw.as<DevSlotW>(); a.slotsw_tex = c->tex_hp; a.roots = roots; a.ntrees = ntrees;
     a.leaf_out = c->w->d_hp_leaf.as<int32_t>(); a.leaf_face_stride = c->w->hp_leaf_fs;
     a.cnt_tests = CNT_HP_TESTS; a.cnt_trav = CNT_HP_TRAV;
     if (hp_values) a.leaf_value = c->d_hp_m.as<float>();
   } else {
-    a.slots = c->d_mp_slots.as<DevSlot>(); a.slots16 = c->d_mp_slots16.as<DevSlot16>(); a.slotsw = c->d_mp_slotsw.as<DevSlotW>();
+    a.slots = c->d_mp_slots.as<DevSlot>(); a.slots16 = c->d_mp_slots16.as<DevSlot16>(); a.slotsw = c->d_mp_slotsw.as<DevSlotW>(); a.slotsw_tex = c->tex_mp;
     a.face_roots = c->w->d_face_roots.as<int32_t>(); a.face_ntrees = c->w->d_face_ntrees.as<int32_t>();
     a.leaf_out = c->w->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->w->ffd_leaf_fs;
     a.cnt_tests = CNT_FFD_TESTS; a.cnt_trav = CNT_FFD_TRAV;
@@ -349,7 +351,7 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
       bool ok = false;
 #define CRF_WIN(NW_, WK_)                                                                                                   \
       if (wv == (NW_ | WK_ << 8)) {                                                                                          \
-        auto kf = c->counting ? k_traverse_win<NW_, WK_, true> : k_traverse_win<NW_, WK_, false>;                            \
+        auto kf = c->counting ? k_traverse_win<NW_, WK_, true> : c->win_tex ? k_traverse_win<NW_, WK_, false, true> : k_traverse_win<NW_, WK_, false>; \
         CU(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmemBytes));                            \
         kf<<<grid, NW_ * 32, kWinSmemBytes, c->w->stream>>>(a, nitems, ncols, c->num_channels);                              \
         ok = true;                                                                                                           \
@@ -745,6 +747,8 @@ void crf_ctx_destroy(crf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   for (auto& w : c->ws) if (w.stream) cudaStreamSynchronize(w.stream);
+  if (c->tex_hp) cudaDestroyTextureObject(c->tex_hp);
+  if (c->tex_mp) cudaDestroyTextureObject(c->tex_mp);
   Buf* all[] = {&c->d_hp_slotsw, &c->d_mp_slotsw, &c->d_hp_slots16, &c->d_mp_slots16, &c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
                 &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_coef_sep[1], &c->d_coef_sep[2], &c->d_coef_sep[3], &c->d_coef_sep[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc};
   for (Buf* b : all) b->release();
@@ -773,6 +777,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if (opt) c->opt = *opt; else crf_options_default(&c->opt);
   if (c->opt.hp_stride < 1 || c->opt.ffd_stride < 1) return fail(CRF_ERR_ARG, "strides must be >= 1");
   if (const char* v = std::getenv("CRF_TRAVERSE_VARIANT")) c->traverse_variant = (int)std::strtol(v, nullptr, 0);
+  if (const char* v = std::getenv("CRF_WIN_TEX")) c->win_tex = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_WIN_HP")) c->win_hp = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_WIN_FFD")) c->win_ffd = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_MS_VARIANT")) c->ms_variant = (int)std::strtol(v, nullptr, 0);
@@ -800,6 +805,14 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if ((rc = upload(c->d_hp_slots16, c->hp.slots16, c->w->stream)) || (rc = upload(c->d_mp_slots16, c->mp.slots16, c->w->stream))) return rc;
   if ((rc = upload(c->d_hp_slotsw, c->hp.slotsw, c->w->stream)) || (rc = upload(c->d_mp_slotsw, c->mp.slotsw, c->w->stream))) return rc;
   CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  for (int k = 0; k < 2; k++) {
+    cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = k ? c->d_mp_slotsw.p : c->d_hp_slotsw.p;
+    rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+    rd.res.linear.sizeInBytes = (k ? c->mp.slotsw.size() : c->hp.slotsw.size()) * sizeof(DevSlotW);
+    cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+    CU(cudaCreateTextureObject(k ? &c->tex_mp : &c->tex_hp, &rd, &td, nullptr));
+  }
   if ((rc = upload(c->d_hp_slots, c->hp.slots, c->w->stream)) || (rc = upload(c->d_hp_roots, c->hp.roots, c->w->stream)) || (rc = upload(c->d_hp_m, c->hp.hp_m, c->w->stream)) ||
       (rc = upload(c->d_mp_slots, c->mp.slots, c->w->stream)) || (rc = upload(c->d_mp_roots, c->mp.roots, c->w->stream)) ||
       (rc = upload(c->d_mp_mask, c->mp.mp_mask, c->w->stream)) || (rc = upload(c->d_mp_leaf, c->mp.mp_leaf, c->w->stream)))

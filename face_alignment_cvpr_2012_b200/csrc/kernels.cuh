@@ -578,6 +578,7 @@ struct TraverseArgs {
   const DevSlot* slots;
   const DevSlot16* slots16;      // compact form of the same slots (k_traverse16)
   const DevSlotW* slotsw;        // window form of the same slots (k_traverse_win)
+  cudaTextureObject_t slotsw_tex;  // the same array as a linear uint4 texture (two texels per record)
   const int32_t* roots;        // shared tree list (head pose) or nullptr
   const int32_t* face_roots;   // [face][kMaxList] composed lists (FFD) or nullptr
   const int32_t* face_ntrees;  // [face] or nullptr
@@ -804,9 +805,15 @@ __device__ __forceinline__ int win_step(const DevSlotW* __restrict__ slots, uint
   return (int)q1.z + ((m1 - m2) > thr ? 1 : 0);   // go left iff mean1 - mean2 <= threshold
 }
 
-template <int NW, int WALKS, bool COUNT>
+template <int NW, int WALKS, bool COUNT, bool TEX = false>
 __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int nitems, int ncols, int nplanes) {
   static_assert(WALKS == 1 || WALKS == 2, "one or two walks per lane");
+  // record fetch: 256-bit global load, or (TEX, the default) two 128-bit texel fetches that return through the texture pipe and
+  // leave the LSU data pipe, the kernel's limiter, to the shared-memory gathers (-5 % time; CRF_WIN_TEX=0 switches it off)
+  auto fetch = [&](int slot, uint4& q0, uint4& q1) {
+    if (TEX) { q0 = tex1Dfetch<uint4>(a.slotsw_tex, 2 * slot); q1 = tex1Dfetch<uint4>(a.slotsw_tex, 2 * slot + 1); }
+    else ldg_slotw(a.slotsw + slot, q0, q1);
+  };
   extern __shared__ __align__(16) uint8_t s_win[];
   const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_win);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -873,15 +880,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int
         const bool vA = vx && y0 + ly < ny, vB = vx && y0 + ly + 4 < ny;
         for (int t = warp; t < nt; t += NW) {
           uint4 a0, a1, b0, b1;
-          ldg_slotw(slots + roots[t], a0, a1);
+          fetch(roots[t], a0, a1);
           b0 = a0; b1 = a1;
           for (;;) {
             const bool la = (int)a1.w < 0, lb = (int)b1.w < 0;
             if (la && lb) break;
             const int ca = win_step(slots, col, rowA, a0, a1, la ? 0u : 1u), cb = win_step(slots, col, rowB, b0, b1, lb ? 0u : 1u);
             if (COUNT) tests += (vA && !la ? 1 : 0) + (vB && !lb ? 1 : 0);
-            if (!la) ldg_slotw(slots + ca, a0, a1);
-            if (!lb) ldg_slotw(slots + cb, b0, b1);
+            if (!la) fetch(ca, a0, a1);
+            if (!lb) fetch(cb, b0, b1);
           }
           int va = (int)a1.y, vb = (int)b1.y;
           if (a.leaf_value) { va = __float_as_int(__ldg(a.leaf_value + va)); vb = __float_as_int(__ldg(a.leaf_value + vb)); }
@@ -897,11 +904,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int
           const uint32_t rowA = ra * kWinRowBytes;
           const bool vA = vx && y0 + py < ny;
           uint4 a0, a1;
-          ldg_slotw(slots + roots[t], a0, a1);
+          fetch(roots[t], a0, a1);
           while ((int)a1.w >= 0) {
             const int ca = win_step(slots, col, rowA, a0, a1, 1u);
             if (COUNT) tests += vA ? 1 : 0;
-            ldg_slotw(slots + ca, a0, a1);
+            fetch(ca, a0, a1);
           }
           int va = (int)a1.y;
           if (a.leaf_value) va = __float_as_int(__ldg(a.leaf_value + va));
