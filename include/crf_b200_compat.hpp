@@ -76,8 +76,12 @@ class FaceForest {
   // src/FaceForest.cpp:15-58: on failure prints the error and leaves the object un-initialised.
   bool load(const FaceForestOptions& o) {
     option_ = o;
-    int rc = crf_model_load(o.head_pose_forest_param.tree_path.c_str(), o.head_pose_forest_param.ntrees, o.mp_forest_param.tree_path.c_str(),
-                            o.mp_forest_param.ntrees, &model_);
+    // a tree path that names a pre-packed image (*.crfb200, written by crf_model_save_packed) holds both forests
+    const std::string& tp = o.mp_forest_param.tree_path;
+    const bool packed = tp.size() > 8 && tp.compare(tp.size() - 8, 8, ".crfb200") == 0;
+    int rc = packed ? crf_model_load_packed(tp.c_str(), &model_)
+                    : crf_model_load(o.head_pose_forest_param.tree_path.c_str(), o.head_pose_forest_param.ntrees, o.mp_forest_param.tree_path.c_str(),
+                                     o.mp_forest_param.ntrees, &model_);
     if (rc != CRF_OK) { std::fprintf(stderr, "(!) Error loading forest: %s\n", crf_last_error()); return false; }
     crf_options_t co;
     crf_options_default(&co);

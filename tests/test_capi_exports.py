@@ -72,3 +72,15 @@ def test_detectface_box_postprocessing(crf):
     assert crf.enlarge_detections([(2, 400, 101, 101)], 480, 640) == [(0, 400, 108, 80)]       # clipped left and bottom
     assert crf.enlarge_detections([(600, 10, 60, 60)], 480, 640) == [(597, 10, 43, 78)]       # clipped right
     assert crf.intersect((700, 0, 10, 10), (0, 0, 640, 480)) == (0, 0, 0, 0)
+
+
+def test_cpp_eval_ffd_driver_builds_and_fails_like_the_reference(crf, tmp_path):
+    """examples/eval_ffd.cpp compiles against the compat header; without its config files it exits with EXIT_FAILURE after the
+    reference's "Default ForestParam initialization" message (src/face_utils.cpp:128-139, src/eval_ffd.cpp:139-143)."""
+    import subprocess
+    from face_alignment_cvpr_2012_b200 import capi
+    exe = tmp_path / "eval_ffd"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "examples" / "eval_ffd.cpp"), "-o", str(exe),
+                    f"-L{capi.LIB_PATH.parent}", "-lcrf_b200", f"-Wl,-rpath,{capi.LIB_PATH.parent}"], check=True)
+    r = subprocess.run([str(exe), str(tmp_path / "missing_ffd.txt"), str(tmp_path / "missing_hp.txt")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "Default ForestParam initialization" in r.stdout

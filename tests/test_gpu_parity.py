@@ -3,6 +3,7 @@ Bit-exact for every integer / byte / index result (scaled pixels, 8-bit planes, 
 head pose and its variance, forest composition); MeanShift means within the 0.5 px of the north star (observed
 <= 1e-4: the only non-identical operation is exp())."""
 import zlib
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -503,6 +504,42 @@ def test_eval_ffd_driver(crf, staged_models, lfw_faces, lfw_golden, gpu, tmp_pat
         iod = np.linalg.norm((gt[0] + gt[1]) / 2 - (gt[6] + gt[7]) / 2)
         want = np.linalg.norm(gt - lfw_golden["recs"][k]["ffd"], axis=1) / iod
         assert np.allclose(e, want, rtol=1e-5, atol=1e-6)
+
+
+def test_cpp_eval_ffd_driver(crf, staged_models, lfw_faces, lfw_golden, gpu, tmp_path):
+    """SURVEY 8 f3 in the reference's language: examples/eval_ffd.cpp (config files -> annotations -> FaceForest::analyzeFace through
+    include/crf_b200_compat.hpp -> errors.txt) on the 20 shipped LFW faces; its errors equal the committed oracle records'."""
+    import subprocess
+    import cv2
+    from face_alignment_cvpr_2012_b200 import capi, workloads as wl
+    root = capi.LIB_PATH.parents[2]
+    exe = tmp_path / "eval_ffd"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(root / "include"), str(root / "examples" / "eval_ffd.cpp"), "-o", str(exe),
+                    f"-L{capi.LIB_PATH.parent}", "-lcrf_b200", f"-Wl,-rpath,{capi.LIB_PATH.parent}"], check=True)
+    data = tmp_path / "data"; data.mkdir()
+    for f in lfw_faces:
+        cv2.imwrite(str(data / (Path(f["name"]).stem + ".ppm")), f["img"])
+    idx = data / "index_random_subset.txt"
+    idx.write_text((wl.STAGED / "imgs" / "index_random_subset.txt").read_text())
+    def cfg(name, ntrees):
+        p = tmp_path / name
+        p.write_text("\n".join(["____Path to images index file", str(idx), "____Path to trees", str(wl.staged_model_path()), "____Number of trees", str(ntrees),
+                                "____Number of tests", "2500", "____Max depth", "20", "____Min patches per node", "20", "____Images per class", "600",
+                                "____Patches per image", "150", "____Face size", "125", "____Patch size ratio", "0.250000", "____Features", "0 1 2"]) + "\n")
+        return str(p)
+    out = tmp_path / "errors.txt"
+    r = subprocess.run([str(exe), "--all", "--out", str(out), cfg("config_ffd.txt", 20), cfg("config_headpose.txt", 15)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "20 faces" in r.stdout, r.stdout + r.stderr
+    err = np.array([[float(v) for v in l.split()] for l in out.read_text().strip().split("\n")])
+    assert err.shape == (20, 10) and abs(float(err.mean()) - 0.0747) < 0.01
+    names = lfw_golden["names"].tolist()
+    order = [f for cls in range(-2, 3) for f in lfw_faces if f["pose"] == cls]
+    for f, e in zip(order, err):
+        k = names.index(f["name"])
+        gt = lfw_golden["gt"][k].astype(np.float64)
+        iod = np.linalg.norm((gt[0] + gt[1]) / 2 - (gt[6] + gt[7]) / 2)
+        want = np.linalg.norm(gt - lfw_golden["recs"][k]["ffd"], axis=1) / iod
+        assert np.allclose(e, want, rtol=1e-4, atol=1e-5)   # errors.txt holds 6 significant digits
 
 
 def test_analyze_image_with_host_haar_detector(crf, staged_models, lfw_faces, gpu):
