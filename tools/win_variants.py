@@ -8,7 +8,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 n = sys.argv[1] if len(sys.argv) > 1 else "2048"
-for hp, ffd in [("30|1", "20|2"), ("15|2", "20|1"), ("32|1", "32|1"), ("24|1", "28|1"), ("20|1", "10|2")]:
+for hp, ffd in [("30|1", "20|2"), ("15|2", "20|2"), ("32|1", "20|1"), ("16|1", "24|1"), ("20|1", "28|1"), ("24|1", "32|1"), ("30|1", "10|2")]:
     env = dict(os.environ)
     f = lambda s: str(int(s.split("|")[0]) | int(s.split("|")[1]) << 8)
     env["CRF_WIN_HP"], env["CRF_WIN_FFD"] = f(hp), f(ffd)
