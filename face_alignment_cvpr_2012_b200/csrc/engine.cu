@@ -150,7 +150,7 @@ struct crf_ctx {
   int sm_count = 148;
   int win_hp = 0, win_ffd = 0;   // k_traverse_win variants (0 = default)
   int win_tex = 1;               // node records of k_traverse_win through the texture pipe (CRF_WIN_TEX=0: 256-bit global loads)
-  cudaTextureObject_t tex_hp = 0, tex_mp = 0;
+  cudaTextureObject_t tex_hp = 0, tex_mp = 0, tex_hp_wide = 0, tex_mp_wide = 0;
   // 1 = consecutive chunks run back to back on one stream (default: measured faster — co-resident Gabor CTAs shrink the L1
   // the gathers live on, and two chunks' stacks thrash L2); 2 = alternate chunks between two streams / work sets
   int nstreams = 1;
@@ -323,12 +323,12 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   a.fd = fd; a.stacks = c->w->d_stacks.as<stack_t>(); a.stack_face_stride = c->w->stack_fs; a.plane_stride = c->w->plane_stride;
   a.stride = stride;
   if (hp) {
-    a.slots = c->d_hp_slots.as<DevSlot>(); a.slots16 = c->d_hp_slots16.as<DevSlot16>(); a.slotsw = c->d_hp_slotsw.as<DevSlotW>(); a.slotsw_tex = c->tex_hp; a.roots = roots; a.ntrees = ntrees;
+    a.slots = c->d_hp_slots.as<DevSlot>(); a.slots16 = c->d_hp_slots16.as<DevSlot16>(); a.slotsw = c->d_hp_slotsw.as<DevSlotW>(); a.slotsw_tex = c->tex_hp; a.slots_tex = c->tex_hp_wide; a.roots = roots; a.ntrees = ntrees;
     a.leaf_out = c->w->d_hp_leaf.as<int32_t>(); a.leaf_face_stride = c->w->hp_leaf_fs;
     a.cnt_tests = CNT_HP_TESTS; a.cnt_trav = CNT_HP_TRAV;
     if (hp_values) a.leaf_value = c->d_hp_m.as<float>();
   } else {
-    a.slots = c->d_mp_slots.as<DevSlot>(); a.slots16 = c->d_mp_slots16.as<DevSlot16>(); a.slotsw = c->d_mp_slotsw.as<DevSlotW>(); a.slotsw_tex = c->tex_mp;
+    a.slots = c->d_mp_slots.as<DevSlot>(); a.slots16 = c->d_mp_slots16.as<DevSlot16>(); a.slotsw = c->d_mp_slotsw.as<DevSlotW>(); a.slotsw_tex = c->tex_mp; a.slots_tex = c->tex_mp_wide;
     a.face_roots = c->w->d_face_roots.as<int32_t>(); a.face_ntrees = c->w->d_face_ntrees.as<int32_t>();
     a.leaf_out = c->w->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->w->ffd_leaf_fs;
     a.cnt_tests = CNT_FFD_TESTS; a.cnt_trav = CNT_FFD_TRAV;
@@ -391,6 +391,7 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   CRF_TRAV(5, 8, 0) CRF_TRAV(5, 8, 1) CRF_TRAV(5, 8, 2) CRF_TRAV(5, 8, 3)
   CRF_TRAV(10, 32, 0) CRF_TRAV(10, 32, 2) CRF_TRAV(10, 8, 2) CRF_TRAV(10, 8, 3)
   CRF_TRAV(15, 32, 2) CRF_TRAV(20, 32, 2) CRF_TRAV(4, 32, 2) CRF_TRAV(8, 32, 2) CRF_TRAV(10, 16, 2) CRF_TRAV(15, 16, 2)
+  CRF_TRAV(15, 16, 10) CRF_TRAV(10, 16, 10) CRF_TRAV(20, 16, 10) CRF_TRAV(15, 32, 10)
 #undef CRF_TRAV
   if (!launched) return fail(CRF_ERR_ARG, "unknown CRF_TRAVERSE_VARIANT");
   KCHECK(); count_launch(c, stage);
@@ -749,6 +750,8 @@ void crf_ctx_destroy(crf_ctx* c) {
   for (auto& w : c->ws) if (w.stream) cudaStreamSynchronize(w.stream);
   if (c->tex_hp) cudaDestroyTextureObject(c->tex_hp);
   if (c->tex_mp) cudaDestroyTextureObject(c->tex_mp);
+  if (c->tex_hp_wide) cudaDestroyTextureObject(c->tex_hp_wide);
+  if (c->tex_mp_wide) cudaDestroyTextureObject(c->tex_mp_wide);
   Buf* all[] = {&c->d_hp_slotsw, &c->d_mp_slotsw, &c->d_hp_slots16, &c->d_mp_slots16, &c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
                 &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_coef_sep[1], &c->d_coef_sep[2], &c->d_coef_sep[3], &c->d_coef_sep[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc};
   for (Buf* b : all) b->release();
@@ -805,18 +808,21 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if ((rc = upload(c->d_hp_slots16, c->hp.slots16, c->w->stream)) || (rc = upload(c->d_mp_slots16, c->mp.slots16, c->w->stream))) return rc;
   if ((rc = upload(c->d_hp_slotsw, c->hp.slotsw, c->w->stream)) || (rc = upload(c->d_mp_slotsw, c->mp.slotsw, c->w->stream))) return rc;
   CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-  for (int k = 0; k < 2; k++) {
-    cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear;
-    rd.res.linear.devPtr = k ? c->d_mp_slotsw.p : c->d_hp_slotsw.p;
-    rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
-    rd.res.linear.sizeInBytes = (k ? c->mp.slotsw.size() : c->hp.slotsw.size()) * sizeof(DevSlotW);
-    cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
-    CU(cudaCreateTextureObject(k ? &c->tex_mp : &c->tex_hp, &rd, &td, nullptr));
-  }
   if ((rc = upload(c->d_hp_slots, c->hp.slots, c->w->stream)) || (rc = upload(c->d_hp_roots, c->hp.roots, c->w->stream)) || (rc = upload(c->d_hp_m, c->hp.hp_m, c->w->stream)) ||
       (rc = upload(c->d_mp_slots, c->mp.slots, c->w->stream)) || (rc = upload(c->d_mp_roots, c->mp.roots, c->w->stream)) ||
       (rc = upload(c->d_mp_mask, c->mp.mp_mask, c->w->stream)) || (rc = upload(c->d_mp_leaf, c->mp.mp_leaf, c->w->stream)))
     return rc;
+  for (int k = 0; k < 4; k++) {   // node records as linear uint4 textures: window form (k < 2) and wide form (k >= 2)
+    cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear;
+    void* ptrs[4] = {c->d_hp_slotsw.p, c->d_mp_slotsw.p, c->d_hp_slots.p, c->d_mp_slots.p};
+    const size_t counts[4] = {c->hp.slotsw.size(), c->mp.slotsw.size(), c->hp.slots.size(), c->mp.slots.size()};
+    cudaTextureObject_t* objs[4] = {&c->tex_hp, &c->tex_mp, &c->tex_hp_wide, &c->tex_mp_wide};
+    rd.res.linear.devPtr = ptrs[k];
+    rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+    rd.res.linear.sizeInBytes = counts[k] * 32;
+    cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+    CU(cudaCreateTextureObject(objs[k], &rd, &td, nullptr));
+  }
   // Riemann abscissae of areaUnderCurve (src/face_utils.cpp:304-323) for the bins of src/FaceForest.cpp:216-222
   {
     float poseT[6];

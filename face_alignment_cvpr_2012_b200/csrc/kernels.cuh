@@ -579,6 +579,7 @@ struct TraverseArgs {
   const DevSlot16* slots16;      // compact form of the same slots (k_traverse16)
   const DevSlotW* slotsw;        // window form of the same slots (k_traverse_win)
   cudaTextureObject_t slotsw_tex;  // the same array as a linear uint4 texture (two texels per record)
+  cudaTextureObject_t slots_tex;   // `slots` as a linear uint4 texture (k_traverse with MODE bit 3)
   const int32_t* roots;        // shared tree list (head pose) or nullptr
   const int32_t* face_roots;   // [face][kMaxList] composed lists (FFD) or nullptr
   const int32_t* face_ntrees;  // [face] or nullptr
@@ -616,7 +617,8 @@ __device__ __forceinline__ uint32_t rect_sum_strips(const stack_t* __restrict__ 
 }
 
 // LW = lanes along x (32: one row of 32 x-adjacent patches; 8: an 8 x 4 block of patches).
-// MODE bit 0: corner loads bypass L1 allocation; bit 1: one 256-bit load per node record instead of two 128-bit.
+// MODE bit 0: corner loads bypass L1 allocation; bit 1: one 256-bit load per node record instead of two 128-bit;
+// bit 3: the node record comes through the texture pipe (two uint4 texel fetches).
 template <int NW, bool COUNT, int LW, int MODE>
 __global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
   extern __shared__ int32_t s_leaf[];  // [32][nt]
@@ -643,7 +645,9 @@ __global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
     if (active) {
       for (;;) {
         uint4 q0, q1;
-        if (MODE & 2) {
+        if (MODE & 8) {   // records through the texture pipe: leaves the LSU data pipe to the corner gathers
+          q0 = tex1Dfetch<uint4>(a.slots_tex, 2 * cur); q1 = tex1Dfetch<uint4>(a.slots_tex, 2 * cur + 1);
+        } else if (MODE & 2) {
           asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                        : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(slots + cur));
         } else {
@@ -790,7 +794,7 @@ __device__ __forceinline__ void ldg_slotw(const DevSlotW* p, uint4& q0, uint4& q
 
 // One node test of a walk.  col = shared address of the lane's patch column, row = byte offset of the lane's patch
 // row inside the ring.  q0 = px1, px2, yh1, yh2; q1 = m1, m2, child, tw.  Returns the next slot.
-__device__ __forceinline__ int win_step(const DevSlotW* __restrict__ slots, uint32_t col, uint32_t row, const uint4 q0, const uint4 q1, uint32_t live) {
+__device__ __forceinline__ int win_step(uint32_t col, uint32_t row, const uint4 q0, const uint4 q1, uint32_t live) {
   constexpr uint32_t kRing = kWinPlaneBytes;
   uint32_t ra1 = row + (q0.z & 0xffffu); ra1 = min(ra1, ra1 - kRing);
   uint32_t rc1 = ra1 + (q0.z >> 16);     rc1 = min(rc1, rc1 - kRing);
@@ -818,7 +822,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int
   const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_win);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lx = lane & 7, ly = lane >> 3;
-  const DevSlotW* __restrict__ slots = a.slotsw;
   unsigned tests = 0;
   unsigned long long trav = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -885,7 +888,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int
           for (;;) {
             const bool la = (int)a1.w < 0, lb = (int)b1.w < 0;
             if (la && lb) break;
-            const int ca = win_step(slots, col, rowA, a0, a1, la ? 0u : 1u), cb = win_step(slots, col, rowB, b0, b1, lb ? 0u : 1u);
+            const int ca = win_step(col, rowA, a0, a1, la ? 0u : 1u), cb = win_step(col, rowB, b0, b1, lb ? 0u : 1u);
             if (COUNT) tests += (vA && !la ? 1 : 0) + (vB && !lb ? 1 : 0);
             if (!la) fetch(ca, a0, a1);
             if (!lb) fetch(cb, b0, b1);
@@ -906,7 +909,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int
           uint4 a0, a1;
           fetch(roots[t], a0, a1);
           while ((int)a1.w >= 0) {
-            const int ca = win_step(slots, col, rowA, a0, a1, 1u);
+            const int ca = win_step(col, rowA, a0, a1, 1u);
             if (COUNT) tests += vA ? 1 : 0;
             fetch(ca, a0, a1);
           }
