@@ -149,6 +149,7 @@ struct crf_ctx {
   int traverse_variant = 0;  // 0 = pick by stride (see launch_traverse)
   int sm_count = 148;
   int win_hp = 0, win_ffd = 0;   // k_traverse_win variants (0 = default)
+  bool win_smem_ok = true;       // the device grants a CTA the 231 040 bytes of dynamic shared memory the window needs
   int win_tex = 1;               // node records of k_traverse_win through the texture pipe (CRF_WIN_TEX=0: 256-bit global loads)
   cudaTextureObject_t tex_hp = 0, tex_mp = 0, tex_hp_wide = 0, tex_mp_wide = 0;
   // 1 = consecutive chunks run back to back on one stream (default: measured faster — co-resident Gabor CTAs shrink the L1
@@ -341,7 +342,7 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   // CRF_TRAVERSE_VARIANT=0x100001 forces it, any other non-zero value selects one of the global-gather variants below.
   {
     const int ncols = (patches_1d(125, 1) + kWinTile - 1) / kWinTile;
-    const bool fits = stride == 1 && (hp ? c->hp.max_extent : c->mp.max_extent) <= kWinExtent && c->num_channels <= kWinMaxPlanes;
+    const bool fits = stride == 1 && (hp ? c->hp.max_extent : c->mp.max_extent) <= kWinExtent && c->num_channels <= kWinMaxPlanes && c->win_smem_ok;
     const bool forced = c->traverse_variant == 0x100001;
     if (forced && !fits) return fail(CRF_ERR_ARG, "CRF_TRAVERSE_VARIANT=0x100001 needs stride 1 and rectangles inside the window");
     if (fits && (forced || (c->traverse_variant == 0 && (long long)n * ncols >= 2LL * c->sm_count))) {
@@ -808,6 +809,11 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if ((rc = upload(c->d_hp_slots16, c->hp.slots16, c->w->stream)) || (rc = upload(c->d_mp_slots16, c->mp.slots16, c->w->stream))) return rc;
   if ((rc = upload(c->d_hp_slotsw, c->hp.slotsw, c->w->stream)) || (rc = upload(c->d_mp_slotsw, c->mp.slotsw, c->w->stream))) return rc;
   CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  {
+    int optin = 0;
+    CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    c->win_smem_ok = optin >= kWinSmemBytes;   // otherwise dense grids stay on the global-gather kernels
+  }
   if ((rc = upload(c->d_hp_slots, c->hp.slots, c->w->stream)) || (rc = upload(c->d_hp_roots, c->hp.roots, c->w->stream)) || (rc = upload(c->d_hp_m, c->hp.hp_m, c->w->stream)) ||
       (rc = upload(c->d_mp_slots, c->mp.slots, c->w->stream)) || (rc = upload(c->d_mp_roots, c->mp.roots, c->w->stream)) ||
       (rc = upload(c->d_mp_mask, c->mp.mp_mask, c->w->stream)) || (rc = upload(c->d_mp_leaf, c->mp.mp_leaf, c->w->stream)))
