@@ -1197,6 +1197,9 @@ __global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
   }
   const int32_t* __restrict__ ids = a.leaf_ids + f * a.leaf_face_stride;
   DevVote* __restrict__ fv = a.votes + (size_t)f * a.vote_cap;
+  // k / nt and patch / ny by multiplication: umulhi(k, 0xffffffff / d + 1) is exact for every k < 2^32 / d (k < 2^23 with
+  // d = nt <= 128, patch < 2^16 with d = ny <= 490; checked exhaustively in test_index_division_by_multiplication)
+  const unsigned m_nt = 0xffffffffu / (unsigned)nt + 1u, m_ny = 0xffffffffu / (unsigned)max(ny, 1) + 1u;
   int leaf_n = 0;
   unsigned mask_n = 0;
   if (k0 + lane < k1) { leaf_n = ids[k0 + lane]; mask_n = __ldg(a.mp_mask + leaf_n); }
@@ -1209,8 +1212,8 @@ __global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
 #pragma unroll
     for (int p = 0; p < kParts; p++) bal[p] = __ballot_sync(0xffffffffu, (mask >> p) & 1u);
     if (mask) {
-      const int patch = k / nt;
-      const int ix = patch / ny, iy = patch - ix * ny;
+      const int patch = nt == 1 ? k : (int)__umulhi((unsigned)k, m_nt);
+      const int ix = ny == 1 ? patch : (int)__umulhi((unsigned)patch, m_ny), iy = patch - ix * ny;
       const int cx = ix * a.stride + kHalfPatch, cy = iy * a.stride + kHalfPatch;  // patch centre (src/face_utils.cpp:281-282)
       union { uint4 q[3]; DevMpLeaf L; } u;
       const uint4* lp = reinterpret_cast<const uint4*>(a.mp_leaf + leaf);

@@ -102,6 +102,19 @@ def test_canny_matches_cv2(O, cv2_golden):
     assert planes.shape[0] == 3 and np.array_equal(planes[1], cv2_golden["canny"]) and np.array_equal(planes[2], cv2_golden["equalize"])
 
 
+def test_index_division_by_multiplication():
+    """k_votes_emit turns the flat leaf index into (patch, tree) and (ix, iy) with umulhi(k, 0xffffffff / d + 1), exact for
+    k < 2^32 / d: trees per face d <= 128 with k < 94 * 490 * 128 < 2^23, patch rows d <= 490 with patch < 94 * 490 < 2^16."""
+    k = np.arange(0, 1 << 23, dtype=np.uint64)
+    for d in range(2, 129):
+        m = np.uint64(0xffffffff // d + 1)
+        assert np.array_equal((k * m) >> np.uint64(32), k // np.uint64(d)), d
+    k = np.arange(0, 1 << 17, dtype=np.uint64)
+    for d in range(2, 491):
+        m = np.uint64(0xffffffff // d + 1)
+        assert np.array_equal((k * m) >> np.uint64(32), k // np.uint64(d)), d
+
+
 def test_meanshift_empty_and_single(O):
     mean, rnd, it = O.meanshift(np.zeros((0, 3), np.float32))
     assert mean.tolist() == [0, 0] and it == 1
