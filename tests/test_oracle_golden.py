@@ -105,8 +105,10 @@ def test_canny_matches_cv2(O, cv2_golden):
 def test_index_division_by_multiplication():
     """k_votes_emit turns the flat leaf index into (patch, tree) and (ix, iy) with umulhi(k, 0xffffffff / d + 1), exact for
     k < 2^32 / d: trees per face d <= 128 with k < 94 * 490 * 128 < 2^23, patch rows d <= 490 with patch < 94 * 490 < 2^16."""
-    k = np.arange(0, 1 << 23, dtype=np.uint64)
+    full = np.arange(0, 1 << 23, dtype=np.uint64)
+    sparse = np.concatenate([full[::13], full[-8192:]])
     for d in range(2, 129):
+        k = full if d in (15, 20, 128) else sparse   # the shipped forests (15 / 20 trees) and the cap exhaustively
         m = np.uint64(0xffffffff // d + 1)
         assert np.array_equal((k * m) >> np.uint64(32), k // np.uint64(d)), d
     k = np.arange(0, 1 << 17, dtype=np.uint64)
