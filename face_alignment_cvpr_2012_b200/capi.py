@@ -59,7 +59,7 @@ FACE_DTYPE = np.dtype([
 # every symbol include/crf_b200.h declares
 EXPORTS = [
     "crf_last_error", "crf_version", "crf_options_default", "crf_model_load", "crf_model_save_packed", "crf_model_load_packed",
-    "crf_model_info", "crf_model_tree_dump", "crf_model_free", "crf_device_count", "crf_ctx_create", "crf_ctx_destroy",
+    "crf_model_info", "crf_model_tree_dump", "crf_model_check_packing", "crf_model_free", "crf_device_count", "crf_ctx_create", "crf_ctx_destroy",
     "crf_ctx_set_profiling", "crf_ctx_stage_ms", "crf_ctx_counters", "crf_ctx_reset_counters", "crf_ctx_stream", "crf_host_alloc",
     "crf_host_free", "crf_analyze_faces", "crf_analyze_batch", "crf_analyze_crops", "crf_headpose_crops", "crf_analyze_crops_device",
     "crf_stage_gray_resize", "crf_stage_channels", "crf_stage_minmax", "crf_stage_norm", "crf_stage_canny", "crf_stage_eval_forest", "crf_stage_headpose",
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.crf_model_load_packed.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.crf_model_info.argtypes = [vp, C.POINTER(ModelInfo)]
     L.crf_model_tree_dump.argtypes = [vp, C.c_int, C.c_int, i32p, C.c_int]
+    L.crf_model_check_packing.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.crf_model_free.argtypes = [vp]
     L.crf_model_free.restype = None
     L.crf_ctx_create.argtypes = [vp, C.c_int, C.POINTER(Options), C.POINTER(vp)]

@@ -737,6 +737,55 @@ int crf_model_tree_dump(const crf_model* m, int which, int tree, int32_t* out, i
   return n;
 }
 
+// Host-only self-check of the device image (no GPU needed): packs the forests as crf_ctx_create does and verifies that the
+// three record forms of every node (wide DevSlot, compact DevSlot16, window DevSlotW) describe the same test, that children
+// are adjacent, that window leaves loop onto themselves, and that max_extent is the largest rectangle extent.
+// Returns the number of records checked (> 0) or a negative status; *max_extent_hp / *max_extent_ffd may be NULL.
+int crf_model_check_packing(const crf_model* m, int* max_extent_hp, int* max_extent_ffd) {
+  if (!m) return fail(CRF_ERR_ARG, "null argument");
+  PackOptions po;
+  std::string err;
+  long long checked = 0;
+  for (int which = 0; which < 2; which++) {
+    PackedForest pf;
+    std::vector<const FlatForest*> fs;
+    if (which == 0) fs.push_back(&m->m.hp); else for (auto& f : m->m.jungle) fs.push_back(&f);
+    const int rc = pack_forests(fs, which == 0 ? KIND_HEADPOSE : KIND_MULTIPART, po, pf, err);
+    if (rc) return fail(rc, err);
+    if (pf.slots.size() != pf.slots16.size() || pf.slots.size() != pf.slotsw.size()) return fail(CRF_ERR_STATE, "record arrays differ in length");
+    int ext = 0;
+    for (size_t i = 0; i < pf.slots.size(); i++) {
+      const DevSlot& a = pf.slots[i]; const DevSlot16& b = pf.slots16[i]; const DevSlotW& w = pf.slotsw[i];
+      const bool leaf16 = (b.r1 >> 26) & 1u, leafw = (w.tw >> 31) & 1u;
+      if ((a.is_leaf != 0) != leaf16 || leaf16 != leafw) return fail(CRF_ERR_STATE, "leaf flags disagree");
+      if (a.is_leaf) {
+        if (b.child != a.child || (int32_t)w.m2 != a.child || w.child != (int32_t)i || (w.tw & 0xffffu) != 0x7fffu || w.px1 || w.px2 || w.yh1 || w.yh2 || w.m1)
+          return fail(CRF_ERR_STATE, "leaf record mismatch");
+      } else {
+        const int x1 = a.a1 % kRowStride, y1 = a.a1 / kRowStride, x2 = a.a2 % kRowStride, y2 = a.a2 / kRowStride;
+        const int h1 = ((a.ns1 - 1) * a.hs1 + a.hl1) / kRowStride, h2 = ((a.ns2 - 1) * a.hs2 + a.hl2) / kRowStride;
+        const bool ok16 = (int)(b.r1 & 31) == x1 && (int)((b.r1 >> 5) & 31) == y1 && (int)((b.r1 >> 10) & 31) == a.w1 && (int)((b.r1 >> 15) & 31) == h1 &&
+                          (int)((b.r1 >> 20) & 63) == a.ch && (int)(b.r2 & 31) == x2 && (int)((b.r2 >> 5) & 31) == y2 && (int)((b.r2 >> 10) & 31) == a.w2 &&
+                          (int)((b.r2 >> 15) & 31) == h2 && (int)((b.r2 >> 20) & 0x3ff) - 256 == a.thr && b.child == a.child &&
+                          (b.areas & 0xffff) == (uint32_t)a.w1 * h1 && (b.areas >> 16) == (uint32_t)a.w2 * h2;
+        const bool okw = w.px1 == (uint32_t)a.ch * kWinPlaneBytes + x1 * 4u && w.px2 == (uint32_t)a.ch * kWinPlaneBytes + x2 * 4u &&
+                         w.yh1 == ((uint32_t)y1 * kWinRowBytes | ((uint32_t)h1 * kWinRowBytes) << 16) && w.yh2 == ((uint32_t)y2 * kWinRowBytes | ((uint32_t)h2 * kWinRowBytes) << 16) &&
+                         w.m1 == a.m1 && w.m2 == a.m2 && w.child == a.child && (int)(short)(w.tw & 0xffffu) == a.thr &&
+                         ((w.tw >> 16) & 0xffu) == a.w1 * 4u && ((w.tw >> 24) & 0x7fu) == a.w2 * 4u &&
+                         a.m1 == magic_for_area((uint32_t)a.w1 * h1) && a.m2 == magic_for_area((uint32_t)a.w2 * h2);
+        if (!ok16 || !okw) return fail(CRF_ERR_STATE, "record forms disagree at slot " + std::to_string(i));
+        if (a.child <= (int32_t)i || (size_t)a.child + 1 >= pf.slots.size()) return fail(CRF_ERR_STATE, "children are not laid out after their parent");
+        ext = std::max(ext, std::max(std::max(x1 + a.w1, y1 + h1), std::max(x2 + a.w2, y2 + h2)));
+      }
+      checked++;
+    }
+    if (ext != pf.max_extent) return fail(CRF_ERR_STATE, "max_extent is not the largest rectangle extent");
+    if (which == 0 && max_extent_hp) *max_extent_hp = ext;
+    if (which == 1 && max_extent_ffd) *max_extent_ffd = ext;
+  }
+  return (int)std::min<long long>(checked, 0x7fffffff);
+}
+
 void crf_model_free(crf_model* m) { delete m; }
 
 int crf_device_count(void) {

@@ -135,3 +135,23 @@ def test_config_file_parser(crf):
     p = crf.loadConfigFile(str(cfg))
     assert (p.ntrees, p.max_depth, p.face_size, p.features, p.tree_path) == (20, 20, 125, [0, 1, 2], "data/trees_ffd")
     assert p.getPatchSize() == 31 and p.image_path.endswith("lfw_ffd_ann.txt")
+
+
+def test_device_record_forms_agree(crf, synth_models, tmp_path):
+    """pack.cc without a GPU: the wide, compact and shared-memory-window node records describe the same tests (crf_model_check_packing),
+    for the synthetic forests, for forests with 30x30 rectangles, and for the shipped forests when they are staged."""
+    import ctypes as C
+    from face_alignment_cvpr_2012_b200 import capi, synthetic_model as sm, workloads as wl
+    def check(model):
+        hp, ffd = C.c_int(-1), C.c_int(-1)
+        n = capi.lib().crf_model_check_packing(model.h, C.byref(hp), C.byref(ffd))
+        assert n > 0, capi.lib().crf_last_error()
+        return n, hp.value, ffd.value
+    n, hp, ffd = check(synth_models[0])
+    assert n == synth_models[0].info["hp_nodes"] + synth_models[0].info["mp_nodes"] and 0 < hp <= 30 and 0 < ffd <= 30
+    big = crf.Model(*sm.write_model(tmp_path / "big", seed=3, hp_depth=6, ffd_depth=6, max_rect=30), 15, 20)
+    assert check(big)[1] <= 30
+    p = wl.staged_model_path()
+    if p is not None:
+        n, hp, ffd = check(crf.Model(packed=str(p)))
+        assert (hp, ffd) == (30, 30) and n == 176841 + 1536652   # SURVEY Appendix C node counts; extents as measured in DESIGN 4.1
