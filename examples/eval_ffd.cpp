@@ -10,7 +10,9 @@
 // converts a directory).  Built with -DCRF_B200_WITH_OPENCV a maintainer swaps load_image for cv::imread.
 //
 //   g++ -std=c++17 -O2 -Iinclude examples/eval_ffd.cpp -Lface_alignment_cvpr_2012_b200/_lib -lcrf_b200 -o eval_ffd
-//   ./eval_ffd [--all] [--annotations FILE] [--out output/errors.txt] [config_ffd.txt [config_headpose.txt]]
+//   ./eval_ffd [--all] [--headpose] [--annotations FILE] [--out output/errors.txt] [config_ffd.txt [config_headpose.txt]]
+// --headpose runs the reference's other evaluation main instead (src/eval_headpose.cpp:57-139): annotations from the head-pose
+// config, "Real:<pose> Predict:<headpose>" per image, no error file.
 // A "Path to trees" that names a *.crfb200 file (the pre-packed forest image) instead of a directory loads that
 // image; both config files then name the same file.
 #include <cmath>
@@ -128,10 +130,11 @@ float getInterOccularDist(const FaceAnnotation& a) {
 
 int main(int argc, char** argv) {
   std::string ffd_config_file = "data/config_ffd.txt", headpose_config_file = "data/config_headpose.txt", out_path = "output/errors.txt", ann_override;
-  bool all = false;
+  bool all = false, headpose = false;
   int npos = 0;
   for (int i = 1; i < argc; i++) {
     if (!std::strcmp(argv[i], "--all")) all = true;
+    else if (!std::strcmp(argv[i], "--headpose")) headpose = true;
     else if (!std::strcmp(argv[i], "--annotations") && i + 1 < argc) ann_override = argv[++i];
     else if (!std::strcmp(argv[i], "--out") && i + 1 < argc) out_path = argv[++i];
     else if (npos++ == 0) ffd_config_file = argv[i];
@@ -140,10 +143,11 @@ int main(int argc, char** argv) {
   Param hp_param, mp_param;
   if (!loadConfigFile(headpose_config_file, hp_param)) return EXIT_FAILURE;
   if (!loadConfigFile(ffd_config_file, mp_param)) return EXIT_FAILURE;
-  if (!ann_override.empty()) mp_param.image_path = ann_override;
+  if (!ann_override.empty()) mp_param.image_path = hp_param.image_path = ann_override;
+  const std::string ann_path = headpose ? hp_param.image_path : mp_param.image_path;   // src/eval_headpose.cpp:118 / src/eval_ffd.cpp:146
 
   std::vector<FaceAnnotation> annotations;
-  if (!loadAnnotations(mp_param.image_path, annotations)) return EXIT_FAILURE;
+  if (!loadAnnotations(ann_path, annotations)) return EXIT_FAILURE;
 
   // src/eval_ffd.cpp:150-165: by head-pose class, the last 10 % of each class is the test set
   std::vector<std::vector<FaceAnnotation>> ann(NUM_HEADPOSE_CLASSES), test_ann(NUM_HEADPOSE_CLASSES);
@@ -164,9 +168,10 @@ int main(int argc, char** argv) {
   for (const auto& cls : test_ann)
     for (const FaceAnnotation& a : cls) {
       std::vector<unsigned char> bgr; int rows = 0, cols = 0;
-      if (a.parts.size() < 8 || !load_image(mp_param.image_path, a.url, bgr, rows, cols)) { std::cerr << "(!) Error: Could not load: " << a.url << std::endl; continue; }
+      if ((!headpose && a.parts.size() < 8) || !load_image(ann_path, a.url, bgr, rows, cols)) { std::cerr << "(!) Error: Could not load: " << a.url << std::endl; continue; }
       crf_b200::Face face;
       ff.analyzeFace(cvlite::Mat(rows, cols, bgr.data()), a.bbox, face);
+      if (headpose) { std::cout << "Real:" << a.pose << " Predict:" << face.headpose << std::endl; continue; }   // src/eval_headpose.cpp:88
       std::vector<float> err;
       const float iod = getInterOccularDist(a);
       for (size_t j = 0; j < face.ffd_cordinates.size() && j < a.parts.size(); j++) {
@@ -176,6 +181,7 @@ int main(int argc, char** argv) {
       errors.push_back(err);
     }
 
+  if (headpose) return EXIT_SUCCESS;
   std::ofstream ofs(out_path.c_str(), std::ios::out);
   if (!ofs.is_open()) { std::cerr << "(!) Error: Could not write: " << out_path << std::endl; return EXIT_FAILURE; }
   double sum = 0; size_t n = 0;

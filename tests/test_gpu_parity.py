@@ -540,6 +540,14 @@ def test_cpp_eval_ffd_driver(crf, staged_models, lfw_faces, lfw_golden, gpu, tmp
         iod = np.linalg.norm((gt[0] + gt[1]) / 2 - (gt[6] + gt[7]) / 2)
         want = np.linalg.norm(gt - lfw_golden["recs"][k]["ffd"], axis=1) / iod
         assert np.allclose(e, want, rtol=1e-4, atol=1e-5)   # errors.txt holds 6 significant digits
+    # the reference's eval_headpose main (src/eval_headpose.cpp): "Real:<pose> Predict:<headpose>" per image
+    r = subprocess.run([str(exe), "--all", "--headpose", cfg("config_ffd.txt", 20), cfg("config_headpose.txt", 15)], capture_output=True, text=True, timeout=300)
+    lines = [l for l in r.stdout.split("\n") if l.startswith("Real:")]
+    assert r.returncode == 0 and len(lines) == 20, r.stdout + r.stderr
+    for f, l in zip(order, lines):
+        real, pred = l.split(" Predict:")
+        assert int(real[5:]) == f["pose"]
+        assert abs(float(pred) - float(lfw_golden["recs"][names.index(f["name"])]["headpose"])) < 1e-5
 
 
 def test_analyze_image_with_host_haar_detector(crf, staged_models, lfw_faces, gpu):
