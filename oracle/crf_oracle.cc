@@ -7,11 +7,12 @@
 // or call it.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference leg use it.
 //
-// Parity pin: the reference cannot be compiled in this image (no OpenCV / Boost
-// headers), and it ships no tests or golden vectors for this path.  The OpenCV-
-// defined stages (cvtColor, resize, integral, Sobel, erode/dilate, filter2D 7x7,
-// normalize, convertTo) are pinned bit-exactly against cv2 4.13 by
-// tests/golden/make_golden.py + tests/test_oracle_vs_cv2.py; the Gabor planes of
+// PARITY UNPINNED by the reference itself: it cannot be compiled in this image (no
+// OpenCV / Boost headers) and it ships no tests or golden vectors for this path
+// (DESIGN.md section 2).  What pins the oracle instead: the OpenCV-defined stages
+// (cvtColor, resize, integral, Sobel, erode/dilate, equalizeHist, Canny, filter2D
+// 7x7, normalize, convertTo) are pinned bit-exactly against cv2 4.13 by
+// tests/golden/make_golden.py + tests/test_oracle_golden.py; the Gabor planes of
 // kernel size >= 9 (cv2 switches to a DFT path there) are pinned statistically
 // (+-1 LSB rate).  The tree parser is pinned on the 115 shipped
 // archives (every token consumed, node counts == header).
