@@ -7,15 +7,18 @@
 // or call it.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference leg use it.
 //
-// PARITY UNPINNED by the reference itself: it cannot be compiled in this image (no
-// OpenCV / Boost headers) and it ships no tests or golden vectors for this path
-// (DESIGN.md section 2).  What pins the oracle instead: the OpenCV-defined stages
-// (cvtColor, resize, integral, Sobel, erode/dilate, equalizeHist, Canny, filter2D
-// 7x7, normalize, convertTo) are pinned bit-exactly against cv2 4.13 by
-// tests/golden/make_golden.py + tests/test_oracle_golden.py; the Gabor planes of
-// kernel size >= 9 (cv2 switches to a DFT path there) are pinned statistically
-// (+-1 LSB rate).  The tree parser is pinned on the 115 shipped
-// archives (every token consumed, node counts == header).
+// PARITY PINNED TO THE REFERENCE'S OWN CODE (round 2): oracle/_ref/libcrf_ref.so is the reference's
+// src/{FaceForest,face_utils,ImageSample,HeadPoseSample,MPSample}.cpp + include/*.hpp compiled UNMODIFIED where
+// they lie (oracle/Makefile `ref`) against type stand-ins for OpenCV / Boost (oracle/shim/; this image has neither).
+// tests/test_reference_pin.py holds this restatement to it bit for bit: the 115 shipped archives read through the
+// reference's serialize() methods, leaf ids, head-pose mean / variance, areaUnderCurve, forest composition, vote
+// lists, MeanShift::shift, analyzeFace end to end.  The one thing the reference does NOT define itself is the
+// OpenCV arithmetic underneath (cvtColor, resize, integral, Sobel, erode/dilate, equalizeHist, Canny, filter2D,
+// normalize, convertTo): those stages are pinned bit-exactly against cv2 4.13 by tests/golden/make_golden.py +
+// tests/test_oracle_golden.py, except filter2D with kernels >= 9x9, where cv2 (2.4.9 and 4.13) takes a DFT path no
+// direct sum can match bit for bit — there the canonical arithmetic is DEFINED here (separable form) and its
+// distance to cv2 and to a double-accumulated direct sum is pinned statistically (+-1 LSB of the u8 plane, rate
+// < 2e-4).
 //
 // All file:line citations are relative to /root/reference/.
 // =============================================================================
@@ -1304,6 +1307,66 @@ void orc_gabor_response(const uint8_t* gray, int H, int W, int index, float* re,
   filter2d_f32(img, gk.im, gk.width, i);
   std::memcpy(re, r.d.data(), sizeof(float) * r.d.size());
   std::memcpy(im, i.d.data(), sizeof(float) * i.d.size());
+}
+
+// ---- single-stage exports used by oracle/shim/cvshim.cc (the OpenCV stand-in of the real-reference build, _ref/):
+// each is one of the cv2-pinned stages above on dense H x W planes.
+void orc_cv_integral(const uint8_t* src, int H, int W, float* dst /* (H+1) x (W+1) */) {
+  Plane8 s; s.rows = H; s.cols = W; s.d.assign(src, src + (size_t)H * W);
+  PlaneF d; integral_f32(s, d);
+  std::memcpy(dst, d.d.data(), sizeof(float) * d.d.size());
+}
+void orc_cv_sobel(const uint8_t* src, int H, int W, int dx, int dy, uint8_t* dst) {
+  Plane8 s; s.rows = H; s.cols = W; s.d.assign(src, src + (size_t)H * W);
+  Plane8 d; sobel_u8(s, d, dx, dy);
+  std::memcpy(dst, d.d.data(), d.d.size());
+}
+void orc_cv_minmax(const uint8_t* src, int H, int W, uint8_t* mn, uint8_t* mx) {
+  Plane8 s; s.rows = H; s.cols = W; s.d.assign(src, src + (size_t)H * W);
+  Plane8 a, b; minmax3x3_u8(s, a, b);
+  if (mn) std::memcpy(mn, a.d.data(), a.d.size());
+  if (mx) std::memcpy(mx, b.d.data(), b.d.size());
+}
+void orc_cv_equalize(const uint8_t* src, int H, int W, uint8_t* dst) {
+  Plane8 s; s.rows = H; s.cols = W; s.d.assign(src, src + (size_t)H * W);
+  Plane8 d; equalize_hist_u8(s, d);
+  std::memcpy(dst, d.d.data(), d.d.size());
+}
+void orc_cv_canny(const uint8_t* src, int H, int W, int low, int high, uint8_t* dst) {
+  Plane8 s; s.rows = H; s.cols = W; s.d.assign(src, src + (size_t)H * W);
+  Plane8 d; canny_u8(s, d, low, high);
+  std::memcpy(dst, d.d.data(), d.d.size());
+}
+// cv::filter2D(u8 -> f32) with a caller-supplied kw x kw kernel.  mode 0: raster order, product and sum rounded separately
+// (== cv2 for the sizes cv2 evaluates directly); mode 1: raster order accumulated in double, rounded once (the closest
+// f32 to the exact response — the neutral stand-in for cv2's DFT path, which no direct sum matches bit for bit).
+void orc_cv_filter2d(const uint8_t* src, int H, int W, const float* kern, int kw, int mode, float* dst) {
+  Plane8 s; s.rows = H; s.cols = W; s.d.assign(src, src + (size_t)H * W);
+  if (mode == 0) {
+    PlaneF d; filter2d_f32(s, std::vector<float>(kern, kern + (size_t)kw * kw), kw, d);
+    std::memcpy(dst, d.d.data(), sizeof(float) * d.d.size());
+    return;
+  }
+  const int r = kw / 2;
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      double acc = 0;
+      for (int j = 0; j < kw; j++) {
+        const int sy = border101(y + j - r, H);
+        for (int i = 0; i < kw; i++) acc += (double)s.at(sy, border101(x + i - r, W)) * (double)kern[(size_t)j * kw + i];
+      }
+      dst[(size_t)y * W + x] = (float)acc;
+    }
+}
+// Canonical complex response of bank kernel `index` (separable form for widths >= 9, raster for 7): what gabor_transform uses.
+void orc_cv_gabor_canonical(const uint8_t* src, int H, int W, int index, float* re, float* im) {
+  Plane8 s; s.rows = H; s.cols = W; s.d.assign(src, src + (size_t)H * W);
+  const auto& gk = gabor_bank()[index];
+  PlaneF r, i;
+  if (gk.width >= 9) gabor_response_separable(s, gk, r, i);
+  else { filter2d_f32(s, gk.re, gk.width, r); filter2d_f32(s, gk.im, gk.width, i); }
+  if (re) std::memcpy(re, r.d.data(), sizeof(float) * r.d.size());
+  if (im) std::memcpy(im, i.d.data(), sizeof(float) * i.d.size());
 }
 
 int orc_num_patches(int W, int H, int patch, int step) {
