@@ -36,7 +36,7 @@ class Options(C.Structure):
     _fields_ = [("hp_stride", C.c_int), ("hp_min_foreground", C.c_float), ("ffd_stride", C.c_int), ("ffd_min_samples", C.c_int),
                 ("ffd_min_foreground", C.c_float), ("ffd_min_pf", C.c_float), ("ffd_max_variance", C.c_float),
                 ("ms_kernel_size", C.c_int), ("ms_max_iterations", C.c_int), ("ms_stopping_criteria", C.c_float),
-                ("max_chunk", C.c_int), ("max_scaled_h", C.c_int)]
+                ("max_chunk", C.c_int), ("max_scaled_h", C.c_int), ("ms_mode", C.c_int)]
 
 
 class ModelInfo(C.Structure):
@@ -63,7 +63,9 @@ EXPORTS = [
     "crf_ctx_set_profiling", "crf_ctx_stage_ms", "crf_ctx_counters", "crf_ctx_reset_counters", "crf_ctx_stream", "crf_host_alloc",
     "crf_host_free", "crf_analyze_faces", "crf_analyze_batch", "crf_analyze_crops", "crf_headpose_crops", "crf_analyze_crops_device",
     "crf_stage_gray_resize", "crf_stage_channels", "crf_stage_minmax", "crf_stage_norm", "crf_stage_canny", "crf_stage_eval_forest", "crf_stage_headpose",
-    "crf_stage_compose", "crf_stage_votes_meanshift", "crf_stage_meanshift",
+    "crf_stage_compose", "crf_stage_compose_batch", "crf_stage_votes_meanshift", "crf_stage_meanshift",
+    "crf_model_load_forest", "crf_model_set_features", "crf_model_get_features", "crf_model_leaf_dump", "crf_stage_feature_channels",
+    "crf_stage_eval_patches", "crf_stage_eval_tests",
 ]
 
 _lib = None
@@ -125,8 +127,16 @@ def lib() -> C.CDLL:
     L.crf_stage_eval_forest.argtypes = [vp, C.c_int, i32p, i32p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.crf_stage_headpose.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, i32p, i32p, i32p, i32p, i32p, i32p]
     L.crf_stage_compose.argtypes = [vp, C.c_float, C.c_float, i32p, i32p, i32p, i32p, i32p, i32p]
+    L.crf_stage_compose_batch.argtypes = [vp, f32p, f32p, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p, C.c_int]
     L.crf_stage_votes_meanshift.argtypes = [vp, i32p, i32p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, f32p, C.c_int, f32p, i32p, i32p]
     L.crf_stage_meanshift.argtypes = [vp, f32p, C.c_int, f32p, i32p, i32p]
+    L.crf_model_load_forest.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    L.crf_model_set_features.argtypes = [vp, i32p, C.c_int]
+    L.crf_model_get_features.argtypes = [vp, i32p, C.c_int]
+    L.crf_model_leaf_dump.argtypes = [vp, C.c_int, C.c_int, f32p, C.c_int]
+    L.crf_stage_feature_channels.argtypes = [vp, u8p, C.c_int, C.c_int, i32p, C.c_int, u8p, C.POINTER(C.c_uint32)]
+    L.crf_stage_eval_patches.argtypes = [vp, C.c_int, i32p, i32p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i32p]
+    L.crf_stage_eval_tests.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i32p]
     _lib = L
     return L
 

@@ -115,6 +115,33 @@ struct StageTimer {
   void destroy() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
 };
 
+// Planes of an ImageSample in the order extractFeatureChannels appends them: features sorted by id, FC_GRAY 1 plane,
+// FC_GABOR 35, FC_SOBEL 2 (d/dy, d/dx), FC_MIN_MAX 2 (erode, dilate), FC_CANNY 1, FC_NORM 1
+// (src/ImageSample.cpp:77-90, include/FeatureChannelFactory.hpp:35-183).
+struct ChannelLayout {
+  int nplanes = 0;
+  int gabor_first = -1;   // first of the 35 Gabor planes, -1 = FC_GABOR not configured
+  PlainPlanes pp{};       // the non-Gabor planes: kernel selector + output plane
+  int n_plain = 0;
+  bool canny = false;
+};
+static ChannelLayout layout_of(const std::vector<int>& sorted_features) {
+  ChannelLayout L;
+  auto plain = [&](int which) { L.pp.which[L.n_plain] = which; L.pp.plane[L.n_plain] = L.nplanes++; L.n_plain++; };
+  for (int f : sorted_features) {
+    switch (f) {
+      case 0: plain(0); break;
+      case 1: L.gabor_first = L.nplanes; L.nplanes += 35; break;
+      case 2: plain(1); plain(2); break;
+      case 3: plain(3); plain(4); break;
+      case 4: plain(6); L.canny = true; break;
+      case 5: plain(5); break;
+      default: break;
+    }
+  }
+  return L;
+}
+
 }  // namespace crf
 
 using namespace crf;
@@ -127,6 +154,8 @@ struct crf_ctx {
   size_t h_stage_bytes[2] = {0, 0};
   crf_options_t opt{};
   int hp_ntrees = 0, mp_ntrees_cfg = 0, num_channels = 38;
+  ChannelLayout layout;   // planes of the model's feature list
+  bool full_model = true; // head-pose forest + 5 pose forests: what analyzeFace needs (a partial model serves Forest<S> alone)
   PackedForest hp, mp;  // host copies (object-id maps for the stage API)
   // device model
   Buf d_hp_slotsw, d_mp_slotsw, d_hp_slots16, d_mp_slots16, d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5], d_coef_sep[5];
@@ -155,6 +184,7 @@ struct crf_ctx {
   // 1 = consecutive chunks run back to back on one stream (default: measured faster — co-resident Gabor CTAs shrink the L1
   // the gathers live on, and two chunks' stacks thrash L2); 2 = alternate chunks between two streams / work sets
   int nstreams = 1;
+  int ms_mode = CRF_MS_FAST;   // resolved from crf_options_t::ms_mode / CRF_MS_MODE at creation
   int ms_variant = 3;   // resident MeanShift CTAs per SM the kernel is compiled for (register cap); CRF_MS_VARIANT overrides
   size_t work_budget = (size_t)64 << 30;  // bytes of work buffers a launch may use (min(64 GB, half of the free memory at creation))
   StageTimer timer;
@@ -278,24 +308,17 @@ static int launch_resize(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, const 
   return CRF_OK;
 }
 
-static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, int extra /* 0: features {0,1,2}; 1: FC_MIN_MAX; 2: FC_NORM; 3: FC_CANNY */, bool want_u8) {
-  const bool minmax_planes = extra != 0;
+static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, const ChannelLayout& L, bool want_u8) {
   uint8_t* u8 = want_u8 ? c->w->d_u8planes.as<uint8_t>() : nullptr;
   uint32_t* dbg32 = want_u8 ? c->w->d_int32.as<uint32_t>() : nullptr;   // full 32-bit integrals, stage API only
-  {
+  if (L.n_plain > 0) {
     Span s(c, CRF_STAGE_PLAIN);
-    PlainPlanes pp{};
-    int nw;
-    if (!minmax_planes) { nw = 3; pp.which[0] = 0; pp.plane[0] = 0; pp.which[1] = 1; pp.plane[1] = 36; pp.which[2] = 2; pp.plane[2] = 37; }
-    else if (extra == 1) { nw = 2; pp.which[0] = 3; pp.plane[0] = 0; pp.which[1] = 4; pp.plane[1] = 1; }
-    else if (extra == 2) { nw = 1; pp.which[0] = 5; pp.plane[0] = 0; }
-    else { nw = 1; pp.which[0] = 6; pp.plane[0] = 0; }
-    const size_t smem = extra == 3 ? (size_t)(Hmax + 2) * 127 * 3 : 0;   // FC_CANNY: u16 magnitudes + u8 map of the padded face
-    k_plain_channels<<<dim3(nw, n), 128, smem, c->w->stream>>>(fd, c->w->d_scaled.as<uint8_t>(), c->w->scaled_fs, c->w->d_stacks.as<stack_t>(), c->w->stack_fs,
-                                                         c->w->plane_stride, u8, c->w->u8_fs, dbg32, pp);
+    const size_t smem = L.canny ? (size_t)(Hmax + 2) * 127 * 3 : 0;   // FC_CANNY: u16 magnitudes + u8 map of the padded face
+    k_plain_channels<<<dim3(L.n_plain, n), 128, smem, c->w->stream>>>(fd, c->w->d_scaled.as<uint8_t>(), c->w->scaled_fs, c->w->d_stacks.as<stack_t>(), c->w->stack_fs,
+                                                                 c->w->plane_stride, u8, c->w->u8_fs, dbg32, L.pp);
     KCHECK(); count_launch(c, CRF_STAGE_PLAIN);
   }
-  if (minmax_planes) return CRF_OK;
+  if (L.gabor_first < 0) return CRF_OK;
   Span s(c, CRF_STAGE_GABOR);
   k_init_minmax<<<(n * 70 + 255) / 256, 256, 0, c->w->stream>>>(c->w->d_minmax.as<uint32_t>(), n * 70);
   KCHECK();
@@ -310,7 +333,7 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, int 
   k_gabor_sep<13><<<gsym, 256, GaborSepSmem<13>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[2].as<float>(), 2, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
   k_gabor_sep<9><<<gsym, 256, GaborSepSmem<9>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[1].as<float>(), 1, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
   k_gabor_mag<7><<<grid, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef[0].as<float2>(), 0, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
-  k_gabor_quant_integral<<<dim3(35, n), 128, 0, c->w->stream>>>(fd, mag, c->w->mag_fs, c->w->mag_ps, mm, c->w->d_stacks.as<stack_t>(), c->w->stack_fs, c->w->plane_stride, 1,
+  k_gabor_quant_integral<<<dim3(35, n), 128, 0, c->w->stream>>>(fd, mag, c->w->mag_fs, c->w->mag_ps, mm, c->w->d_stacks.as<stack_t>(), c->w->stack_fs, c->w->plane_stride, L.gabor_first,
                                                              u8, c->w->u8_fs, dbg32);
   KCHECK(); count_launch(c, CRF_STAGE_GABOR, 7);
   return CRF_OK;
@@ -357,7 +380,16 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
         kf<<<grid, NW_ * 32, kWinSmemBytes, c->w->stream>>>(a, nitems, ncols, c->num_channels);                              \
         ok = true;                                                                                                           \
       }
+#define CRF_WINP(NW_)                                                                                                       \
+      if (wv == (NW_ | 2 << 8 | 1 << 12)) {   /* two walks per lane on horizontal neighbours, shared record fetch */        \
+        auto kf = c->counting ? k_traverse_win<NW_, 2, true, false, true> : c->win_tex ? k_traverse_win<NW_, 2, false, true, true> : k_traverse_win<NW_, 2, false, false, true>; \
+        CU(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmemBytes));                            \
+        kf<<<grid, NW_ * 32, kWinSmemBytes, c->w->stream>>>(a, nitems, ncols, c->num_channels);                              \
+        ok = true;                                                                                                           \
+      }
       CRF_WIN(15, 2) CRF_WIN(20, 2) CRF_WIN(10, 2) CRF_WIN(30, 1) CRF_WIN(32, 1) CRF_WIN(20, 1) CRF_WIN(24, 1) CRF_WIN(28, 1) CRF_WIN(16, 1)
+      CRF_WINP(15) CRF_WINP(20) CRF_WINP(10) CRF_WINP(16) CRF_WINP(24)
+#undef CRF_WINP
 #undef CRF_WIN
       if (!ok) return fail(CRF_ERR_ARG, "unknown CRF_WIN_HP / CRF_WIN_FFD variant");
       KCHECK(); count_launch(c, stage);
@@ -416,6 +448,16 @@ static int launch_meanshift(crf_ctx* c, const FaceDesc* fd, int nchains, crf_fac
   const int cpc = nchains >= 8192 ? 32 : std::max(1, std::min(8, nchains / 296));   // small batches: up to two CTAs per SM before chains share one
   const dim3 grid((nchains + cpc - 1) / cpc);
   unsigned long long* cnt = c->counting ? c->d_counters.as<unsigned long long>() : nullptr;
+  if (c->ms_mode == CRF_MS_FAST) {
+    // one CTA per chain; wide CTAs when the grids are dense (a stride-1 chain holds ~18 k votes, a default-stride one ~2 k)
+    const bool dense = c->w->ffd_leaf_fs >= 65536 || c->w->vote_cap >= 65536;
+    if (dense) k_meanshift_fast<512><<<nchains, 512, 0, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(),
+                                                                       c->w->d_vote_base.as<int32_t>(), mo, faces, cnt);
+    else k_meanshift_fast<128><<<nchains, 128, 0, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(),
+                                                                 c->w->d_vote_base.as<int32_t>(), mo, faces, cnt);
+    KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
+    return CRF_OK;
+  }
 #define CRF_MS(MINB)                                                                                                                                    \
   k_meanshift<MINB, false><<<grid, kFoldThreads, MsGeom<false>::smem, c->w->stream>>>(fd, nchains, c->w->d_votes.as<DevVote>(), c->w->vote_cap, c->w->d_vote_counts.as<int32_t>(), \
                                                                   c->w->d_vote_base.as<int32_t>(), cpc, mo, faces, cnt)
@@ -452,7 +494,7 @@ static int run_faces(crf_ctx* c, const FaceDesc* d_fd, int n, int Hmax, const ui
   int rc;
   if ((rc = launch_resize(c, d_fd, n, Hmax, d_imgs))) return rc;
   if (imgs_consumed) CU(cudaEventRecord(imgs_consumed, c->w->stream));
-  if ((rc = launch_channels(c, d_fd, n, Hmax, 0, false))) return rc;
+  if ((rc = launch_channels(c, d_fd, n, Hmax, c->layout, false))) return rc;
   if ((rc = launch_traverse(c, d_fd, n, Hmax, true, c->opt.hp_stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees, true))) return rc;
   if ((rc = launch_hp_reduce(c, d_fd, n, c->opt.hp_stride, !headpose_only, tree_cap, d_faces))) return rc;
   if (headpose_only) return CRF_OK;
@@ -467,8 +509,11 @@ static int run_faces(crf_ctx* c, const FaceDesc* d_fd, int n, int Hmax, const ui
 static int pick_chunk(const crf_ctx* c, int Hmax, bool headpose_only) {
   const size_t np_hp = (size_t)patches_1d(125, c->opt.hp_stride) * patches_1d(Hmax, c->opt.hp_stride);
   const size_t np_ffd = headpose_only ? 0 : (size_t)patches_1d(125, c->opt.ffd_stride) * patches_1d(Hmax, c->opt.ffd_stride);
-  const size_t per_face = (size_t)Hmax * 128 + (size_t)(Hmax + 1) * kRowStride * sizeof(stack_t) * 38 + (size_t)Hmax * 128 * 4 * 35 + np_hp * c->hp_ntrees * 4 +
-                          np_ffd * c->mp_ntrees_cfg * (4 + 3 * sizeof(DevVote)) + 4096;
+  // the same terms ensure() reserves per face
+  const size_t per_face = (size_t)Hmax * 128 + (size_t)(Hmax + 1) * kRowStride * sizeof(stack_t) * c->layout.nplanes +
+                          (c->layout.gabor_first >= 0 ? (size_t)Hmax * 128 * 4 * 35 + 35 * 2 * 4 : 0) + np_hp * c->hp_ntrees * 4 +
+                          np_ffd * c->mp_ntrees_cfg * (4 + 3 * sizeof(DevVote)) + (size_t)kMaxList * 4 + 4 +
+                          (headpose_only ? 0 : (size_t)kVoteSegs * kParts * 4 + 2 * kParts * 4) + sizeof(FaceDesc) + sizeof(crf_face_t);
   const size_t budget = c->work_budget / c->nstreams;
   long long chunk = (long long)(budget / per_face);
   const int cap = c->opt.max_chunk > 0 ? c->opt.max_chunk : 4096;
@@ -494,7 +539,7 @@ static int pull_counters(crf_ctx* c) {
 static int rerun_wide(crf_ctx* c, const FaceDesc* d_fd_all, const std::vector<FaceDesc>& descs, const uint8_t* d_imgs, crf_face_t* d_faces_all,
                       const std::vector<int>& which) {
   for (int i : which) {
-    Plan p; p.n = 1; p.Hmax = descs[i].H; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = kMaxList; p.vote_factor = kParts;
+    Plan p; p.n = 1; p.Hmax = descs[i].H; p.nplanes = c->layout.nplanes; p.need_gabor = c->layout.gabor_first >= 0; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = kMaxList; p.vote_factor = kParts;
     int rc = ensure(c, p);
     if (rc) return rc;
     if ((rc = run_faces(c, d_fd_all + i, 1, p.Hmax, d_imgs, d_faces_all + i, false, kMaxList, nullptr))) return rc;
@@ -507,6 +552,7 @@ static int rerun_wide(crf_ctx* c, const FaceDesc* d_fd_all, const std::vector<Fa
 static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, int rows, int cols, size_t step, const crf_rect_t* boxes,
                         const int* image_of_box, int n, crf_face_t* out, bool headpose_only) {
   if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!c->full_model) return fail(CRF_ERR_STATE, "analyzeFace needs the head-pose forest and the 5 pose forests; this context holds a single forest");
   if (n < 0 || (n > 0 && (!images || !boxes || !out))) return fail(CRF_ERR_ARG, "null argument");
   if (n == 0) return CRF_OK;
   if (step < (size_t)cols * 3) return fail(CRF_ERR_ARG, "step smaller than a row");
@@ -525,7 +571,19 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
   // when the boxes cover well under the frames' area (a few faces in a 1080p / 4K frame), only the box pixels travel — packed
   // row by row into a pinned staging buffer on the host while the GPU works on the previous chunk, then one H2D copy.
   // Pageable sources always go through the staging buffer (a threaded pack + pinned H2D beats the driver's pageable copy).
-  const bool src_pinned = is_pinned_host(images[image_of_box ? image_of_box[0] : 0]);
+  for (int i = 0; i < n; i++) {
+    const int im = image_of_box ? image_of_box[i] : i;
+    if (im < 0 || im >= n_images || !images[im]) return fail(CRF_ERR_ARG, "image index out of range");
+  }
+  // a batch is treated as pinned only if every frame it names is (one pageable frame sends the whole batch through the packed path)
+  bool src_pinned = true;
+  {
+    int last = -1;
+    for (int i = 0; i < n && src_pinned; i++) {
+      const int im = image_of_box ? image_of_box[i] : i;
+      if (im != last) { src_pinned = is_pinned_host(images[im]); last = im; }
+    }
+  }
   struct Chunk { int f0, f1, Hmax; bool roi; size_t bytes; std::vector<int> frames; };
   std::vector<Chunk> chunks;
   std::vector<crf_rect_t> src_box((size_t)n);   // where the pixels are in the caller's frame (ROI mode rewrites the descriptor)
@@ -578,7 +636,7 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
       c->h_stage_bytes[b] = max_roi + max_roi / 4;
     }
   }
-  Plan p; p.n = max_faces; p.Hmax = Hmax_all; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
+  Plan p; p.n = max_faces; p.Hmax = Hmax_all; p.nplanes = c->layout.nplanes; p.need_gabor = c->layout.gabor_first >= 0; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
   p.need_ffd = !headpose_only;
   const int nsets = chunks.size() > 1 ? c->nstreams : 1;
   for (int k = 0; k < nsets; k++) { c->w = &c->ws[k]; if ((rc = ensure(c, p))) return rc; }
@@ -672,7 +730,7 @@ void crf_options_default(crf_options_t* o) {
   o->hp_stride = 4; o->hp_min_foreground = 0.5f;                       // include/FaceForest.hpp:33-43
   o->ffd_stride = 3; o->ffd_min_samples = 2; o->ffd_min_foreground = 0.5f; o->ffd_min_pf = 0.25f; o->ffd_max_variance = 25.f;  // :45-58
   o->ms_kernel_size = 10; o->ms_max_iterations = 7; o->ms_stopping_criteria = 0.05f;  // include/MeanShift.hpp:16-25
-  o->max_chunk = 0; o->max_scaled_h = 0;
+  o->max_chunk = 0; o->max_scaled_h = 0; o->ms_mode = CRF_MS_DEFAULT;
 }
 
 int crf_model_load(const char* hp_dir, int hp_ntrees, const char* ffd_dir, int ffd_ntrees, crf_model** out) {
@@ -702,6 +760,70 @@ int crf_model_load_packed(const char* path, crf_model** out) {
   if (rc) return fail(rc, err);
   *out = m.release();
   return CRF_OK;
+}
+
+// Forest<S>::load on its own (include/Forest.hpp:103-129): a model holding just the head-pose forest (kind 0) or just one
+// facial-feature forest (kind 1, as pose forest 0).  Serves the Forest / Tree / ImageSample level of the reference interface;
+// analyzeFace needs crf_model_load.
+int crf_model_load_forest(const char* dir, int ntrees, int kind, crf_model** out) {
+  if (!out || !dir || (kind != 0 && kind != 1)) return fail(CRF_ERR_ARG, "bad argument");
+  *out = nullptr;
+  std::unique_ptr<crf_model> m(new crf_model());
+  std::string err;
+  int rc;
+  if (kind == 0) {
+    rc = load_forest_dir(dir, ntrees, KIND_HEADPOSE, m->m.hp, err);
+    m->m.hp_ntrees_cfg = ntrees;
+  } else {
+    m->m.jungle.resize(1);
+    rc = load_forest_dir(dir, ntrees, KIND_MULTIPART, m->m.jungle[0], err);
+    m->m.mp_ntrees_cfg = ntrees;
+  }
+  if (rc == CRF_OK) rc = validate_model(m->m, err);
+  if (rc) { std::fprintf(stderr, "(!) %s\n", err.c_str()); return fail(rc, err); }
+  *out = m.release();
+  return CRF_OK;
+}
+
+// ForestParam::features as the run-time configuration gives them (data/config_*.txt line 22; src/FaceForest.cpp:207 uses
+// hp_forest_param.features for both forests).  Default: the list stored in the head-pose forest's archives.
+int crf_model_set_features(crf_model* m, const int* features, int n) {
+  if (!m) return fail(CRF_ERR_ARG, "null argument");
+  std::string err;
+  const int rc = set_model_features(m->m, features, n, err);
+  return rc ? fail(rc, err) : CRF_OK;
+}
+
+int crf_model_get_features(const crf_model* m, int* features, int cap) {
+  if (!m) return fail(CRF_ERR_ARG, "null argument");
+  for (int i = 0; i < (int)m->m.features.size() && i < cap && features; i++) features[i] = m->m.features[i];
+  return (int)m->m.features.size();
+}
+
+// Leaf payloads of one tree in pre-order leaf numbering, 44 floats per leaf:
+//   head pose (which = -1): [object_id, hp_nsamples, hp_foreground, hp_labels[5]]                       (include/HeadPoseSample.hpp:144-162)
+//   pose forest which >= 0: [object_id, mp_samples, mp_foreground, mp_parts_offset[10][2], mp_parts_variance[10], mp_prob_foreground[10]]  (include/MPSample.hpp:137-159)
+int crf_model_leaf_dump(const crf_model* m, int which, int tree, float* out, int cap_leaves) {
+  if (!m) return fail(CRF_ERR_ARG, "null argument");
+  if (which >= (int)m->m.jungle.size()) return fail(CRF_ERR_ARG, "forest index out of range");
+  const FlatForest& f = which < 0 ? m->m.hp : m->m.jungle[which];
+  if (tree < 0 || tree >= (int)f.trees.size()) return fail(CRF_ERR_ARG, "tree index out of range");
+  const FlatTree& t = f.trees[tree];
+  const int n = which < 0 ? (int)t.hp_leaves.size() : (int)t.mp_leaves.size();
+  for (int i = 0; i < n && i < cap_leaves && out; i++) {
+    float* o = out + (size_t)i * 44;
+    std::fill(o, o + 44, 0.f);
+    if (which < 0) {
+      const HpLeaf& L = t.hp_leaves[i];
+      o[0] = (float)L.object_id; o[1] = (float)L.nsamples; o[2] = L.foreground;
+      for (int j = 0; j < 5; j++) o[3 + j] = (float)L.labels[j];
+    } else {
+      const MpLeaf& L = t.mp_leaves[i];
+      o[0] = (float)L.object_id; o[1] = (float)L.samples; o[2] = L.foreground;
+      for (int j = 0; j < 10; j++) { o[3 + 2 * j] = (float)L.offset[j][0]; o[4 + 2 * j] = (float)L.offset[j][1]; o[23 + j] = L.variance[j]; o[33 + j] = L.prob_foreground[j]; }
+    }
+  }
+  return n;
 }
 
 int crf_model_info(const crf_model* m, crf_model_info_t* info) {
@@ -817,12 +939,20 @@ void crf_ctx_destroy(crf_ctx* c) {
 }
 
 int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf_ctx** out) {
-  if (!m || !out) return fail(CRF_ERR_ARG, "null argument");
+  if (!out) return fail(CRF_ERR_ARG, "null argument");
   *out = nullptr;
+  // m == NULL: a context without forests, for the stages that need none (feature channels, evalTest, MeanShift) —
+  // ImageSample and MeanShift of the reference interface exist independently of any forest
+  static const crf_model no_forests = [] { crf_model e; e.m.features = {0, 1, 2}; e.m.num_channels = 38; return e; }();
+  if (!m) m = &no_forests;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(CRF_ERR_CUDA, "no CUDA device: this library has no CPU fallback"); }
   if (device < 0 || device >= ndev) return fail(CRF_ERR_ARG, "device index out of range");
-  if (m->m.jungle.size() != CRF_NUM_POSE_FORESTS) return fail(CRF_ERR_UNSUPPORTED, "the facial-feature jungle must hold 5 pose forests (src/FaceForest.cpp:216-222)");
+  // analyzeFace needs the head-pose forest and exactly 5 pose forests (poseT hard-codes 5 bins, src/FaceForest.cpp:216-222); a model
+  // with one of the two (Forest<S>::load on its own) still gets a context for the Forest / ImageSample level of the interface
+  const bool full = !m->m.hp.trees.empty() && m->m.jungle.size() == CRF_NUM_POSE_FORESTS;
+  if (!m->m.hp.trees.empty() && !m->m.jungle.empty() && m->m.jungle.size() != CRF_NUM_POSE_FORESTS)
+    return fail(CRF_ERR_UNSUPPORTED, "the facial-feature jungle must hold 5 pose forests (src/FaceForest.cpp:216-222)");
   CU(cudaSetDevice(device));
   crf_ctx* c = new crf_ctx();
   struct Guard { crf_ctx* c; ~Guard() { if (c) crf_ctx_destroy(c); } } guard{c};
@@ -834,6 +964,10 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if (const char* v = std::getenv("CRF_WIN_HP")) c->win_hp = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_WIN_FFD")) c->win_ffd = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_MS_VARIANT")) c->ms_variant = (int)std::strtol(v, nullptr, 0);
+  c->ms_mode = c->opt.ms_mode == CRF_MS_EXACT ? CRF_MS_EXACT : CRF_MS_FAST;
+  if (c->opt.ms_mode == CRF_MS_DEFAULT)
+    if (const char* v = std::getenv("CRF_MS_MODE")) c->ms_mode = std::strcmp(v, "exact") == 0 ? CRF_MS_EXACT : CRF_MS_FAST;
+  if (c->opt.ms_mode < CRF_MS_DEFAULT || c->opt.ms_mode > CRF_MS_FAST) return fail(CRF_ERR_ARG, "ms_mode must be CRF_MS_DEFAULT, CRF_MS_EXACT or CRF_MS_FAST");
   if (const char* v = std::getenv("CRF_STREAMS")) c->nstreams = std::strtol(v, nullptr, 0) == 2 ? 2 : 1;
   for (auto& w : c->ws) CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -845,16 +979,18 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   po.hp_min_foreground = c->opt.hp_min_foreground; po.ffd_min_samples = c->opt.ffd_min_samples; po.ffd_min_foreground = c->opt.ffd_min_foreground;
   po.ffd_min_pf = c->opt.ffd_min_pf; po.ffd_max_variance = c->opt.ffd_max_variance;
   std::string err;
-  int rc = pack_forests({&m->m.hp}, KIND_HEADPOSE, po, c->hp, err);
-  if (rc) return fail(rc, err);
+  int rc = CRF_OK;
+  if (!m->m.hp.trees.empty() && (rc = pack_forests({&m->m.hp}, KIND_HEADPOSE, po, c->hp, err))) return fail(rc, err);
   std::vector<const FlatForest*> jf;
   for (auto& f : m->m.jungle) jf.push_back(&f);
-  rc = pack_forests(jf, KIND_MULTIPART, po, c->mp, err);
-  if (rc) return fail(rc, err);
+  if (!jf.empty() && (rc = pack_forests(jf, KIND_MULTIPART, po, c->mp, err))) return fail(rc, err);
   c->hp_ntrees = (int)c->hp.roots.size();
-  c->mp_ntrees_cfg = m->m.mp_ntrees_cfg;
+  c->mp_ntrees_cfg = std::max(m->m.mp_ntrees_cfg, 1);
   c->num_channels = m->m.num_channels;
-  if (c->hp_ntrees > kMaxList || c->mp_ntrees_cfg > kMaxList || c->mp_ntrees_cfg < 1) return fail(CRF_ERR_UNSUPPORTED, "forest size outside 1..128 trees");
+  c->full_model = full;
+  c->layout = layout_of(std::vector<int>(m->m.features.begin(), m->m.features.end()));
+  if (c->layout.nplanes != c->num_channels) return fail(CRF_ERR_STATE, "feature list and plane count disagree");
+  if (c->hp_ntrees > kMaxList || c->mp_ntrees_cfg > kMaxList) return fail(CRF_ERR_UNSUPPORTED, "forest size outside 1..128 trees");
   if ((rc = upload(c->d_hp_slots16, c->hp.slots16, c->w->stream)) || (rc = upload(c->d_mp_slots16, c->mp.slots16, c->w->stream))) return rc;
   if ((rc = upload(c->d_hp_slotsw, c->hp.slotsw, c->w->stream)) || (rc = upload(c->d_mp_slotsw, c->mp.slotsw, c->w->stream))) return rc;
   CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -872,6 +1008,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
     void* ptrs[4] = {c->d_hp_slotsw.p, c->d_mp_slotsw.p, c->d_hp_slots.p, c->d_mp_slots.p};
     const size_t counts[4] = {c->hp.slotsw.size(), c->mp.slotsw.size(), c->hp.slots.size(), c->mp.slots.size()};
     cudaTextureObject_t* objs[4] = {&c->tex_hp, &c->tex_mp, &c->tex_hp_wide, &c->tex_mp_wide};
+    if (counts[k] == 0) continue;   // a partial model has no records of the other kind
     rd.res.linear.devPtr = ptrs[k];
     rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
     rd.res.linear.sizeInBytes = counts[k] * 32;
@@ -892,7 +1029,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
     if ((rc = upload(c->d_xs, xs, c->w->stream))) return rc;
     c->ct.xs = c->d_xs.as<double>();
     c->ct.jungle_roots = c->d_mp_roots.as<int32_t>();
-    for (int i = 0; i < 5; i++) { c->ct.forest_base[i] = c->mp.forest_base[i]; c->ct.forest_ntrees[i] = c->mp.forest_ntrees[i]; }
+    for (int i = 0; i < 5 && i < (int)c->mp.forest_base.size(); i++) { c->ct.forest_base[i] = c->mp.forest_base[i]; c->ct.forest_ntrees[i] = c->mp.forest_ntrees[i]; }
     c->ct.ntrees_cfg = c->mp_ntrees_cfg;
     c->ct.list_cap = c->mp_ntrees_cfg;
   }
@@ -1008,6 +1145,7 @@ int crf_headpose_crops(crf_ctx* c, const uint8_t* bgr_batch, int n, int rows, in
 
 int crf_analyze_crops_device(crf_ctx* c, const uint8_t* d_bgr_batch, int n, int rows, int cols, crf_face_t* d_out, int headpose_only) {
   if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!c->full_model) return fail(CRF_ERR_STATE, "analyzeFace needs the head-pose forest and the 5 pose forests; this context holds a single forest");
   if (n < 0 || (n > 0 && (!d_bgr_batch || !d_out))) return fail(CRF_ERR_ARG, "null argument");
   if (n == 0) return CRF_OK;
   CU(cudaSetDevice(c->device));
@@ -1026,7 +1164,7 @@ int crf_analyze_crops_device(crf_ctx* c, const uint8_t* d_bgr_batch, int n, int 
   CU(cudaMemcpyAsync(c->d_fd.p, descs.data(), (size_t)n * sizeof(FaceDesc), cudaMemcpyHostToDevice, s0));
   CU(cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(crf_face_t), s0));
   const int chunk = pick_chunk(c, Hmax, headpose_only != 0);
-  Plan p; p.n = std::min(n, chunk); p.Hmax = Hmax; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
+  Plan p; p.n = std::min(n, chunk); p.Hmax = Hmax; p.nplanes = c->layout.nplanes; p.need_gabor = c->layout.gabor_first >= 0; p.hp_stride = c->opt.hp_stride; p.ffd_stride = c->opt.ffd_stride; p.tree_cap = c->mp_ntrees_cfg;
   p.need_ffd = !headpose_only;
   const int nsets = n > chunk ? c->nstreams : 1;
   for (int k = 0; k < nsets; k++) { c->w = &c->ws[k]; if ((rc = ensure(c, p))) return rc; }
@@ -1102,45 +1240,33 @@ static int stage_download_planes(crf_ctx* c, int nplanes, int W, int H, uint8_t*
   return CRF_OK;
 }
 
-int crf_stage_channels(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals) {
+// ImageSample::extractFeatureChannels for an explicit feature list (src/ImageSample.cpp:77-90): the ids are sorted, then each
+// appends its planes (include/FeatureChannelFactory.hpp:35-183).  Returns the plane count (> 0) or a negative status.
+int crf_stage_feature_channels(crf_ctx* c, const uint8_t* scaled, int W, int H, const int* features, int nfeatures, uint8_t* planes_u8, uint32_t* integrals) {
   if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
-  if (!scaled) return fail(CRF_ERR_ARG, "null argument");
+  if (!scaled || !features || nfeatures < 1 || nfeatures > 6) return fail(CRF_ERR_ARG, "bad argument");
+  std::vector<int> f(features, features + nfeatures);
+  std::sort(f.begin(), f.end());
+  for (size_t i = 0; i < f.size(); i++)
+    if (planes_of_feature(f[i]) == 0 || (i > 0 && f[i] == f[i - 1])) return fail(CRF_ERR_ARG, "feature ids must be distinct values of 0..5");
+  const ChannelLayout L = layout_of(f);
   CU(cudaSetDevice(c->device));
-  int rc = stage_upload_scaled(c, scaled, W, H, 38, true, true, false, false, 1, 4, 3);
+  int rc = stage_upload_scaled(c, scaled, W, H, L.nplanes, L.gabor_first >= 0, true, false, false, 1, 4, 3);
   if (rc) return rc;
-  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, 0, true))) return rc;
-  return stage_download_planes(c, 38, W, H, planes_u8, integrals);
+  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, L, true))) return rc;
+  if ((rc = stage_download_planes(c, L.nplanes, W, H, planes_u8, integrals))) return rc;
+  return L.nplanes;
 }
 
-int crf_stage_minmax(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals) {
-  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
-  if (!scaled) return fail(CRF_ERR_ARG, "null argument");
-  CU(cudaSetDevice(c->device));
-  int rc = stage_upload_scaled(c, scaled, W, H, 38, false, true, false, false, 1, 4, 3);
-  if (rc) return rc;
-  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, 1, true))) return rc;
-  return stage_download_planes(c, 2, W, H, planes_u8, integrals);
+static int stage_fixed_features(crf_ctx* c, const uint8_t* scaled, int W, int H, std::initializer_list<int> feats, uint8_t* planes_u8, uint32_t* integrals) {
+  const std::vector<int> f(feats);
+  const int rc = crf_stage_feature_channels(c, scaled, W, H, f.data(), (int)f.size(), planes_u8, integrals);
+  return rc < 0 ? rc : CRF_OK;
 }
-
-int crf_stage_norm(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* plane_u8, uint32_t* integral) {
-  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
-  if (!scaled) return fail(CRF_ERR_ARG, "null argument");
-  CU(cudaSetDevice(c->device));
-  int rc = stage_upload_scaled(c, scaled, W, H, 38, false, true, false, false, 1, 4, 3);
-  if (rc) return rc;
-  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, 2, true))) return rc;
-  return stage_download_planes(c, 1, W, H, plane_u8, integral);
-}
-
-int crf_stage_canny(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* plane_u8, uint32_t* integral) {
-  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
-  if (!scaled) return fail(CRF_ERR_ARG, "null argument");
-  CU(cudaSetDevice(c->device));
-  int rc = stage_upload_scaled(c, scaled, W, H, 38, false, true, false, false, 1, 4, 3);
-  if (rc) return rc;
-  if ((rc = launch_channels(c, c->d_fd.as<FaceDesc>(), 1, H, 3, true))) return rc;
-  return stage_download_planes(c, 1, W, H, plane_u8, integral);
-}
+int crf_stage_channels(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals) { return stage_fixed_features(c, scaled, W, H, {0, 1, 2}, planes_u8, integrals); }
+int crf_stage_minmax(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals) { return stage_fixed_features(c, scaled, W, H, {3}, planes_u8, integrals); }
+int crf_stage_norm(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* plane_u8, uint32_t* integral) { return stage_fixed_features(c, scaled, W, H, {5}, plane_u8, integral); }
+int crf_stage_canny(crf_ctx* c, const uint8_t* scaled, int W, int H, uint8_t* plane_u8, uint32_t* integral) { return stage_fixed_features(c, scaled, W, H, {4}, plane_u8, integral); }
 
 // planes -> integral stack of one synthetic face
 static int stage_planes_to_stack(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int H, bool hp, bool ffd, int tree_cap, int hp_stride, int ffd_stride) {
@@ -1164,7 +1290,7 @@ static int stage_set_list(crf_ctx* c, const int* tree_forest, const int* tree_in
   if (!tree_forest || !tree_index || ntrees < 0 || ntrees > kMaxList) return fail(CRF_ERR_ARG, "bad composed forest");
   std::vector<int32_t> list((size_t)kMaxList, 0);
   for (int i = 0; i < ntrees; i++) {
-    if (tree_forest[i] < 0 || tree_forest[i] >= CRF_NUM_POSE_FORESTS || tree_index[i] < 0 || tree_index[i] >= c->mp.forest_ntrees[tree_forest[i]])
+    if (tree_forest[i] < 0 || tree_forest[i] >= (int)c->mp.forest_ntrees.size() || tree_index[i] < 0 || tree_index[i] >= c->mp.forest_ntrees[tree_forest[i]])
       return fail(CRF_ERR_ARG, "bad composed forest");
     list[i] = c->mp.roots[c->mp.forest_base[tree_forest[i]] + tree_index[i]];
   }
@@ -1181,6 +1307,7 @@ int crf_stage_eval_forest(crf_ctx* c, int which, const int* tree_forest, const i
   CU(cudaSetDevice(c->device));
   const bool hp = which < 0;
   const PackedForest& pf = hp ? c->hp : c->mp;
+  if (pf.slots.empty()) return fail(CRF_ERR_STATE, "the context's model does not hold that forest");
   if (max_channel_used(pf) >= C) return fail(CRF_ERR_ARG, "forest reads a channel the planes do not provide");
   const int nt = hp ? c->hp_ntrees : ntrees;
   int rc = stage_planes_to_stack(c, planes_u8, C, W, H, hp, !hp, std::max(nt, 1), stride, stride);
@@ -1196,12 +1323,77 @@ int crf_stage_eval_forest(crf_ctx* c, int which, const int* tree_forest, const i
   return pull_counters(c);
 }
 
+// Forest<S>::evaluateMT for explicit patch origins (the per-sample level: one call of the reference per patch).
+// patch_xy: npatches x (x, y); leaf_ids: [patch][tree] Boost object ids.
+int crf_stage_eval_patches(crf_ctx* c, int which, const int* tree_forest, const int* tree_index, int ntrees, const uint8_t* planes_u8, int C, int W, int H,
+                           const int* patch_xy, int npatches, int32_t* leaf_ids) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!leaf_ids || !patch_xy || npatches < 0) return fail(CRF_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  const bool hp = which < 0;
+  const PackedForest& pf = hp ? c->hp : c->mp;
+  if (pf.slots.empty()) return fail(CRF_ERR_STATE, "the context's model does not hold that forest");
+  if (max_channel_used(pf) >= C) return fail(CRF_ERR_ARG, "forest reads a channel the planes do not provide");
+  for (int i = 0; i < npatches; i++)
+    if (patch_xy[2 * i] < 0 || patch_xy[2 * i + 1] < 0 || patch_xy[2 * i] + kPatch > W || patch_xy[2 * i + 1] + kPatch > H) return fail(CRF_ERR_ARG, "patch outside the face");
+  const int nt = hp ? c->hp_ntrees : ntrees;
+  if (npatches == 0 || nt == 0) return CRF_OK;
+  int rc = stage_planes_to_stack(c, planes_u8, C, W, H, false, false, std::max(nt, 1), 1, 1);
+  if (rc) return rc;
+  if (!hp && (rc = stage_set_list(c, tree_forest, tree_index, ntrees))) return rc;
+  Buf d_p, d_leaf;
+  struct Free { Buf* b[2]; ~Free() { for (Buf* x : b) x->release(); } } fr{{&d_p, &d_leaf}};
+  if ((rc = d_p.reserve((size_t)npatches * 8)) || (rc = d_leaf.reserve((size_t)npatches * nt * 4))) return rc;
+  CU(cudaMemcpyAsync(d_p.p, patch_xy, (size_t)npatches * 8, cudaMemcpyHostToDevice, c->w->stream));
+  TraverseArgs a{};
+  a.stacks = c->w->d_stacks.as<stack_t>(); a.stack_face_stride = c->w->stack_fs; a.plane_stride = c->w->plane_stride;
+  a.slots = hp ? c->d_hp_slots.as<DevSlot>() : c->d_mp_slots.as<DevSlot>();
+  if (hp) { a.roots = c->d_hp_roots.as<int32_t>(); a.ntrees = c->hp_ntrees; }
+  else { a.face_roots = c->w->d_face_roots.as<int32_t>(); a.face_ntrees = c->w->d_face_ntrees.as<int32_t>(); }
+  a.leaf_out = d_leaf.as<int32_t>();
+  k_traverse_patches<<<(npatches * nt + 127) / 128, 128, 0, c->w->stream>>>(a, d_p.as<int2>(), npatches);
+  KCHECK(); count_launch(c, hp ? CRF_STAGE_HP_TRAVERSE : CRF_STAGE_FFD_TRAVERSE);
+  std::vector<int32_t> raw((size_t)npatches * nt);
+  CU(cudaMemcpyAsync(raw.data(), d_leaf.p, raw.size() * 4, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
+  for (size_t i = 0; i < raw.size(); i++) leaf_ids[i] = pf.leaf_oid[(size_t)raw[i]];
+  return CRF_OK;
+}
+
+// ImageSample::evalTest(SimplePatchFeature, Rect) (src/ImageSample.cpp:30-64) for n tests on caller-supplied planes:
+// tests = n x {channel, x1, y1, w1, h1, x2, y2, w2, h2, patch_x, patch_y}; out[i] = mean(rect1) - mean(rect2).
+int crf_stage_eval_tests(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int H, const int* tests, int n, int* out) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (n < 0 || (n > 0 && (!tests || !out))) return fail(CRF_ERR_ARG, "bad argument");
+  if (n == 0) return CRF_OK;
+  for (int i = 0; i < n; i++) {
+    const int* t = tests + (size_t)i * 11;
+    if (t[0] < 0 || t[0] >= C) return fail(CRF_ERR_ARG, "test reads a channel the planes do not provide");
+    for (int k = 0; k < 2; k++) {
+      const int x = t[9] + t[1 + 4 * k], y = t[10] + t[2 + 4 * k], w = t[3 + 4 * k], h = t[4 + 4 * k];
+      if (w < 1 || h < 1 || x < 0 || y < 0 || x + w > W || y + h > H) return fail(CRF_ERR_ARG, "test rectangle outside the face");
+    }
+  }
+  CU(cudaSetDevice(c->device));
+  int rc = stage_planes_to_stack(c, planes_u8, C, W, H, false, false, 1, 1, 1);
+  if (rc) return rc;
+  Buf d_t, d_o;
+  struct Free { Buf* b[2]; ~Free() { for (Buf* x : b) x->release(); } } fr{{&d_t, &d_o}};
+  if ((rc = d_t.reserve((size_t)n * 44)) || (rc = d_o.reserve((size_t)n * 4))) return rc;
+  CU(cudaMemcpyAsync(d_t.p, tests, (size_t)n * 44, cudaMemcpyHostToDevice, c->w->stream));
+  k_eval_tests<<<(n + 127) / 128, 128, 0, c->w->stream>>>(c->w->d_stacks.as<stack_t>(), c->w->plane_stride, d_t.as<int>(), n, d_o.as<int>());
+  KCHECK(); count_launch(c, CRF_STAGE_PLAIN);
+  CU(cudaMemcpyAsync(out, d_o.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
+  return CRF_OK;
+}
+
 static void fill_list_out(crf_ctx* c, const std::vector<int32_t>& list, int n, int* tree_forest, int* tree_index) {
   for (int i = 0; i < n; i++) {
     const auto it = std::upper_bound(c->mp.roots.begin(), c->mp.roots.end(), list[i]);  // roots ascend with the tree number
     const int t = (int)(it - c->mp.roots.begin()) - 1;
     int f = 0;
-    while (f + 1 < CRF_NUM_POSE_FORESTS && c->mp.forest_base[f + 1] <= t) f++;
+    while (f + 1 < (int)c->mp.forest_base.size() && c->mp.forest_base[f + 1] <= t) f++;
     if (tree_forest) tree_forest[i] = f;
     if (tree_index) tree_index[i] = t - c->mp.forest_base[f];
   }
@@ -1230,13 +1422,16 @@ int crf_stage_headpose(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int H
   if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
   if (stride < 1) return fail(CRF_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
+  if (c->hp.slots.empty()) return fail(CRF_ERR_STATE, "the context's model does not hold the head-pose forest");
   if (max_channel_used(c->hp) >= C) return fail(CRF_ERR_ARG, "forest reads a channel the planes do not provide");
   int rc = stage_planes_to_stack(c, planes_u8, C, W, H, true, false, 1, stride, stride);
   if (rc) return rc;
   if ((rc = c->d_faces.reserve(sizeof(crf_face_t)))) return rc;
   CU(cudaMemsetAsync(c->d_faces.p, 0, sizeof(crf_face_t), c->w->stream));
   if ((rc = launch_traverse(c, c->d_fd.as<FaceDesc>(), 1, H, true, stride, c->d_hp_roots.as<int32_t>(), c->hp_ntrees, c->hp_ntrees, true))) return rc;
-  if ((rc = launch_hp_reduce(c, c->d_fd.as<FaceDesc>(), 1, stride, true, kMaxList, c->d_faces.as<crf_face_t>()))) return rc;
+  // the composition needs the 5 pose forests; a head-pose-only model (Forest<HeadPoseSample>::load on its own) gets mean and variance
+  if ((rc = launch_hp_reduce(c, c->d_fd.as<FaceDesc>(), 1, stride, c->full_model, kMaxList, c->d_faces.as<crf_face_t>()))) return rc;
+  if (!c->full_model) CU(cudaMemsetAsync(c->w->d_face_ntrees.p, 0, 4, c->w->stream));
   rc = stage_fetch_compose(c, headpose, variance, tree_counts, dominant, tree_forest, tree_index, ntrees, flags);
   c->timer.collect();
   return rc ? rc : pull_counters(c);
@@ -1245,6 +1440,7 @@ int crf_stage_headpose(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int H
 int crf_stage_compose(crf_ctx* c, float headpose, float variance, int tree_counts[CRF_NUM_POSE_FORESTS], int* dominant, int* tree_forest, int* tree_index,
                       int* ntrees, int* flags) {
   if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!c->full_model) return fail(CRF_ERR_STATE, "the forest composition needs the 5 pose forests");
   CU(cudaSetDevice(c->device));
   int rc;
   if ((rc = c->d_faces.reserve(sizeof(crf_face_t))) || (rc = c->w->d_face_roots.reserve(kMaxList * 4)) || (rc = c->w->d_face_ntrees.reserve(4))) return rc;
@@ -1256,12 +1452,60 @@ int crf_stage_compose(crf_ctx* c, float headpose, float variance, int tree_count
   return stage_fetch_compose(c, nullptr, nullptr, tree_counts, dominant, tree_forest, tree_index, ntrees, flags);
 }
 
+int crf_stage_compose_batch(crf_ctx* c, const float* headpose, const float* variance, int n, int* tree_counts, int* dominant, int* ntrees, int* flags,
+                            int* tree_forest, int* tree_index, int list_cap) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (n < 0 || (n > 0 && (!headpose || !variance)) || list_cap < 0 || list_cap > kMaxList) return fail(CRF_ERR_ARG, "bad argument");
+  if (!c->full_model) return fail(CRF_ERR_STATE, "the forest composition needs the 5 pose forests");
+  if (n == 0) return CRF_OK;
+  CU(cudaSetDevice(c->device));
+  int rc;
+  Buf d_in, d_lists, d_nt, d_faces;
+  struct Free { Buf* b[4]; ~Free() { for (Buf* x : b) x->release(); } } fr{{&d_in, &d_lists, &d_nt, &d_faces}};
+  if ((rc = d_in.reserve((size_t)n * 8)) || (rc = d_lists.reserve((size_t)n * kMaxList * 4)) || (rc = d_nt.reserve((size_t)n * 4)) ||
+      (rc = d_faces.reserve((size_t)n * sizeof(crf_face_t))))
+    return rc;
+  cudaStream_t s = c->w->stream;
+  CU(cudaMemcpyAsync(d_in.p, headpose, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_in.as<float>() + n, variance, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(d_faces.p, 0, (size_t)n * sizeof(crf_face_t), s));
+  ComposeTables ct = c->ct;
+  ct.list_cap = kMaxList;
+  k_compose_batch<<<(n + 8) / 9, 288, 0, s>>>(d_in.as<float>(), d_in.as<float>() + n, n, ct, d_faces.as<crf_face_t>(), d_lists.as<int32_t>(), d_nt.as<int32_t>());
+  KCHECK(); count_launch(c, CRF_STAGE_HP_REDUCE);
+  std::vector<crf_face_t> faces((size_t)n);
+  std::vector<int32_t> lists((size_t)n * kMaxList), nt((size_t)n);
+  CU(cudaMemcpyAsync(faces.data(), d_faces.p, (size_t)n * sizeof(crf_face_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(lists.data(), d_lists.p, (size_t)n * kMaxList * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(nt.data(), d_nt.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  std::vector<int32_t> one((size_t)kMaxList);
+  std::vector<int> tf((size_t)kMaxList), ti((size_t)kMaxList);
+  for (int i = 0; i < n; i++) {
+    if (tree_counts) std::memcpy(tree_counts + (size_t)i * CRF_NUM_POSE_FORESTS, faces[(size_t)i].tree_counts, sizeof(int) * CRF_NUM_POSE_FORESTS);
+    if (dominant) dominant[i] = faces[(size_t)i].dominant;
+    if (flags) flags[i] = faces[(size_t)i].flags & 1;
+    if (ntrees) ntrees[i] = nt[(size_t)i];
+    if (list_cap > 0 && (tree_forest || tree_index)) {
+      const int m = std::min(nt[(size_t)i], list_cap);
+      std::copy(lists.begin() + (size_t)i * kMaxList, lists.begin() + (size_t)i * kMaxList + m, one.begin());
+      fill_list_out(c, one, m, tf.data(), ti.data());
+      for (int k = 0; k < list_cap; k++) {
+        if (tree_forest) tree_forest[(size_t)i * list_cap + k] = k < m ? tf[(size_t)k] : -1;
+        if (tree_index) tree_index[(size_t)i * list_cap + k] = k < m ? ti[(size_t)k] : -1;
+      }
+    }
+  }
+  return CRF_OK;
+}
+
 int crf_stage_votes_meanshift(crf_ctx* c, const int* tree_forest, const int* tree_index, int ntrees, const uint8_t* planes_u8, int C, int W, int H, int stride,
                               int n_votes[CRF_NUM_PARTS], float* votes_xyw, int vote_cap, float mean_xy[CRF_NUM_PARTS][2], int rounded_xy[CRF_NUM_PARTS][2],
                               int iters[CRF_NUM_PARTS]) {
   if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
   if (stride < 1) return fail(CRF_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
+  if (c->mp.slots.empty()) return fail(CRF_ERR_STATE, "the context's model does not hold a facial-feature forest");
   if (max_channel_used(c->mp) >= C) return fail(CRF_ERR_ARG, "forest reads a channel the planes do not provide");
   int rc = stage_planes_to_stack(c, planes_u8, C, W, H, false, true, std::max(ntrees, 1), stride, stride);
   if (rc) return rc;

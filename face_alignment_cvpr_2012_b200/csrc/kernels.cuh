@@ -120,8 +120,9 @@ __device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, stack_t*
 
 // a5 + a7 (+ a7b): FC_GRAY, FC_SOBEL (d/dy then d/dx, 8U-saturated), FC_MIN_MAX
 // (include/FeatureChannelFactory.hpp:46-57, :120-165).  grid = (nwhich, faces), 128 threads.
-// which: 0 gray, 1 Sobel dy, 2 Sobel dx, 3 erode, 4 dilate, 5 equalizeHist (FC_NORM, :58-70).  plane_of[which] = output plane index.
-struct PlainPlanes { int which[5]; int plane[5]; };
+// which: 0 gray, 1 Sobel dy, 2 Sobel dx, 3 erode, 4 dilate, 5 equalizeHist (FC_NORM, :58-70), 6 Canny (FC_CANNY, :166-179).
+// plane[k] = output plane index of entry k.
+struct PlainPlanes { int which[8]; int plane[8]; };
 
 __global__ void __launch_bounds__(128) k_plain_channels(const FaceDesc* __restrict__ fd, const uint8_t* __restrict__ scaled, size_t scaled_face_stride,
                                                         stack_t* __restrict__ stacks, size_t stack_face_stride, size_t plane_stride,
@@ -695,6 +696,47 @@ __global__ void __launch_bounds__(NW * 32) k_traverse(TraverseArgs a) {
   }
 }
 
+// Forest<S>::evaluateMT for an explicit list of patch origins (the per-sample level of the reference interface:
+// include/Forest.hpp:81-90 is called once per patch).  One thread per (patch, tree), global gathers on the wide records.
+// patches: (x, y) of the patch's top-left corner in the scaled face; leaf_out: [patch][tree].
+__global__ void __launch_bounds__(128) k_traverse_patches(TraverseArgs a, const int2* __restrict__ patches, int npatches) {
+  const int nt = a.face_ntrees ? a.face_ntrees[0] : a.ntrees;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npatches * nt) return;
+  const int p = idx / nt, t = idx - p * nt;
+  const int32_t* roots = a.face_roots ? a.face_roots : a.roots;
+  const stack_t* __restrict__ origin = a.stacks + (size_t)patches[p].y * kRowStride + patches[p].x;
+  int cur = roots[t];
+  for (;;) {
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(a.slots + cur)), q1 = __ldg(reinterpret_cast<const uint4*>(a.slots + cur) + 1);
+    if ((q1.x >> 8) & 0xff) { a.leaf_out[idx] = (int)q1.w; return; }
+    const stack_t* __restrict__ pl = origin + (size_t)(q1.x & 0xff) * a.plane_stride;
+    const uint32_t a1 = q0.x & 0xffff, w1 = (q0.x >> 16) & 0xff, a2 = q0.z & 0xffff, w2 = (q0.z >> 16) & 0xff;
+    const uint32_t s1 = rect_sum_strips<false>(pl, a1, w1, q0.x >> 24, q0.y & 0xffff, q0.y >> 16);
+    const uint32_t s2 = rect_sum_strips<false>(pl, a2, w2, q0.z >> 24, q0.w & 0xffff, q0.w >> 16);
+    const int m1 = (int)__umulhi(s1 << 1, q1.y), m2 = (int)__umulhi(s2 << 1, q1.z);
+    cur = (int)q1.w + ((m1 - m2) > (int)(short)(q1.x >> 16) ? 1 : 0);   // go left iff mean1 - mean2 <= threshold
+  }
+}
+
+// ImageSample::evalTest(SimplePatchFeature, Rect) (src/ImageSample.cpp:30-64) for a list of tests on one face's integral stack:
+// tests[i] = {channel, x1, y1, w1, h1, x2, y2, w2, h2, patch_x, patch_y}; out[i] = mean(rect1) - mean(rect2) with the
+// reference's truncating means.
+__global__ void k_eval_tests(const stack_t* __restrict__ stack, size_t plane_stride, const int* __restrict__ tests, int n, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int* t = tests + (size_t)i * 11;
+  const stack_t* __restrict__ pl = stack + (size_t)t[0] * plane_stride;
+  int mean[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int x = t[9] + t[1 + 4 * k], y = t[10] + t[2 + 4 * k], w = t[3 + 4 * k], h = t[4 + 4 * k];
+    const uint32_t A = pl[(size_t)y * kRowStride + x], B = pl[(size_t)y * kRowStride + x + w], C = pl[(size_t)(y + h) * kRowStride + x], D = pl[(size_t)(y + h) * kRowStride + x + w];
+    mean[k] = (int)((D - B - C + A) / (uint32_t)(w * h));   // == (int)(sum / float(w * h)) of the reference for sums < 2^24
+  }
+  out[i] = mean[0] - mean[1];
+}
+
 // Exact floor(s / area) for s <= 255 * area < 2^18 without a stored reciprocal: float estimate, then a +-1 fix-up.
 __device__ __forceinline__ int mean_exact(uint32_t s, uint32_t area) {
   int q = (int)(__uint2float_rn(s) * __frcp_rn(__uint2float_rn(area)));
@@ -809,9 +851,15 @@ __device__ __forceinline__ int win_step(uint32_t col, uint32_t row, const uint4 
   return (int)q1.z + ((m1 - m2) > thr ? 1 : 0);   // go left iff mean1 - mean2 <= threshold
 }
 
-template <int NW, int WALKS, bool COUNT, bool TEX = false>
+// PAIRX (two walks per lane only): the lane's two patches are HORIZONTAL neighbours instead of rows ly / ly + 4.  Neighbours one
+// pixel apart share most of their path (~12 of ~15 nodes), so the second walk's record fetch is skipped while both sit
+// on the same node (the record is copied between registers): fewer requests on the texture pipe and to L2.  Lane (i = lane & 3,
+// y = lane >> 2) takes patches (2i + s, y) and (2i + 1 - s, y), s = y >= 4: with the 40-word row pitch (== 8 mod 32) each walk's 32
+// lanes then still fall into 32 different banks when the warp is converged.
+template <int NW, int WALKS, bool COUNT, bool TEX = false, bool PAIRX = false>
 __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int nitems, int ncols, int nplanes) {
   static_assert(WALKS == 1 || WALKS == 2, "one or two walks per lane");
+  static_assert(!PAIRX || WALKS == 2, "PAIRX pairs the two walks of a lane");
   // record fetch: 256-bit global load, or (TEX, the default) two 128-bit texel fetches that return through the texture pipe and
   // leave the LSU data pipe, the kernel's limiter, to the shared-memory gathers (-5 % time; CRF_WIN_TEX=0 switches it off)
   auto fetch = [&](int slot, uint4& q0, uint4& q1) {
@@ -875,7 +923,34 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int
       }
       const int r0 = y0 % kWinRows;
       const uint32_t col = s_base + lx * 4;
-      if (WALKS == 2) {
+      if (WALKS == 2 && PAIRX) {
+        const int py = lane >> 2, sft = py >> 2, xa = 2 * (lane & 3) + sft, xb = 2 * (lane & 3) + 1 - sft;
+        int ra = r0 + py;
+        ra -= ra >= kWinRows ? kWinRows : 0;
+        const uint32_t rowA = ra * kWinRowBytes;
+        const uint32_t colA = s_base + xa * 4, colB = s_base + xb * 4;
+        const bool vy = y0 + py < ny, vA = vy && x0 + xa < nx, vB = vy && x0 + xb < nx;
+        for (int t = warp; t < nt; t += NW) {
+          uint4 a0, a1, b0, b1;
+          fetch(roots[t], a0, a1);
+          b0 = a0; b1 = a1;
+          for (;;) {
+            const bool la = (int)a1.w < 0, lb = (int)b1.w < 0;
+            if (la && lb) break;
+            const int ca = win_step(colA, rowA, a0, a1, la ? 0u : 1u), cb = win_step(colB, rowA, b0, b1, lb ? 0u : 1u);
+            if (COUNT) tests += (vA && !la ? 1 : 0) + (vB && !lb ? 1 : 0);
+            if (!la) fetch(ca, a0, a1);
+            if (!lb) {
+              if (!la && cb == ca) { b0 = a0; b1 = a1; }   // both walks moved to the same node: one fetch serves both
+              else fetch(cb, b0, b1);
+            }
+          }
+          int va = (int)a1.y, vb = (int)b1.y;
+          if (a.leaf_value) { va = __float_as_int(__ldg(a.leaf_value + va)); vb = __float_as_int(__ldg(a.leaf_value + vb)); }
+          if (vA) out[((size_t)(x0 + xa) * ny + (y0 + py)) * nt + t] = va;
+          if (vB) out[((size_t)(x0 + xb) * ny + (y0 + py)) * nt + t] = vb;
+        }
+      } else if (WALKS == 2) {
         int ra = r0 + ly, rb = r0 + ly + 4;
         ra -= ra >= kWinRows ? kWinRows : 0;
         rb -= rb >= kWinRows ? kWinRows : 0;
@@ -1101,6 +1176,15 @@ __global__ void __launch_bounds__(kFoldThreads) k_hp_reduce_compose(const FaceDe
 // Composition alone (stage API).
 __global__ void k_compose_only(float headpose, float variance, ComposeTables ct, crf_face_t* face, int32_t* list, int32_t* ntrees) {
   compose_face(headpose, variance, ct, threadIdx.x & 31, face, list, ntrees);
+}
+
+// Composition of many (headpose, variance) pairs (stage API: knife-edge sweeps of floor(area * ntrees)).  One warp per pair;
+// 288 threads = the 9 warps compose_face's shared scratch is sized for.
+__global__ void __launch_bounds__(288) k_compose_batch(const float* __restrict__ headpose, const float* __restrict__ variance, int n, ComposeTables ct,
+                                                       crf_face_t* __restrict__ faces, int32_t* __restrict__ lists, int32_t* __restrict__ ntrees) {
+  const int i = blockIdx.x * 9 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  compose_face(headpose[i], variance[i], ct, threadIdx.x & 31, faces + i, lists + (size_t)i * kMaxList, ntrees + i);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1428,6 +1512,91 @@ __global__ void __launch_bounds__(kFoldThreads, MINB) k_meanshift(const FaceDesc
     if (counters) {
       atomicAdd(&counters[CNT_VOTES], (unsigned long long)s_n[lane]);
       atomicAdd(&counters[CNT_VOTE_PASSES], (unsigned long long)s_n[lane] * (1 + it));
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// a14, tolerance mode (crf_options_t::ms_mode = CRF_MS_FAST, the default): the same MeanShift::shift iteration
+// (include/MeanShift.hpp:52-135) with the three sums of a pass reduced as a fixed tree instead of the reference's
+// sequential f32 fold, f32 distance and exp2-based kernel weight.  One CTA per (face, part) chain: its vote list
+// (8 B per vote) is streamed once per pass with coalesced loads and stays L2-resident between passes; per-thread
+// partial sums -> warp butterfly -> fixed-order sum over the warps, so the result is deterministic (independent of
+// scheduling) though not bit-identical to the sequential order.  The north star's landmark tolerance is 0.5 px; the
+// observed distance to the exact mode is ~1e-4 px (tests/test_gpu_reference_campaign.py).  Head pose, composition and the
+// vote lists are untouched by the mode.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_meanshift_fast(const FaceDesc* __restrict__ fd, int nchains, const DevVote* __restrict__ votes, size_t vote_cap,
+                                                          const int32_t* __restrict__ vote_counts, const int32_t* __restrict__ vote_base, MeanShiftOpt o,
+                                                          crf_face_t* __restrict__ faces, unsigned long long* counters) {
+  constexpr int NWARP = BLOCK / 32;
+  __shared__ float s_part[2][3][NWARP];
+  const int c = blockIdx.x;
+  if (c >= nchains) return;
+  const int f = c / kParts, p = c - f * kParts;
+  const int cnt = vote_counts[c];
+  if (cnt < 0) return;   // face over the vote budget: left to the wide re-run
+  const int2* __restrict__ v = reinterpret_cast<const int2*>(votes + (size_t)f * vote_cap + vote_base[c]);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float nk = -1.4426950408889634f / (float)o.kernel;   // exp(-d / lamda) = 2^(d * nk)
+  float mx = 0.f, my = 0.f;
+  int it = 0;
+  for (int pass = 0; pass <= o.max_iterations; pass++) {
+    float sw = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll 4
+    for (int k = tid; k < cnt; k += BLOCK) {
+      const int2 q = __ldg(v + k);
+      const float x = (float)(short)(q.x & 0xffff), y = (float)(q.x >> 16);
+      float w = __int_as_float(q.y);
+      if (pass > 0) {
+        const float dx = mx - x, dy = my - y;
+        w *= ex2_approx(sqrt_approx(__fmaf_rn(dx, dx, dy * dy)) * nk);
+      }
+      sw += w;
+      sx = __fmaf_rn(x, w, sx);
+      sy = __fmaf_rn(y, w, sy);
+    }
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+      sw += __shfl_xor_sync(0xffffffffu, sw, ofs);
+      sx += __shfl_xor_sync(0xffffffffu, sx, ofs);
+      sy += __shfl_xor_sync(0xffffffffu, sy, ofs);
+    }
+    float (*part)[NWARP] = s_part[pass & 1];
+    if (lane == 0) { part[0][warp] = sw; part[1][warp] = sx; part[2][warp] = sy; }
+    __syncthreads();   // double-buffered: the next pass writes the other buffer, so one barrier per pass suffices
+    sw = sx = sy = 0.f;
+#pragma unroll
+    for (int j = 0; j < NWARP; j++) { sw += part[0][j]; sx += part[1][j]; sy += part[2][j]; }   // same order in every thread
+    if (sw > 0.f) { sx /= sw; sy /= sw; }
+    if (pass == 0) {
+      mx = sx; my = sy;
+    } else {
+      const float ex = sx - mx, ey = sy - my;
+      const bool conv = sqrt((double)ex * ex + (double)ey * ey) < o.stopping;
+      mx = sx; my = sy;
+      it++;
+      if (conv) break;
+    }
+  }
+  if (tid == 0) {
+    const int rx = __float2int_rn(mx), ry = __float2int_rn(my);
+    crf_face_t* face = faces + f;
+    face->ffd_f[p][0] = mx; face->ffd_f[p][1] = my;
+    face->ffd_scaled[p][0] = rx; face->ffd_scaled[p][1] = ry;
+    const float inv = 1.0f / fd[f].scale;
+    face->ffd[p][0] = __float2int_rn(rx * inv);
+    face->ffd[p][1] = __float2int_rn(ry * inv);
+    face->ms_iters[p] = it;
+    face->n_votes[p] = cnt;
+    if (counters) {
+      atomicAdd(&counters[CNT_VOTES], (unsigned long long)cnt);
+      atomicAdd(&counters[CNT_VOTE_PASSES], (unsigned long long)cnt * (1 + it));
     }
   }
 }

@@ -292,26 +292,33 @@ int load_model_dirs(const std::string& hp_dir, int hp_ntrees, const std::string&
   return validate_model(m, err);
 }
 
-int validate_model(const Model& mc, std::string& err) {
-  Model& m = const_cast<Model&>(mc);
-  if (m.hp.trees.empty()) { err = "head-pose forest is empty"; return CRF_ERR_FORMAT; }
-  const ForestParamLite& p = m.hp.trees[0].param;
-  m.face_size = p.face_size;
-  m.patch_size = (int32_t)std::round(p.face_size * p.patch_size_ratio);  // ForestParam::getPatchSize (Constants.hpp:26-30)
-  if (m.face_size != 125 || m.patch_size != 31) { err = "only face_size 125 / patch 31 models are supported by the device layout"; return CRF_ERR_UNSUPPORTED; }
-  // features {0,1,2} -> 38 planes (src/ImageSample.cpp:77-90, FeatureChannelFactory.hpp:46-141)
+static int check_against_features(Model& m, std::string& err) {
   int planes = 0;
-  for (int i = 0; i < p.n_features; i++) planes += p.features[i] == 0 ? 1 : p.features[i] == 1 ? 35 : p.features[i] == 2 ? 2 : p.features[i] == 3 ? 2 : 1;
+  for (size_t i = 0; i < m.features.size(); i++) {
+    const int np = planes_of_feature(m.features[i]);
+    if (np == 0) { err = "unknown feature channel id " + std::to_string(m.features[i]) + " (include/FeatureChannelFactory.hpp:18-23 defines 0..5)"; return CRF_ERR_UNSUPPORTED; }
+    if (i > 0 && m.features[i] == m.features[i - 1]) { err = "feature channel id listed twice"; return CRF_ERR_UNSUPPORTED; }
+    planes += np;
+  }
+  if (planes < 1 || planes > 64) { err = "feature list gives " + std::to_string(planes) + " planes (1..64 supported)"; return CRF_ERR_UNSUPPORTED; }
   m.num_channels = planes;
   auto check_forest = [&](const FlatForest& f, const char* what) -> bool {
     for (const FlatTree& t : f.trees) {
       if (t.param.face_size != m.face_size || (int32_t)std::round(t.param.face_size * t.param.patch_size_ratio) != m.patch_size) {
         err = std::string(what) + ": trees disagree on face/patch size"; return false;
       }
+      if ((f.kind == KIND_HEADPOSE && !t.mp_leaves.empty()) || (f.kind == KIND_MULTIPART && !t.hp_leaves.empty())) {
+        err = std::string(what) + ": leaf records of the wrong kind"; return false;
+      }
       for (const FlatNode& n : t.nodes) {
         if (n.leaf >= 0) continue;
         if (n.r1[0] + n.r1[2] >= m.patch_size || n.r1[1] + n.r1[3] >= m.patch_size || n.r2[0] + n.r2[2] >= m.patch_size ||
             n.r2[1] + n.r2[3] >= m.patch_size) { err = std::string(what) + ": split rectangle leaves the patch"; return false; }
+        // the reference would index m_feature_channels out of bounds (src/ImageSample.cpp:38); here it would read another face's planes
+        if ((int)n.channel >= planes) {
+          err = std::string(what) + ": a split reads feature channel " + std::to_string((int)n.channel) + " but the feature list provides only " + std::to_string(planes) + " planes";
+          return false;
+        }
       }
     }
     return true;
@@ -320,6 +327,34 @@ int validate_model(const Model& mc, std::string& err) {
   for (auto& f : m.jungle)
     if (!check_forest(f, "facial-feature forest")) return CRF_ERR_UNSUPPORTED;
   return CRF_OK;
+}
+
+int validate_model(const Model& mc, std::string& err) {
+  Model& m = const_cast<Model&>(mc);
+  // a model may hold the head-pose forest only, or facial-feature forests only (Forest<S>::load on its own); what a call needs is
+  // checked where it is made
+  const FlatTree* first = !m.hp.trees.empty() ? &m.hp.trees[0] : nullptr;
+  for (auto& f : m.jungle) if (!first && !f.trees.empty()) first = &f.trees[0];
+  if (!first) { err = "model holds no tree"; return CRF_ERR_FORMAT; }
+  const ForestParamLite& p = first->param;
+  m.face_size = p.face_size;
+  m.patch_size = (int32_t)std::round(p.face_size * p.patch_size_ratio);  // ForestParam::getPatchSize (Constants.hpp:26-30)
+  if (m.face_size != 125 || m.patch_size != 31) { err = "only face_size 125 / patch 31 models are supported by the device layout"; return CRF_ERR_UNSUPPORTED; }
+  // features -> planes in sorted id order (src/ImageSample.cpp:77-90, FeatureChannelFactory.hpp:35-183)
+  m.features.assign(p.features, p.features + std::max(0, std::min(p.n_features, 8)));
+  std::sort(m.features.begin(), m.features.end());
+  return check_against_features(m, err);
+}
+
+int set_model_features(Model& m, const int* features, int n, std::string& err) {
+  if (n < 1 || n > 6 || !features) { err = "feature list must hold 1..6 ids"; return CRF_ERR_ARG; }
+  const std::vector<int32_t> saved = m.features;
+  const int saved_planes = m.num_channels;
+  m.features.assign(features, features + n);
+  std::sort(m.features.begin(), m.features.end());
+  const int rc = check_against_features(m, err);
+  if (rc != CRF_OK) { m.features = saved; m.num_channels = saved_planes; }
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------

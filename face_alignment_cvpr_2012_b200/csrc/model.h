@@ -71,7 +71,13 @@ struct Model {
   int32_t face_size = 125;
   int32_t patch_size = 31;
   int32_t num_channels = 38;  // features {0,1,2}: gray + 35 Gabor + 2 Sobel
+  // Feature channels in the order ImageSample::extractFeatureChannels builds them (sorted ids, src/ImageSample.cpp:77-90);
+  // taken from the head-pose forest's stored ForestParam (src/FaceForest.cpp:207 uses hp_forest_param.features for BOTH forests)
+  std::vector<int32_t> features;
 };
+
+// Planes FeatureChannelFactory::extractChannel appends for one feature id (include/FeatureChannelFactory.hpp:35-183); 0 = unknown id.
+inline int planes_of_feature(int f) { return f == 0 ? 1 : f == 1 ? 35 : f == 2 ? 2 : f == 3 ? 2 : f == 4 ? 1 : f == 5 ? 1 : 0; }
 
 // All return 0 on success, negative crf_status otherwise, and fill err.
 int parse_tree_file(const std::string& path, ForestKind kind, FlatTree& out, std::string& err);
@@ -80,5 +86,7 @@ int load_model_dirs(const std::string& hp_dir, int hp_ntrees, const std::string&
 int save_model_packed(const Model& m, const std::string& path, std::string& err);
 int load_model_packed(const std::string& path, Model& out, std::string& err);
 int validate_model(const Model& m, std::string& err);
+// Replaces the feature list (sorted on entry) and re-validates (every split must read a plane the list provides).
+int set_model_features(Model& m, const int* features, int n, std::string& err);
 
 }  // namespace crf

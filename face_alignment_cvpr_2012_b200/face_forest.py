@@ -123,17 +123,47 @@ class Face:  # include/FaceForest.hpp:70-75
 class Model:
     """What FaceForest's constructor loads (src/FaceForest.cpp:15-58): the head-pose forest + the jungle."""
 
-    def __init__(self, hp_dir: str | None = None, ffd_dir: str | None = None, hp_ntrees: int = 15, ffd_ntrees: int = 20, packed: str | None = None):
+    def __init__(self, hp_dir: str | None = None, ffd_dir: str | None = None, hp_ntrees: int = 15, ffd_ntrees: int = 20, packed: str | None = None,
+                 forest_dir: str | None = None, kind: str = "hp", ntrees: int | None = None, features=None):
         L = capi.lib()
         h = C.c_void_p()
         if packed:
             capi.check(L.crf_model_load_packed(str(packed).encode(), C.byref(h)))
+        elif forest_dir is not None:   # Forest<S>::load on its own: one forest, no composition
+            capi.check(L.crf_model_load_forest(str(forest_dir).encode(), ntrees if ntrees is not None else (hp_ntrees if kind == "hp" else ffd_ntrees),
+                                               0 if kind == "hp" else 1, C.byref(h)))
         else:
             capi.check(L.crf_model_load(str(hp_dir).encode(), hp_ntrees, str(ffd_dir).encode(), ffd_ntrees, C.byref(h)))
         self.h = h
+        if features is not None:
+            self.set_features(features)
+        self._refresh()
+
+    def _refresh(self) -> None:
         info = capi.ModelInfo()
-        capi.check(L.crf_model_info(self.h, C.byref(info)))
+        capi.check(capi.lib().crf_model_info(self.h, C.byref(info)))
         self.info = {n: getattr(info, n) for n, _ in info._fields_}
+
+    def set_features(self, features) -> None:
+        """ForestParam::features of the run-time configuration (any subset of 0..5)."""
+        f = np.ascontiguousarray(features, np.int32)
+        capi.check(capi.lib().crf_model_set_features(self.h, capi.ptr(f, C.c_int32), len(f)))
+        self._refresh()
+
+    @property
+    def features(self) -> list:
+        f = np.zeros(8, np.int32)
+        n = capi.lib().crf_model_get_features(self.h, capi.ptr(f, C.c_int32), 8)
+        return f[:n].tolist()
+
+    def leaf_dump(self, which: int, tree: int) -> np.ndarray:
+        L = capi.lib()
+        n = L.crf_model_leaf_dump(self.h, which, tree, None, 0)
+        if n < 0:
+            capi.check(n)
+        out = np.zeros((n, 44), np.float32)
+        L.crf_model_leaf_dump(self.h, which, tree, capi.ptr(out, C.c_float), n)
+        return out
 
     def save_packed(self, path: str) -> None:
         capi.check(capi.lib().crf_model_save_packed(self.h, str(path).encode()))
@@ -159,7 +189,10 @@ class Model:
             pass
 
 
-def _options(o: FaceForestOptions | None, hp_stride=None, ffd_stride=None, max_chunk=None) -> Options:
+MS_MODES = {None: 0, "default": 0, "exact": 1, "fast": 2}   # crf_b200.h: CRF_MS_DEFAULT / CRF_MS_EXACT / CRF_MS_FAST
+
+
+def _options(o: FaceForestOptions | None, hp_stride=None, ffd_stride=None, max_chunk=None, ms_mode=None) -> Options:
     opt = Options()
     capi.lib().crf_options_default(C.byref(opt))
     if o is not None:
@@ -180,6 +213,8 @@ def _options(o: FaceForestOptions | None, hp_stride=None, ffd_stride=None, max_c
         opt.ffd_stride = ffd_stride
     if max_chunk is not None:
         opt.max_chunk = max_chunk
+    if ms_mode is not None:
+        opt.ms_mode = MS_MODES[ms_mode]
     return opt
 
 
@@ -189,7 +224,8 @@ class Context:
     def __init__(self, model: Model, device: int = 0, options: Options | None = None):
         self.model = model
         h = C.c_void_p()
-        capi.check(capi.lib().crf_ctx_create(model.h, device, C.byref(options) if options is not None else None, C.byref(h)))
+        # model may be None: a context without forests (feature channels, evalTest, MeanShift)
+        capi.check(capi.lib().crf_ctx_create(model.h if model is not None else None, device, C.byref(options) if options is not None else None, C.byref(h)))
         self.h = h
         self.device = device
 
@@ -284,6 +320,45 @@ class Context:
         capi.check(fn(self.h, capi.ptr(scaled, C.c_uint8), W, H, capi.ptr(planes, C.c_uint8), capi.ptr(integ, C.c_uint32)))
         return planes, integ
 
+    def stage_feature_channels(self, scaled: np.ndarray, features):
+        """ImageSample::extractFeatureChannels for an explicit feature list: (planes u8 [C,H,W], integrals u32 [C,H+1,W+1])."""
+        scaled = np.ascontiguousarray(scaled, np.uint8)
+        H, W = scaled.shape
+        f = np.ascontiguousarray(features, np.int32)
+        n = sum({0: 1, 1: 35, 2: 2, 3: 2, 4: 1, 5: 1}.get(int(v), 0) for v in set(f.tolist()))
+        planes = np.zeros((max(n, 1), H, W), np.uint8); integ = np.zeros((max(n, 1), H + 1, W + 1), np.uint32)
+        rc = capi.lib().crf_stage_feature_channels(self.h, capi.ptr(scaled, C.c_uint8), W, H, capi.ptr(f, C.c_int32), len(f), capi.ptr(planes, C.c_uint8),
+                                                   capi.ptr(integ, C.c_uint32))
+        if rc < 0:
+            capi.check(rc)
+        assert rc == n
+        return planes, integ
+
+    def stage_eval_patches(self, planes: np.ndarray, patch_xy, forest_idx=None, tree_idx=None) -> np.ndarray:
+        """Forest<S>::evaluateMT for explicit patch origins: leaf ids [patch][tree]."""
+        planes = np.ascontiguousarray(planes, np.uint8)
+        Cn, H, W = planes.shape
+        xy = np.ascontiguousarray(patch_xy, np.int32).reshape(-1, 2)
+        if forest_idx is None:
+            ids = np.zeros((len(xy), self.model.info["hp_trees"]), np.int32)
+            capi.check(capi.lib().crf_stage_eval_patches(self.h, -1, None, None, 0, capi.ptr(planes, C.c_uint8), Cn, W, H, capi.ptr(xy, C.c_int32), len(xy),
+                                                         capi.ptr(ids, C.c_int32)))
+            return ids
+        fi = np.ascontiguousarray(forest_idx, np.int32); ti = np.ascontiguousarray(tree_idx, np.int32)
+        ids = np.zeros((len(xy), len(fi)), np.int32)
+        capi.check(capi.lib().crf_stage_eval_patches(self.h, 0, capi.ptr(fi, C.c_int32), capi.ptr(ti, C.c_int32), len(fi), capi.ptr(planes, C.c_uint8), Cn, W, H,
+                                                     capi.ptr(xy, C.c_int32), len(xy), capi.ptr(ids, C.c_int32)))
+        return ids
+
+    def stage_eval_tests(self, planes: np.ndarray, tests) -> np.ndarray:
+        """ImageSample::evalTest for n tests {channel, r1(x,y,w,h), r2(x,y,w,h), patch_x, patch_y}."""
+        planes = np.ascontiguousarray(planes, np.uint8)
+        Cn, H, W = planes.shape
+        t = np.ascontiguousarray(tests, np.int32).reshape(-1, 11)
+        out = np.zeros(len(t), np.int32)
+        capi.check(capi.lib().crf_stage_eval_tests(self.h, capi.ptr(planes, C.c_uint8), Cn, W, H, capi.ptr(t, C.c_int32), len(t), capi.ptr(out, C.c_int32)))
+        return out
+
     def stage_eval_forest(self, planes: np.ndarray, stride: int, forest_idx=None, tree_idx=None) -> np.ndarray:
         planes = np.ascontiguousarray(planes, np.uint8)
         Cn, H, W = planes.shape
@@ -318,6 +393,15 @@ class Context:
         capi.check(capi.lib().crf_stage_compose(self.h, headpose, variance, capi.ptr(counts, C.c_int32), C.byref(dom), capi.ptr(fi, C.c_int32),
                                                 capi.ptr(ti, C.c_int32), C.byref(nt), C.byref(flags)))
         return dict(tree_counts=counts, dominant=dom.value, forest_idx=fi[: nt.value].copy(), tree_idx=ti[: nt.value].copy(), flags=flags.value)
+
+    def stage_compose_batch(self, headpose, variance, list_cap: int = 24) -> dict:
+        hp = np.ascontiguousarray(headpose, np.float32); var = np.ascontiguousarray(variance, np.float32)
+        n = len(hp)
+        counts = np.zeros((n, 5), np.int32); dom = np.zeros(n, np.int32); nt = np.zeros(n, np.int32); flags = np.zeros(n, np.int32)
+        fi = np.zeros((n, list_cap), np.int32); ti = np.zeros((n, list_cap), np.int32)
+        capi.check(capi.lib().crf_stage_compose_batch(self.h, capi.ptr(hp, C.c_float), capi.ptr(var, C.c_float), n, capi.ptr(counts, C.c_int32), capi.ptr(dom, C.c_int32),
+                                                      capi.ptr(nt, C.c_int32), capi.ptr(flags, C.c_int32), capi.ptr(fi, C.c_int32), capi.ptr(ti, C.c_int32), list_cap))
+        return dict(tree_counts=counts, dominant=dom, ntrees=nt, flags=flags, forest_idx=fi, tree_idx=ti)
 
     def stage_votes_meanshift(self, planes: np.ndarray, stride: int, forest_idx, tree_idx, vote_cap: int = 0) -> dict:
         planes = np.ascontiguousarray(planes, np.uint8)

@@ -81,13 +81,14 @@ class _TreeWriter:
 
 
 def tree_text(kind: str, max_depth: int, rng: np.random.Generator, channels: int = 38, leaf_prob: float = 0.15, max_rect: int = 22,
-              ntrees: int = 15, face_size: int = 125, ratio: str = "0.25", finished: bool = True, always_vote: bool = False) -> str:
+              ntrees: int = 15, face_size: int = 125, ratio: str = "0.25", finished: bool = True, always_vote: bool = False,
+              features=(0, 1, 2)) -> str:
     w = _TreeWriter(kind, max_depth, rng, channels, leaf_prob, max_rect, always_vote)
     w.node(0)
     n_nodes = 2 ** (max_depth + 1) - 1
     path = "data/trees_headpose" if kind == "hp" else "data/trees_ffd"
     hdr = ["22", "serialization::archive", "10", "0", "0", str(n_nodes), str(n_nodes if finished else n_nodes - 1), "0", "0",
-           str(max_depth), "20", "2000", str(ntrees), "400", "200", str(face_size), ratio, str(len(path)), path, "9", "index.txt", "3", "0", "0", "1", "2",
+           str(max_depth), "20", "2000", str(ntrees), "400", "200", str(face_size), ratio, str(len(path)), path, "9", "index.txt", str(len(features)), "0"] + [str(int(f)) for f in features] + [
            "8", "tree.txt"]
     return " ".join(hdr + w.tok) + "\n"
 

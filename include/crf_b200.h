@@ -61,7 +61,17 @@ typedef struct {
   float ms_stopping_criteria;  /* 0.05 */
   int   max_chunk;             /* faces per launch; 0 = as many as fit min(64 GB, half the free memory), at most 4096 */
   int   max_scaled_h;          /* ignored: work buffers grow on demand (kept for ABI stability) */
+  int   ms_mode;               /* CRF_MS_DEFAULT / CRF_MS_EXACT / CRF_MS_FAST, see below */
 } crf_options_t;
+
+/* How MeanShift::shift's sums (include/MeanShift.hpp:79-135) are evaluated.
+ * CRF_MS_EXACT: the reference's sequential f32 order, double-precision norm and glibc-identical expf: iteration counts identical,
+ *               means within 1e-3 px of the CPU reference (observed 0.0 on every campaign face).
+ * CRF_MS_FAST:  the same iteration with tree-reduced f32 sums and a hardware exp2: deterministic, within the 0.5 px landmark
+ *               tolerance of the north star (observed ~1e-4 px), ~8x faster.  Head pose, forest composition, leaf ids and the
+ *               vote lists are bit-exact in both modes.
+ * CRF_MS_DEFAULT = CRF_MS_FAST unless the environment says CRF_MS_MODE=exact. */
+enum { CRF_MS_DEFAULT = 0, CRF_MS_EXACT = 1, CRF_MS_FAST = 2 };
 
 /* Face (include/FaceForest.hpp:70-75) plus the intermediate results the parity tests need. */
 typedef struct {
@@ -110,7 +120,22 @@ int crf_model_load(const char* hp_dir, int hp_ntrees, const char* ffd_dir, int f
 /* "next" row f1: pre-packed binary image of the same forests (versioned, checksummed). */
 int crf_model_save_packed(const crf_model* m, const char* path);
 int crf_model_load_packed(const char* path, crf_model** out);
+/* Forest<S>::load on its own (include/Forest.hpp:103-129): a model with only the head-pose forest (kind 0) or only one
+ * facial-feature forest (kind 1).  Enough for the Forest / Tree / ImageSample level of the interface (crf_stage_eval_forest,
+ * crf_stage_eval_patches, crf_stage_headpose's mean / variance); crf_analyze_* need crf_model_load. */
+int crf_model_load_forest(const char* dir, int ntrees, int kind, crf_model** out);
+/* ForestParam::features as the run-time configuration gives them (data/config_*.txt; src/FaceForest.cpp:207 builds the one
+ * ImageSample of a face from hp_forest_param.features): any subset of {0 GRAY, 1 GABOR, 2 SOBEL, 3 MIN_MAX, 4 CANNY, 5 NORM}
+ * (include/FeatureChannelFactory.hpp:18-23), sorted by the library as src/ImageSample.cpp:86 does.  Default: the list stored in the
+ * archives.  Fails with CRF_ERR_UNSUPPORTED if a split of the model reads a plane the list does not provide. */
+int crf_model_set_features(crf_model* m, const int* features, int n);
+int crf_model_get_features(const crf_model* m, int* features, int cap);   /* returns the count */
 int crf_model_info(const crf_model* m, crf_model_info_t* info);
+/* Leaf payloads of one tree (which = -1 head pose, 0..4 pose forest) in pre-order leaf numbering, 44 floats per leaf:
+ * head pose: [object_id, hp_nsamples, hp_foreground, hp_labels[5]]  (include/HeadPoseSample.hpp:144-162);
+ * pose forest: [object_id, mp_samples, mp_foreground, mp_parts_offset[10][2], mp_parts_variance[10], mp_prob_foreground[10]]
+ * (include/MPSample.hpp:137-159).  Returns the leaf count. */
+int crf_model_leaf_dump(const crf_model* m, int which, int tree, float* out, int cap_leaves);
 /* Pre-order dump of one tree (which = -1 head pose, 0..4 pose forest), 16 ints per node:
  * [is_leaf, depth, ch, r1x,r1y,r1w,r1h, r2x,r2y,r2w,r2h, thr, left_oid, right_oid, nsamples, object_id] */
 int crf_model_tree_dump(const crf_model* m, int which, int tree, int32_t* out, int cap_nodes);
@@ -121,6 +146,7 @@ void crf_model_free(crf_model* m);
 
 /* ---- context */
 int crf_device_count(void);
+/* m may be NULL: a context without forests, for the stages that need none (feature channels, evalTest, MeanShift). */
 int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf_ctx** out);
 void crf_ctx_destroy(crf_ctx* ctx);
 int crf_ctx_set_profiling(crf_ctx* ctx, int on);                  /* CUDA events around every stage */
@@ -155,6 +181,10 @@ int crf_stage_gray_resize(crf_ctx* ctx, const uint8_t* bgr, int rows, int cols, 
 /* ImageSample::extractFeatureChannels (src/ImageSample.cpp:77-90) with features {0,1,2}:
  * planes_u8 [38][H][W] (may be NULL), integrals [38][H+1][W+1] u32 (may be NULL). */
 int crf_stage_channels(crf_ctx* ctx, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals);
+/* The same for an explicit feature list (any subset of 0..5, sorted by the library): planes in the order
+ * FeatureChannelFactory::extractChannel appends them.  Returns the plane count (> 0) or a negative status. */
+int crf_stage_feature_channels(crf_ctx* ctx, const uint8_t* scaled, int W, int H, const int* features, int nfeatures,
+                               uint8_t* planes_u8, uint32_t* integrals);
 /* FC_MIN_MAX (include/FeatureChannelFactory.hpp:142-165): planes [2][H][W], integrals [2][H+1][W+1]. */
 int crf_stage_minmax(crf_ctx* ctx, const uint8_t* scaled, int W, int H, uint8_t* planes_u8, uint32_t* integrals);
 /* FC_NORM (include/FeatureChannelFactory.hpp:58-70): cv::equalizeHist; plane [H][W], integral [H+1][W+1]. */
@@ -168,6 +198,13 @@ int crf_stage_canny(crf_ctx* ctx, const uint8_t* scaled, int W, int H, uint8_t* 
  * leaf_ids: [patch][tree] in the reference's order (x outer, y inner), value = Boost object id. */
 int crf_stage_eval_forest(crf_ctx* ctx, int which, const int* tree_forest, const int* tree_index, int ntrees,
                           const uint8_t* planes_u8, int C, int W, int H, int stride, int32_t* leaf_ids);
+/* Forest<S>::evaluateMT(sample, leafs) (include/Forest.hpp:81-90) for explicit patch origins — the per-sample level of the
+ * interface.  patch_xy: npatches x (x, y) top-left corners in the scaled face; leaf_ids: [patch][tree] Boost object ids. */
+int crf_stage_eval_patches(crf_ctx* ctx, int which, const int* tree_forest, const int* tree_index, int ntrees,
+                           const uint8_t* planes_u8, int C, int W, int H, const int* patch_xy, int npatches, int32_t* leaf_ids);
+/* ImageSample::evalTest(SimplePatchFeature, Rect) (src/ImageSample.cpp:30-64) for n tests:
+ * tests = n x {channel, x1, y1, w1, h1, x2, y2, w2, h2, patch_x, patch_y}; out[i] = mean(rect1) - mean(rect2). */
+int crf_stage_eval_tests(crf_ctx* ctx, const uint8_t* planes_u8, int C, int W, int H, const int* tests, int n, int* out);
 /* getHeadPoseVotesMT reduce + areaUnderCurve + composition (src/face_utils.cpp:219-241, :304-323;
  * src/FaceForest.cpp:215-250) from planes: returns headpose, variance, counts, dominant and the composed list. */
 int crf_stage_headpose(crf_ctx* ctx, const uint8_t* planes_u8, int C, int W, int H, int stride,
@@ -176,6 +213,10 @@ int crf_stage_headpose(crf_ctx* ctx, const uint8_t* planes_u8, int C, int W, int
 /* composition alone from (headpose, variance) */
 int crf_stage_compose(crf_ctx* ctx, float headpose, float variance, int tree_counts[CRF_NUM_POSE_FORESTS], int* dominant,
                       int* tree_forest, int* tree_index, int* ntrees, int* flags);
+/* the same for n pairs in one launch (knife-edge sweeps of floor(area * ntrees), src/FaceForest.cpp:243): tree_counts [n][5],
+ * dominant / ntrees / flags [n], tree_forest / tree_index [n][list_cap] (first list_cap entries, -1 padded); any output may be NULL. */
+int crf_stage_compose_batch(crf_ctx* ctx, const float* headpose, const float* variance, int n, int* tree_counts, int* dominant,
+                            int* ntrees, int* flags, int* tree_forest, int* tree_index, int list_cap);
 /* getFacialFeaturesVotesMT vote emission + MeanShift::shift x10 (src/face_utils.cpp:277-301,
  * include/MeanShift.hpp:52-135) for an explicit composed forest.  votes_xyw (optional): [10][vote_cap][3]. */
 int crf_stage_votes_meanshift(crf_ctx* ctx, const int* tree_forest, const int* tree_index, int ntrees,

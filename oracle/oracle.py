@@ -187,11 +187,11 @@ class Model:
         return dict(leaf_ids=ids.reshape(-1, nt), n_votes=nv, votes=votes if vote_cap else None, mean=mean, rounded=rnd,
                     iters=it, visits=vis.value)
 
-    def analyze_face(self, bgr: np.ndarray, box, hp_stride=4, ffd_stride=3, threads=1, headpose_only=False, want_stats=False):
+    def analyze_face(self, bgr: np.ndarray, box, hp_stride=4, ffd_stride=3, threads=1, headpose_only=False, want_stats=False, features_mask=7):
         L = lib()
         bgr = np.ascontiguousarray(bgr, np.uint8)
         rows, cols = bgr.shape[:2]
-        opt = OrcOptions(hp_stride, ffd_stride, threads, 7, int(headpose_only))
+        opt = OrcOptions(hp_stride, ffd_stride, threads, features_mask, int(headpose_only))
         out = OrcFace(); stats = np.zeros(4, np.int64)
         r = L.orc_analyze_face(self.h, _p(bgr, C.c_uint8), rows, cols, cols * 3, int(box[0]), int(box[1]), int(box[2]), int(box[3]),
                                C.byref(opt), C.byref(out), _p(stats, C.c_longlong) if want_stats else None)

@@ -1,0 +1,107 @@
+"""GPU: configurable feature lists, the per-sample level of the interface (evaluateMT on explicit patches,
+ImageSample::evalTest) and contexts on partial models — each against the oracle."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(crf):
+    if crf.lib().crf_device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box (there is no CPU fallback)")
+    return True
+
+
+def _img(rng, H, W):
+    import cv2
+    return cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), 1.5)
+
+
+@pytest.mark.parametrize("features", [(0, 1, 2, 3, 4, 5), (3, 0), (5, 4, 2), (1,), (0, 2, 3)])
+def test_feature_channel_lists(O, crf, gpu, features):
+    """FeatureChannelFactory::extractChannel over a configured list: planes appended in sorted-id order."""
+    ctx = crf.Context(None, 0)
+    rng = np.random.default_rng(sum(features))
+    for H, W in [(125, 125), (141, 124)]:
+        img = _img(rng, H, W)
+        planes, integ = ctx.stage_feature_channels(img, features)
+        op, oi = O.channels(img, features_mask=sum(1 << f for f in features))
+        assert planes.shape == op.shape and np.array_equal(planes, op)
+        assert np.array_equal(integ, oi.astype(np.uint32))
+    with pytest.raises(crf.CrfError):
+        ctx.stage_feature_channels(img, [0, 0])
+
+
+def test_forests_on_42_planes_end_to_end(O, crf, gpu, tmp_path):
+    """A forest trained on all six feature kinds (42 planes; its splits read channels up to 41): whole path and stride-1
+    (the shared-memory window holds at most 38 planes, so dense grids fall back to the global-gather kernels)."""
+    from face_alignment_cvpr_2012_b200 import synthetic_model as sm, workloads as wl
+    hp, ffd = sm.write_model(tmp_path / "all", seed=21, channels=42, features=(0, 1, 2, 3, 4, 5))
+    gm, om = crf.Model(hp, ffd, 15, 20), O.Model(hp, ffd, 15, 20)
+    used = max(int(gm.tree_dump(w, t)[:, 2].max()) for w in (-1, 0, 3) for t in range(5))
+    assert used >= 38
+    crops, _ = wl.make_crops(12, seed=5)
+    for hs, fs, sel in [(4, 3, range(12)), (1, 1, (0, 7))]:
+        ctx = crf.Context(gm, 0, crf._options(None, hp_stride=hs, ffd_stride=fs))
+        got = ctx.analyze_crops(crops)
+        for i in sel:
+            want = om.analyze_face(crops[i], (0, 0, 100, 100), hs, fs, threads=4, features_mask=63)
+            assert got[i]["headpose"].tobytes() == want["headpose"].tobytes() and got[i]["variance"].tobytes() == want["variance"].tobytes()
+            assert np.array_equal(got[i]["tree_counts"], want["tree_counts"]) and np.array_equal(got[i]["n_votes"], want["n_votes"])
+            assert np.array_equal(got[i]["ms_iters"], want["ms_iters"]) and np.abs(got[i]["ffd_f"] - want["ffd_f"]).max() <= 1e-3
+    # a 3-plane model (features 0 and 2) and the same trees with MIN_MAX added at run time
+    hp3, ffd3 = sm.write_model(tmp_path / "three", seed=22, channels=3, features=(0, 2))
+    g3, o3 = crf.Model(hp3, ffd3, 15, 20), O.Model(hp3, ffd3, 15, 20)
+    got = crf.Context(g3, 0).analyze_crops(crops[:4])
+    for i in range(4):
+        want = o3.analyze_face(crops[i], (0, 0, 100, 100), features_mask=0b101)
+        assert got[i]["headpose"].tobytes() == want["headpose"].tobytes() and np.array_equal(got[i]["ffd"], want["ffd"])
+    g3.set_features([0, 2, 3])
+    got2 = crf.Context(g3, 0).analyze_crops(crops[:4])
+    assert got2.tobytes() == got.tobytes()   # the trees never read the two added planes
+
+
+def test_evaluate_on_explicit_patches_and_eval_test(O, crf, gpu, synth_models, synth_dirs):
+    """Forest<S>::evaluateMT per sample and ImageSample::evalTest: the dense-grid results picked at arbitrary patches, the
+    integer mean-difference formula, and the same through contexts that hold a single forest."""
+    gm, om = synth_models
+    hp, ffd = synth_dirs
+    rng = np.random.default_rng(9)
+    planes = rng.integers(0, 256, (38, 140, 125), dtype=np.uint8)
+    ctx = crf.Context(gm, 0)
+    dense = ctx.stage_eval_forest(planes, 1)                       # [x * ny + y][tree]
+    ny = 140 - 31
+    xy = np.stack([rng.integers(0, 125 - 31, 50), rng.integers(0, ny, 50)], 1)
+    pick = dense[xy[:, 0] * ny + xy[:, 1]]
+    assert np.array_equal(ctx.stage_eval_patches(planes, xy), pick)
+    fi = rng.integers(0, 5, 20); ti = rng.integers(0, 20, 20)
+    dense_f = ctx.stage_eval_forest(planes, 1, fi, ti)
+    assert np.array_equal(ctx.stage_eval_patches(planes, xy, fi, ti), dense_f[xy[:, 0] * ny + xy[:, 1]])
+    # single-forest contexts (Forest<S>::load on its own)
+    c_hp = crf.Context(crf.Model(forest_dir=hp, kind="hp", ntrees=15), 0)
+    assert np.array_equal(c_hp.stage_eval_patches(planes, xy), pick)
+    r_full, r_hp = ctx.stage_headpose(planes, 4), c_hp.stage_headpose(planes, 4)
+    assert r_hp["headpose"] == r_full["headpose"] and r_hp["variance"] == r_full["variance"] and len(r_hp["forest_idx"]) == 0
+    c_mp = crf.Context(crf.Model(forest_dir=str(Path(ffd) / "forest_2"), kind="mp", ntrees=20), 0)
+    t2 = np.arange(20)
+    assert np.array_equal(c_mp.stage_eval_patches(planes, xy, np.zeros(20, int), t2), ctx.stage_eval_patches(planes, xy, np.full(20, 2), t2))
+    for bad in (lambda: c_hp.stage_eval_forest(planes, 3, fi, ti), lambda: c_mp.stage_headpose(planes, 4), lambda: c_hp.analyze_crops(np.zeros((1, 100, 100, 3), np.uint8)),
+                lambda: ctx.stage_eval_patches(planes, [[100, 5]])):
+        with pytest.raises(crf.CrfError):
+            bad()
+    # evalTest
+    integ = np.zeros((38, 141, 126), np.int64)
+    integ[:, 1:, 1:] = planes.astype(np.int64).cumsum(1).cumsum(2)
+    tests, want = [], []
+    for _ in range(500):
+        c = int(rng.integers(0, 38)); px = int(rng.integers(0, 125 - 31)); py = int(rng.integers(0, 140 - 31))
+        r = []
+        for _k in range(2):
+            w, h = int(rng.integers(1, 23)), int(rng.integers(1, 23))
+            r.append((int(rng.integers(0, 31 - w)), int(rng.integers(0, 31 - h)), w, h))
+        m = [int(integ[c, py + y + h, px + x + w] - integ[c, py + y, px + x + w] - integ[c, py + y + h, px + x] + integ[c, py + y, px + x]) // (w * h) for (x, y, w, h) in r]
+        tests.append([c, *r[0], *r[1], px, py]); want.append(m[0] - m[1])
+    assert np.array_equal(crf.Context(None, 0).stage_eval_tests(planes, tests), np.array(want, np.int32))

@@ -85,7 +85,7 @@ def test_channels_golden_plane(sctx, cv2_golden):
     ref = cv2_golden["gabor_u8_cv2"]
     assert np.array_equal(planes[1:8], ref[:7])
     d = planes[1:36].astype(int) - ref.astype(int)
-    assert np.abs(d).max() <= 1 and (d != 0).mean() < 1e-3
+    assert np.abs(d).max() <= 1 and (d != 0).mean() <= 2e-4
 
 
 def test_norm_channel(O, sctx, cv2_golden):
@@ -133,12 +133,19 @@ def test_forest_leaf_ids_synthetic_model(O, sctx, synth_models, stride, H, W):
     s.close()
 
 
+@pytest.mark.parametrize("win", ["default", "rows", "pairx"])
 @pytest.mark.parametrize("H,W,nt", [(125, 125, 20), (148, 124, 20), (33, 125, 7), (40, 125, 23), (200, 125, 20), (32, 125, 20), (70, 124, 41)])
-def test_window_traversal_forced(O, crf, gpu, synth_models, monkeypatch, H, W, nt):
+def test_window_traversal_forced(O, crf, gpu, synth_models, monkeypatch, H, W, nt, win):
     """k_traverse_win (shared-memory window, ring rows, two walks per lane) on one ragged face: partial tiles right and
-    below, heights that need 1..22 tile steps, tree lists shorter / longer than the warps of a CTA, and the counters."""
+    below, heights that need 1..22 tile steps, tree lists shorter / longer than the warps of a CTA, and the counters.
+    win: the launch shapes in use — library defaults, two walks per lane on rows ly / ly + 4 (and one walk per lane for
+    the head-pose forest), two walks per lane on horizontal neighbours with the shared record fetch (PAIRX)."""
     gm, om = synth_models
     monkeypatch.setenv("CRF_TRAVERSE_VARIANT", "0x100001")
+    if win == "rows":
+        monkeypatch.setenv("CRF_WIN_HP", str(30 | 1 << 8)); monkeypatch.setenv("CRF_WIN_FFD", str(20 | 2 << 8))
+    elif win == "pairx":
+        monkeypatch.setenv("CRF_WIN_HP", str(15 | 2 << 8 | 1 << 12)); monkeypatch.setenv("CRF_WIN_FFD", str(20 | 2 << 8 | 1 << 12))
     ctx = crf.Context(gm, 0)
     ctx.set_profiling(False, True)
     rng = np.random.default_rng(H * 7 + nt)

@@ -155,3 +155,53 @@ def test_device_record_forms_agree(crf, synth_models, tmp_path):
     if p is not None:
         n, hp, ffd = check(crf.Model(packed=str(p)))
         assert (hp, ffd) == (30, 30) and n == 176841 + 1536652   # SURVEY Appendix C node counts; extents as measured in DESIGN 4.1
+
+
+def test_feature_lists_and_channel_validation(crf, O, tmp_path):
+    """ForestParam::features drives the plane layout (src/ImageSample.cpp:77-90): a model is accepted only if every split reads
+    a plane its feature list provides — the reference would index m_feature_channels out of bounds, the GPU would read the
+    next face's planes."""
+    from face_alignment_cvpr_2012_b200 import synthetic_model as sm
+    # all six feature kinds: 1 + 35 + 2 + 2 + 1 + 1 = 42 planes, splits read channels 0..41
+    hp, ffd = sm.write_model(tmp_path / "all", seed=3, hp_trees=4, hp_depth=6, ffd_trees=3, ffd_depth=6, channels=42, features=(5, 0, 3, 1, 4, 2))
+    m = crf.Model(hp, ffd, 4, 3)
+    assert m.features == [0, 1, 2, 3, 4, 5] and m.info["num_channels"] == 42
+    # the same trees under the shipped configuration (features 0 1 2 -> 38 planes) read planes that do not exist
+    with pytest.raises(crf.CrfError) as e:
+        m.set_features([0, 1, 2])
+    assert e.value.code == -6 and "feature channel" in str(e.value)
+    assert m.features == [0, 1, 2, 3, 4, 5]   # a rejected list leaves the model unchanged
+    # archives that store features {0, 2} (3 planes) but whose splits read channel 30: rejected at load, text and packed alike
+    hp2, ffd2 = sm.write_model(tmp_path / "bad", seed=4, hp_trees=2, hp_depth=5, ffd_trees=2, ffd_depth=5, channels=38, features=(0, 2))
+    with pytest.raises(crf.CrfError) as e:
+        crf.Model(hp2, ffd2, 2, 2)
+    assert e.value.code == -6
+    # ... and accepted when the splits stay inside the 3 planes; the run-time list may add planes but not remove used ones
+    hp3, ffd3 = sm.write_model(tmp_path / "ok", seed=5, hp_trees=2, hp_depth=5, ffd_trees=2, ffd_depth=5, channels=3, features=(0, 2))
+    m3 = crf.Model(hp3, ffd3, 2, 2)
+    assert m3.features == [0, 2] and m3.info["num_channels"] == 3
+    m3.set_features([2, 0, 3])
+    assert m3.features == [0, 2, 3] and m3.info["num_channels"] == 5
+    for bad in ([0, 0], [7], []):
+        with pytest.raises(crf.CrfError):
+            m3.set_features(bad)
+    p = tmp_path / "m3.crfb200"
+    crf.Model(hp3, ffd3, 2, 2).save_packed(str(p))
+    assert crf.Model(packed=str(p)).features == [0, 2]
+
+
+def test_single_forest_models_and_leaf_dump(crf, O, synth_dirs, synth_models):
+    """Forest<S>::load on its own (include/Forest.hpp:103-129) and the leaf payloads (HeadPoseLeaf / MPLeaf)."""
+    hp, ffd = synth_dirs
+    gm, om = synth_models
+    one = crf.Model(forest_dir=hp, kind="hp", ntrees=15)
+    assert one.info["hp_trees"] == 15 and one.info["mp_forests"] == 0
+    two = crf.Model(forest_dir=str(Path(ffd) / "forest_3"), kind="mp", ntrees=20)
+    assert two.info["hp_trees"] == 0 and two.info["mp_forests"] == 1 and two.info["mp_trees"] == 20
+    assert np.array_equal(two.tree_dump(0, 7), gm.tree_dump(3, 7))
+    for which, t in [(-1, 0), (-1, 14), (0, 0), (4, 19)]:
+        a, b = gm.leaf_dump(which, t), om.leaf_dump(which, t)
+        assert a.shape == b.shape and np.array_equal(a, b)
+    assert np.array_equal(two.leaf_dump(0, 5), gm.leaf_dump(3, 5))
+    with pytest.raises(crf.CrfError):
+        crf.Model(forest_dir=str(Path(hp) / "missing"), kind="hp", ntrees=15)

@@ -58,7 +58,7 @@ def test_gabor_7x7_filter2d_bit_exact(O, cv2_golden):
 
 def test_gabor_planes_vs_cv2(O, cv2_golden):
     """nu = 0 planes are bit-exact; for >= 9x9 kernels cv2 switches to a DFT path, so the pin is statistical:
-    every difference is +-1 LSB and rarer than 1e-3 (observed ~1e-5)."""
+    every difference is +-1 LSB and rarer than 2e-4 (observed ~6e-5)."""
     img = cv2_golden["plane"]
     planes, _ = O.channels(img, features_mask=0b0010)
     ref = cv2_golden["gabor_u8_cv2"]
@@ -66,7 +66,7 @@ def test_gabor_planes_vs_cv2(O, cv2_golden):
     assert np.array_equal(planes[:7], ref[:7])
     d = planes.astype(int) - ref.astype(int)
     assert np.abs(d).max() <= 1
-    assert (d != 0).mean() < 1e-3
+    assert (d != 0).mean() <= 2e-4
 
 
 def test_gabor_bank_geometry(O):
@@ -128,3 +128,42 @@ def test_area_under_curve_sums_to_one(O):
     edges = [-2.5, -0.35, -0.2, 0.2, 0.35, 2.5]
     tot = sum(float(O.area_under_curve(edges[i], edges[i + 1], 0.1, 0.15)) for i in range(5))
     assert abs(tot - 1.0) < 0.06
+
+
+def test_cv2_gabor_planes_downstream(O, lfw_faces):
+    """What the +-1-LSB distance between the canonical Gabor arithmetic and cv2's filter2D (DFT path for kernels >= 9x9) does
+    downstream: cv2-made planes and the oracle's planes through the shipped forests on LFW faces + synthetic crops.  Observed on
+    the full set (20 faces + 64 crops, tests/test_gpu_reference_campaign.py runs it on the GPU): 2.8e-5 of the u8 samples differ,
+    1e-5 of the leaf ids, landmarks move by <= 0.02 px."""
+    import cv2
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    p = wl.staged_model_path()
+    if p is None:
+        pytest.skip("staged/model.crfb200 not present")
+    om = O.Model(packed=str(p))
+    bank = O.gabor_bank()
+    crops, _ = wl.make_crops(6, seed=4806)
+    items = [(f["img"], f["box"]) for f in lfw_faces[:6]] + [(c, (0, 0, 100, 100)) for c in crops]
+    n_px = n_diff = n_leaf = n_leaf_diff = 0
+    worst = 0.0
+    for img, box in items:
+        x, y, w, h = box
+        sw, sh, _ = O.scaled_size(w, h)
+        g = O.resize(O.bgr2gray(img)[y:y + h, x:x + w], sh, sw)
+        planes, _ = O.channels(g, threads=4)
+        cvp = planes.copy()
+        for k, (re, im) in enumerate(bank):
+            r = cv2.filter2D(g, cv2.CV_32F, re); i = cv2.filter2D(g, cv2.CV_32F, im)
+            m = cv2.pow(cv2.add(cv2.pow(i, 2), cv2.pow(r, 2)), 0.5)
+            cvp[1 + k] = cv2.convertScaleAbs(cv2.normalize(m, None, 0, 1, cv2.NORM_MINMAX), alpha=255)
+        d = cvp.astype(np.int16) - planes
+        assert np.abs(d).max() <= 1 and not d[0].any() and not d[36:].any()
+        n_px += d[1:36].size; n_diff += int((d != 0).sum())
+        sa, sb = O.Sample(planes=planes), O.Sample(planes=cvp)
+        _, hpa, va, _ = om.eval_hp(sa, 4); _, hpb, vb, _ = om.eval_hp(sb, 4)
+        _, _, fi, ti, _ = om.compose(hpa, va)
+        ea, eb = om.eval_ffd(sa, fi, ti, 3), om.eval_ffd(sb, fi, ti, 3)
+        n_leaf += ea["leaf_ids"].size; n_leaf_diff += int((ea["leaf_ids"] != eb["leaf_ids"]).sum())
+        worst = max(worst, float(np.abs(ea["mean"] - eb["mean"]).max()), abs(float(hpa) - float(hpb)))
+        sa.close(); sb.close()
+    assert n_diff / n_px <= 2e-4 and n_leaf_diff / n_leaf <= 1e-3 and worst <= 0.5
