@@ -785,6 +785,23 @@ int crf_model_load_forest(const char* dir, int ntrees, int kind, crf_model** out
   return CRF_OK;
 }
 
+// Tree<S>::load(Tree**, path) (include/Tree.hpp:193-237): a model holding the single tree of one archive file.
+int crf_model_load_tree(const char* path, int kind, crf_model** out) {
+  if (!out || !path || (kind != 0 && kind != 1)) return fail(CRF_ERR_ARG, "bad argument");
+  *out = nullptr;
+  std::unique_ptr<crf_model> m(new crf_model());
+  std::string err;
+  FlatForest& f = kind == 0 ? m->m.hp : (m->m.jungle.resize(1), m->m.jungle[0]);
+  f.kind = kind == 0 ? KIND_HEADPOSE : KIND_MULTIPART;
+  f.trees.resize(1);
+  int rc = parse_tree_file(path, f.kind, f.trees[0], err);
+  // Forest::load_tree rejects unfinished trees (include/Forest.hpp:142-152); Tree::load itself reloads them
+  if (rc == CRF_OK) { (kind == 0 ? m->m.hp_ntrees_cfg : m->m.mp_ntrees_cfg) = 1; rc = validate_model(m->m, err); }
+  if (rc) { std::fprintf(stderr, "  %s\n", err.c_str()); return fail(rc, err); }
+  *out = m.release();
+  return CRF_OK;
+}
+
 // ForestParam::features as the run-time configuration gives them (data/config_*.txt line 22; src/FaceForest.cpp:207 uses
 // hp_forest_param.features for both forests).  Default: the list stored in the head-pose forest's archives.
 int crf_model_set_features(crf_model* m, const int* features, int n) {
@@ -1538,6 +1555,28 @@ int crf_stage_votes_meanshift(crf_ctx* c, const int* tree_forest, const int* tre
   }
   c->timer.collect();
   return pull_counters(c);
+}
+
+int crf_stage_area_under_curve(crf_ctx* c, float x1, float x2, double mean, double std_, float* area) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!area) return fail(CRF_ERR_ARG, "null argument");
+  if (!(x2 - x1 <= 1000.f)) return fail(CRF_ERR_ARG, "integration range too wide");   // 1e5 serial steps at most
+  CU(cudaSetDevice(c->device));
+  k_area_under_curve<<<1, 1, 0, c->w->stream>>>(x1, x2, mean, std_, c->d_misc.as<float>());
+  KCHECK(); count_launch(c, CRF_STAGE_HP_REDUCE);
+  CU(cudaMemcpyAsync(area, c->d_misc.p, 4, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
+  return CRF_OK;
+}
+
+// MeanShift::shift(votes, result, num_iterations, kernel, stopping_criteria) (include/MeanShift.hpp:52-76) with per-call options.
+int crf_stage_meanshift_opt(crf_ctx* c, const float* votes_xyw, int n, int kernel, int max_iterations, float stopping, float mean_xy[2], int rounded_xy[2], int* iters) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  const crf_options_t saved = c->opt;
+  c->opt.ms_kernel_size = kernel; c->opt.ms_max_iterations = max_iterations; c->opt.ms_stopping_criteria = stopping;
+  const int rc = crf_stage_meanshift(c, votes_xyw, n, mean_xy, rounded_xy, iters);
+  c->opt = saved;
+  return rc;
 }
 
 int crf_stage_meanshift(crf_ctx* c, const float* votes_xyw, int n, float mean_xy[2], int rounded_xy[2], int* iters) {

@@ -1173,6 +1173,18 @@ __global__ void __launch_bounds__(kFoldThreads) k_hp_reduce_compose(const FaceDe
       compose_face(s_mean[j], s_var[j], ct, lane, faces + f0 + j, face_roots + (size_t)(f0 + j) * kMaxList, face_ntrees + f0 + j);
 }
 
+// areaUnderCurve(x1, x2, mean, std) (src/face_utils.cpp:304-323) for arbitrary bounds: the reference's serial Riemann sum
+// (x += 0.01 in double from (double)x1) on one thread.
+__global__ void k_area_under_curve(float x1, float x2, double mean, double sd, float* out) {
+  double sum = 0;
+  const double step = 0.01;
+  for (double x = x1; x < x2; x += step) {
+    const double t = (x - mean) / sd;
+    sum += exp(-0.5 * (t * t)) * step;
+  }
+  *out = (float)(sum * 1.0 / (sd * sqrt(2 * 3.14159265358979323846)));
+}
+
 // Composition alone (stage API).
 __global__ void k_compose_only(float headpose, float variance, ComposeTables ct, crf_face_t* face, int32_t* list, int32_t* ntrees) {
   compose_face(headpose, variance, ct, threadIdx.x & 31, face, list, ntrees);

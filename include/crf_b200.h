@@ -124,6 +124,8 @@ int crf_model_load_packed(const char* path, crf_model** out);
  * facial-feature forest (kind 1).  Enough for the Forest / Tree / ImageSample level of the interface (crf_stage_eval_forest,
  * crf_stage_eval_patches, crf_stage_headpose's mean / variance); crf_analyze_* need crf_model_load. */
 int crf_model_load_forest(const char* dir, int ntrees, int kind, crf_model** out);
+/* Tree<S>::load(Tree**, path) (include/Tree.hpp:193-237): a model holding the single tree of one archive file (kind 0 / 1). */
+int crf_model_load_tree(const char* path, int kind, crf_model** out);
 /* ForestParam::features as the run-time configuration gives them (data/config_*.txt; src/FaceForest.cpp:207 builds the one
  * ImageSample of a face from hp_forest_param.features): any subset of {0 GRAY, 1 GABOR, 2 SOBEL, 3 MIN_MAX, 4 CANNY, 5 NORM}
  * (include/FeatureChannelFactory.hpp:18-23), sorted by the library as src/ImageSample.cpp:86 does.  Default: the list stored in the
@@ -223,8 +225,13 @@ int crf_stage_votes_meanshift(crf_ctx* ctx, const int* tree_forest, const int* t
                               const uint8_t* planes_u8, int C, int W, int H, int stride,
                               int n_votes[CRF_NUM_PARTS], float* votes_xyw, int vote_cap,
                               float mean_xy[CRF_NUM_PARTS][2], int rounded_xy[CRF_NUM_PARTS][2], int iters[CRF_NUM_PARTS]);
-/* MeanShift::shift on a caller-supplied vote list (x, y, weight triples). */
+/* MeanShift::shift on a caller-supplied vote list (x, y, weight triples), with the context's MeanShiftOption ... */
 int crf_stage_meanshift(crf_ctx* ctx, const float* votes_xyw, int n, float mean_xy[2], int rounded_xy[2], int* iters);
+/* ... or with per-call options: shift(votes, result, num_iterations, kernel, stopping_criteria) (include/MeanShift.hpp:52-76). */
+int crf_stage_meanshift_opt(crf_ctx* ctx, const float* votes_xyw, int n, int kernel, int max_iterations, float stopping,
+                            float mean_xy[2], int rounded_xy[2], int* iters);
+/* areaUnderCurve(x1, x2, mean, std) (src/face_utils.cpp:304-323; include/face_utils.hpp:103-108). */
+int crf_stage_area_under_curve(crf_ctx* ctx, float x1, float x2, double mean, double std_, float* area);
 
 #ifdef __cplusplus
 }
