@@ -29,10 +29,7 @@ namespace {
 const int NUM_HEADPOSE_CLASSES = 5;          // include/Constants.hpp:66
 const float TRAIN_IMAGES_PERCENTAGE = 0.9f;  // include/Constants.hpp:68
 
-struct Param : crf_b200::ForestParam {       // the remaining fields of include/Constants.hpp:24-60
-  std::string image_path;
-  int ntests = 0, min_patches = 0, nimages = 0, npatches = 0;
-};
+typedef crf_b200::ForestParam Param;          // include/Constants.hpp:24-60
 
 struct FaceAnnotation {                       // include/face_utils.hpp:44-52
   std::string url;
@@ -159,7 +156,7 @@ int main(int argc, char** argv) {
   }
 
   crf_b200::FaceForestOptions ff_options;
-  ff_options.head_pose_forest_param = hp_param;
+  ff_options.hp_forest_param = hp_param;
   ff_options.mp_forest_param = mp_param;
   crf_b200::FaceForest ff(ff_options);
   if (!ff.is_inizialized) return EXIT_FAILURE;
@@ -170,7 +167,7 @@ int main(int argc, char** argv) {
       std::vector<unsigned char> bgr; int rows = 0, cols = 0;
       if ((!headpose && a.parts.size() < 8) || !load_image(ann_path, a.url, bgr, rows, cols)) { std::cerr << "(!) Error: Could not load: " << a.url << std::endl; continue; }
       crf_b200::Face face;
-      ff.analyzeFace(cvlite::Mat(rows, cols, bgr.data()), a.bbox, face);
+      ff.analyzeFace(cvlite::Mat(rows, cols, CV_8UC3, bgr.data()), a.bbox, face);
       if (headpose) { std::cout << "Real:" << a.pose << " Predict:" << face.headpose << std::endl; continue; }   // src/eval_headpose.cpp:88
       std::vector<float> err;
       const float iod = getInterOccularDist(a);

@@ -126,7 +126,7 @@ def main(argv=None) -> int:
     except FileNotFoundError as e:
         print(f"(!) {e}", file=sys.stderr)
         return 1
-    opt = FaceForestOptions(head_pose_forest_param=hp_param, mp_forest_param=mp_param, packed_model=args.packed)
+    opt = FaceForestOptions(hp_forest_param=hp_param, mp_forest_param=mp_param, packed_model=args.packed)
     ann_path = args.annotations or (mp_param.image_path if args.what == "ffd" else hp_param.image_path)
     annotations = loadAnnotations(ann_path)
     if annotations is None:

@@ -101,15 +101,18 @@ def enlarge_detections(boxes, rows: int, cols: int) -> list:
 
 @dataclass
 class FaceForestOptions:  # include/FaceForest.hpp:60-68
-    fd_option: FaceDetectionOption = field(default_factory=FaceDetectionOption)
-    head_pose_forest_param: ForestParam = field(default_factory=ForestParam)
+    hp_forest_param: ForestParam = field(default_factory=ForestParam)
     mp_forest_param: ForestParam = field(default_factory=ForestParam)
-    pose_option: HeadPoseEstimatorOption = field(default_factory=HeadPoseEstimatorOption)
-    multi_part_option: MultiPartEstimatorOption = field(default_factory=MultiPartEstimatorOption)
-    mean_shift_option: MeanShiftOption = field(default_factory=MeanShiftOption)
+    fd_option: FaceDetectionOption = field(default_factory=FaceDetectionOption)
+    hp_option: HeadPoseEstimatorOption = field(default_factory=HeadPoseEstimatorOption)
+    mp_option: MultiPartEstimatorOption = field(default_factory=MultiPartEstimatorOption)
+    mp_forest_paths: list = field(default_factory=list)
+    # extensions (not in the reference's struct)
+    mean_shift_option: MeanShiftOption = field(default_factory=MeanShiftOption)   # default-constructed inside estimateFacialFeatures there
     packed_model: str = ""   # "next" row f1: pre-packed binary image instead of the two tree directories
     device: int = 0
     max_chunk: int = 0
+    ms_mode: str = "default"   # crf_b200.h: MeanShift evaluation mode ("default" | "exact" | "fast")
 
 
 @dataclass
@@ -196,17 +199,18 @@ def _options(o: FaceForestOptions | None, hp_stride=None, ffd_stride=None, max_c
     opt = Options()
     capi.lib().crf_options_default(C.byref(opt))
     if o is not None:
-        opt.hp_stride = o.pose_option.step_size
-        opt.hp_min_foreground = o.pose_option.min_foreground_probability
-        opt.ffd_stride = o.multi_part_option.step_size
-        opt.ffd_min_samples = o.multi_part_option.min_samples
-        opt.ffd_min_foreground = o.multi_part_option.min_forground
-        opt.ffd_min_pf = o.multi_part_option.min_pf
-        opt.ffd_max_variance = o.multi_part_option.max_variance
+        opt.hp_stride = o.hp_option.step_size
+        opt.hp_min_foreground = o.hp_option.min_foreground_probability
+        opt.ffd_stride = o.mp_option.step_size
+        opt.ffd_min_samples = o.mp_option.min_samples
+        opt.ffd_min_foreground = o.mp_option.min_forground
+        opt.ffd_min_pf = o.mp_option.min_pf
+        opt.ffd_max_variance = o.mp_option.max_variance
         opt.ms_kernel_size = o.mean_shift_option.kernel_size
         opt.ms_max_iterations = o.mean_shift_option.max_iterations
         opt.ms_stopping_criteria = o.mean_shift_option.stopping_criteria
         opt.max_chunk = o.max_chunk
+        opt.ms_mode = MS_MODES[o.ms_mode]
     if hp_stride is not None:
         opt.hp_stride = hp_stride
     if ffd_stride is not None:
@@ -433,7 +437,7 @@ class FaceForest:
                 if o.packed_model:
                     model = Model(packed=o.packed_model)
                 else:
-                    model = Model(o.head_pose_forest_param.tree_path, o.mp_forest_param.tree_path, o.head_pose_forest_param.ntrees or 15,
+                    model = Model(o.hp_forest_param.tree_path, o.mp_forest_param.tree_path, o.hp_forest_param.ntrees or 15,
                                   o.mp_forest_param.ntrees or 20)
             self.model = model
             self.ctx = Context(model, self.option.device, _options(self.option))
