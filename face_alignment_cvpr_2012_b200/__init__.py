@@ -6,6 +6,6 @@ MeanShift) as hand-written sm_100a kernels behind the C ABI of include/crf_b200.
 """
 from .capi import FACE_DTYPE, CrfError, Options, Rect, build, lib  # noqa: F401
 from .face_forest import (Context, Face, FaceDetectionOption, FaceForest, FaceForestOptions, ForestParam, HeadPoseEstimatorOption, enlarge_detections, intersect,  # noqa: F401
-                          MeanShift, MeanShiftOption, Model, MultiPartEstimatorOption, loadConfigFile, _options)
+                          MeanShift, MeanShiftOption, Model, MultiContext, MultiPartEstimatorOption, loadConfigFile, _options)
 
-__all__ = ["FaceForest", "FaceForestOptions", "Face", "ForestParam", "Model", "Context", "MeanShift", "CrfError", "build", "lib"]
+__all__ = ["FaceForest", "FaceForestOptions", "Face", "ForestParam", "Model", "Context", "MultiContext", "MeanShift", "CrfError", "build", "lib"]

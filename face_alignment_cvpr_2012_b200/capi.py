@@ -66,6 +66,7 @@ EXPORTS = [
     "crf_stage_compose", "crf_stage_compose_batch", "crf_stage_votes_meanshift", "crf_stage_meanshift",
     "crf_model_load_forest", "crf_model_set_features", "crf_model_get_features", "crf_model_leaf_dump", "crf_stage_feature_channels",
     "crf_stage_eval_patches", "crf_stage_eval_tests", "crf_model_load_tree", "crf_stage_meanshift_opt", "crf_stage_area_under_curve",
+    "crf_multi_create", "crf_multi_destroy", "crf_multi_device_count", "crf_multi_ctx", "crf_multi_analyze_batch", "crf_multi_analyze_crops",
 ]
 
 _lib = None
@@ -140,6 +141,14 @@ def lib() -> C.CDLL:
     L.crf_model_load_tree.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.crf_stage_meanshift_opt.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, C.c_float, f32p, i32p, i32p]
     L.crf_stage_area_under_curve.argtypes = [vp, C.c_float, C.c_float, C.c_double, C.c_double, f32p]
+    L.crf_multi_create.argtypes = [vp, i32p, C.c_int, C.POINTER(Options), C.POINTER(vp)]
+    L.crf_multi_destroy.argtypes = [vp]
+    L.crf_multi_destroy.restype = None
+    L.crf_multi_device_count.argtypes = [vp]
+    L.crf_multi_ctx.argtypes = [vp, C.c_int]
+    L.crf_multi_ctx.restype = vp
+    L.crf_multi_analyze_batch.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(Rect), i32p, C.c_int, vp]
+    L.crf_multi_analyze_crops.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     _lib = L
     return L
 

@@ -1211,6 +1211,96 @@ int crf_analyze_crops_device(crf_ctx* c, const uint8_t* d_bgr_batch, int n, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Several GPUs behind one caller: one context and one host thread per GPU, contiguous shards of the faces
+// (cut at frame boundaries when the boxes are grouped by frame), a full forest replica per GPU, results written straight
+// into the caller's array.  No collective: faces are independent, only the records come back.
+// ---------------------------------------------------------------------------------------------
+struct crf_multi {
+  std::vector<crf_ctx*> ctx;
+};
+
+void crf_multi_destroy(crf_multi* m) {
+  if (!m) return;
+  for (crf_ctx* c : m->ctx) crf_ctx_destroy(c);
+  delete m;
+}
+
+int crf_multi_create(const crf_model* model, const int* devices, int n_devices, const crf_options_t* opt, crf_multi** out) {
+  if (!out || !model || n_devices < 0) return fail(CRF_ERR_ARG, "bad argument");
+  *out = nullptr;
+  std::vector<int> dev;
+  if (!devices || n_devices == 0) {
+    const int n = crf_device_count();
+    if (n < 1) return fail(CRF_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    for (int i = 0; i < n; i++) dev.push_back(i);
+  } else dev.assign(devices, devices + n_devices);
+  std::unique_ptr<crf_multi, void (*)(crf_multi*)> m(new crf_multi(), crf_multi_destroy);
+  for (int d : dev) {
+    crf_ctx* c = nullptr;
+    const int rc = crf_ctx_create(model, d, opt, &c);
+    if (rc) return rc;
+    m->ctx.push_back(c);
+  }
+  *out = m.release();
+  return CRF_OK;
+}
+
+int crf_multi_device_count(const crf_multi* m) { return m ? (int)m->ctx.size() : 0; }
+crf_ctx* crf_multi_ctx(crf_multi* m, int i) { return m && i >= 0 && i < (int)m->ctx.size() ? m->ctx[(size_t)i] : nullptr; }
+
+static int multi_run(crf_multi* m, const uint8_t* const* images, int n_images, int rows, int cols, size_t step, const crf_rect_t* boxes, const int* image_of_box, int n,
+                     crf_face_t* out, bool headpose_only) {
+  if (!m || m->ctx.empty()) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (n < 0 || (n > 0 && (!images || !boxes || !out))) return fail(CRF_ERR_ARG, "null argument");
+  const int G = (int)m->ctx.size();
+  // shard g = faces [cut[g], cut[g + 1]): even split, moved to the nearest frame boundary when consecutive boxes share frames
+  std::vector<int> cut((size_t)G + 1, n);
+  cut[0] = 0;
+  for (int g = 1; g < G; g++) {
+    int c = (int)((long long)n * g / G);
+    if (image_of_box && c > 0 && c < n) {
+      int lo = c, hi = c;
+      while (lo > cut[(size_t)g - 1] && image_of_box[lo] == image_of_box[lo - 1]) lo--;
+      while (hi < n && image_of_box[hi] == image_of_box[hi - 1]) hi++;
+      // take the closer boundary unless that would empty a shard
+      c = (c - lo <= hi - c && lo > cut[(size_t)g - 1]) ? lo : (hi < n ? hi : (lo > cut[(size_t)g - 1] ? lo : c));
+    }
+    cut[(size_t)g] = std::max(c, cut[(size_t)g - 1]);
+  }
+  std::vector<int> rcs((size_t)G, CRF_OK);
+  std::vector<std::string> errs((size_t)G);
+  auto work = [&](int g) {
+    const int f0 = cut[(size_t)g], f1 = cut[(size_t)g + 1];
+    if (f1 <= f0) return;
+    // a shard names its frames through the caller's image_of_box; crops (image_of_box == NULL) are one frame per face
+    rcs[(size_t)g] = analyze_host(m->ctx[(size_t)g], image_of_box ? images : images + f0, image_of_box ? n_images : f1 - f0, rows, cols, step, boxes + f0,
+                                  image_of_box ? image_of_box + f0 : nullptr, f1 - f0, out + f0, headpose_only);
+    if (rcs[(size_t)g]) errs[(size_t)g] = g_last_error;   // thread-local in the worker: hand it to the caller
+  };
+  std::vector<std::thread> th;
+  for (int g = 1; g < G; g++) th.emplace_back(work, g);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int g = 0; g < G; g++)
+    if (rcs[(size_t)g]) return fail(rcs[(size_t)g], "GPU shard " + std::to_string(g) + ": " + errs[(size_t)g]);
+  return CRF_OK;
+}
+
+int crf_multi_analyze_batch(crf_multi* m, const uint8_t* const* images, int n_images, int rows, int cols, size_t step, const crf_rect_t* boxes,
+                            const int* image_of_box, int n, crf_face_t* out) {
+  if (!image_of_box && n > 0) return fail(CRF_ERR_ARG, "null argument");
+  return multi_run(m, images, n_images, rows, cols, step, boxes, image_of_box, n, out, false);
+}
+
+int crf_multi_analyze_crops(crf_multi* m, const uint8_t* bgr_batch, int n, int rows, int cols, crf_face_t* out, int headpose_only) {
+  if (n < 0 || (n > 0 && !bgr_batch)) return fail(CRF_ERR_ARG, "null argument");
+  std::vector<const uint8_t*> imgs((size_t)std::max(n, 0));
+  std::vector<crf_rect_t> boxes((size_t)std::max(n, 0), crf_rect_t{0, 0, cols, rows});
+  for (int i = 0; i < n; i++) imgs[(size_t)i] = bgr_batch + (size_t)i * rows * cols * 3;
+  return multi_run(m, imgs.data(), n, rows, cols, (size_t)cols * 3, boxes.data(), nullptr, n, out, headpose_only != 0);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage-level entry points
 // ---------------------------------------------------------------------------------------------
 int crf_stage_gray_resize(crf_ctx* c, const uint8_t* bgr, int rows, int cols, size_t step, crf_rect_t box, uint8_t* scaled, int* W, int* H) {

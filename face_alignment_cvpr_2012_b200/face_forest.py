@@ -425,6 +425,53 @@ class Context:
         return mean, rnd, it.value
 
 
+class MultiContext:
+    """Several GPUs behind one caller (crf_multi_*): one context and one host thread per GPU inside the library, contiguous
+    shards of the faces, records written straight into one array.  devices=None: every visible GPU."""
+
+    def __init__(self, model: Model, devices=None, options: Options | None = None):
+        self.model = model
+        h = C.c_void_p()
+        d = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        capi.check(capi.lib().crf_multi_create(model.h, None if d is None else capi.ptr(d, C.c_int32), 0 if d is None else len(d),
+                                               C.byref(options) if options is not None else None, C.byref(h)))
+        self.h = h
+        self.n_devices = capi.lib().crf_multi_device_count(self.h)
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            capi.lib().crf_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def analyze_crops(self, crops: np.ndarray, headpose_only: bool = False) -> np.ndarray:
+        crops = np.ascontiguousarray(crops, np.uint8)
+        n, rows, cols = crops.shape[:3]
+        out = np.zeros(n, FACE_DTYPE)
+        capi.check(capi.lib().crf_multi_analyze_crops(self.h, crops.ctypes.data, n, rows, cols, out.ctypes.data, int(headpose_only)))
+        return out
+
+    def analyze_crops_ptr(self, host_ptr: int, n: int, rows: int, cols: int, out: np.ndarray, headpose_only: bool = False) -> None:
+        capi.check(capi.lib().crf_multi_analyze_crops(self.h, host_ptr, n, rows, cols, out.ctypes.data, int(headpose_only)))
+
+    def analyze_batch(self, frames, boxes, image_of_box) -> np.ndarray:
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames] if not isinstance(frames, np.ndarray) else np.ascontiguousarray(frames, np.uint8)
+        n_images = len(frames)
+        rows, cols = frames[0].shape[:2]
+        ptrs = (C.c_void_p * n_images)(*[f.ctypes.data for f in frames])
+        n = len(boxes)
+        rects = (Rect * max(n, 1))(*[Rect(int(b[0]), int(b[1]), int(b[2]), int(b[3])) for b in boxes])
+        iob = np.ascontiguousarray(image_of_box, np.int32)
+        out = np.zeros(n, FACE_DTYPE)
+        capi.check(capi.lib().crf_multi_analyze_batch(self.h, ptrs, n_images, rows, cols, cols * 3, rects, capi.ptr(iob, C.c_int32), n, out.ctypes.data))
+        return out
+
+
 class FaceForest:
     """FaceForest (include/FaceForest.hpp:77-159, src/FaceForest.cpp).  Face boxes are supplied by the caller."""
 

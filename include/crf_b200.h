@@ -175,6 +175,19 @@ int crf_headpose_crops(crf_ctx* ctx, const uint8_t* bgr_batch, int n, int rows, 
  * on crf_ctx_stream(); used to measure the kernel path without PCIe. */
 int crf_analyze_crops_device(crf_ctx* ctx, const uint8_t* d_bgr_batch, int n, int rows, int cols, crf_face_t* d_out, int headpose_only);
 
+/* ---- several GPUs behind one caller: one context + one host thread per GPU, contiguous shards of the faces (cut at frame
+ * boundaries when the boxes are grouped by frame), a forest replica per GPU, records written straight into `out`.  No collective:
+ * faces are independent (FaceForest::analyzeImage's loop over faces, src/FaceForest.cpp:174-180).  devices NULL / n_devices 0 = every
+ * visible GPU; a device may be listed more than once. */
+typedef struct crf_multi crf_multi;
+int crf_multi_create(const crf_model* m, const int* devices, int n_devices, const crf_options_t* opt, crf_multi** out);
+void crf_multi_destroy(crf_multi* mg);
+int crf_multi_device_count(const crf_multi* mg);
+crf_ctx* crf_multi_ctx(crf_multi* mg, int i);   /* shard i's context (counters, profiling) */
+int crf_multi_analyze_batch(crf_multi* mg, const uint8_t* const* images, int n_images, int rows, int cols, size_t step,
+                            const crf_rect_t* boxes, const int* image_of_box, int n, crf_face_t* out);
+int crf_multi_analyze_crops(crf_multi* mg, const uint8_t* bgr_batch, int n, int rows, int cols, crf_face_t* out, int headpose_only);
+
 /* ---- stage-level entry points (device results copied back) used by the parity tests and by the
  * reference-shaped classes in crf_b200_compat.hpp. */
 /* src/FaceForest.cpp:196-204: cvtColor + ROI + resize.  scaled: caller buffer of at least max_h x 125 bytes, dense rows of *W. */

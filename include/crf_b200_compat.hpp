@@ -99,7 +99,7 @@ struct FaceForestOptions {
   HeadPoseEstimatorOption hp_option;
   MultiPartEstimatorOption mp_option;
   std::vector<std::string> mp_forest_paths;
-  int device = 0;                         // CUDA device of the context
+  int device = 0;                         // CUDA device of the context; -1 = all visible GPUs, the faces of a call sharded over them
   int ms_mode = CRF_MS_DEFAULT;           // crf_b200.h: MeanShift evaluation mode
   MeanShiftOption mean_shift_option;      // the reference default-constructs this inside estimateFacialFeatures (src/FaceForest.cpp:89)
 };
@@ -136,12 +136,17 @@ inline int& default_device() { static int d = 0; return d; }
 // A loaded model and the GPU context made for it.  The leaf-vote predicate (src/face_utils.cpp:285-290) is folded into the device
 // image when a context is created, so a call with other thresholds re-creates the context (the last one is kept).
 struct Loaded {
-  crf_model* model = nullptr; crf_ctx* ctx = nullptr; crf_options_t opt; int device = 0;
-  ~Loaded() { if (ctx) crf_ctx_destroy(ctx); if (model) crf_model_free(model); }
+  crf_model* model = nullptr; crf_ctx* ctx = nullptr; crf_multi* multi = nullptr; crf_options_t opt; int device = 0;
+  ~Loaded() { if (multi) crf_multi_destroy(multi); if (ctx) crf_ctx_destroy(ctx); if (model) crf_model_free(model); }
+  // device < 0: every visible GPU behind this one caller (crf_multi_*: one context + host thread per GPU, faces sharded)
+  crf_multi* all_gpus(const crf_options_t& want) {
+    if (!multi) check(crf_multi_create(model, nullptr, 0, &want, &multi));
+    return multi;
+  }
   crf_ctx* context(const crf_options_t& want) {
     if (!ctx || std::memcmp(&want, &opt, sizeof opt) != 0) {
       if (ctx) { crf_ctx_destroy(ctx); ctx = nullptr; }
-      check(crf_ctx_create(model, device, &want, &ctx));
+      check(crf_ctx_create(model, device < 0 ? 0 : device, &want, &ctx));
       opt = want;
     }
     return ctx;
@@ -663,7 +668,13 @@ class FaceForest {
     std::vector<crf_rect_t> r(boxes.size());
     for (size_t i = 0; i < boxes.size(); i++) r[i] = crf_rect_t{boxes[i].x, boxes[i].y, boxes[i].width, boxes[i].height};
     std::vector<crf_face_t> out(boxes.size());
-    check(crf_analyze_faces(context(), img.data, img.rows, img.cols, img.step, r.data(), (int)r.size(), out.data()));
+    if (m_options.device < 0) {
+      const uint8_t* frames[1] = {img.data};
+      const std::vector<int> zero(boxes.size(), 0);
+      check(crf_multi_analyze_batch(loaded_->all_gpus(options()), frames, 1, img.rows, img.cols, img.step, r.data(), zero.data(), (int)r.size(), out.data()));
+    } else {
+      check(crf_analyze_faces(context(), img.data, img.rows, img.cols, img.step, r.data(), (int)r.size(), out.data()));
+    }
     if (!append) faces.clear();
     for (size_t i = 0; i < boxes.size(); i++) {
       Face f;

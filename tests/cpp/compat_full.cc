@@ -146,6 +146,16 @@ int main(int argc, char** argv) {
   m_mp_forest.evaluateMT(&one_patch, mleafs.data());
   std::printf("mp_forest.evaluateMT");
   for (MPLeaf* l : mleafs) std::printf(" %d", l->mp_samples);
-  std::printf("\ncompat_full ok\n");
+  // device = -1: the same analyzeImage with every visible GPU behind the one caller
+  FaceForestOptions all = ff_options;
+  all.device = -1;
+  FaceForest ff_all(all);
+  std::vector<Face> many;
+  std::vector<cvlite::Rect> boxes{bbox, cvlite::Rect(40, 10, 90, 105), cvlite::Rect(0, 0, 120, 120), bbox};
+  ff_all.analyzeImage(img, boxes, many);
+  bool same = many.size() == 4 && many[0].headpose == face.headpose && many[3].headpose == face.headpose;
+  for (size_t i = 0; same && i < 10; i++) same = many[0].ffd_cordinates[i].x == face.ffd_cordinates[i].x && many[3].ffd_cordinates[i].y == face.ffd_cordinates[i].y;
+  std::printf("\nmulti.same %d\n", (int)same);
+  std::printf("compat_full ok\n");
   return 0;
 }

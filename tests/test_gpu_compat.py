@@ -100,4 +100,5 @@ def test_reference_interface_in_cpp(crf, O, synth_dirs, synth_models, tmp_path, 
     ef = om.eval_ffd(s, fi, ti, 1)
     ids = ef["leaf_ids"][33 * ny1 + 41]
     assert [int(v) for v in out["mp_forest.evaluateMT"]] == [int(_leaf(om, int(fi[k]), int(ti[k]), ids[k])[1]) for k in range(len(fi))]
+    assert out["multi.same"] == ["1"]
     s.close()

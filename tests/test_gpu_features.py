@@ -105,3 +105,26 @@ def test_evaluate_on_explicit_patches_and_eval_test(O, crf, gpu, synth_models, s
         m = [int(integ[c, py + y + h, px + x + w] - integ[c, py + y, px + x + w] - integ[c, py + y + h, px + x] + integ[c, py + y, px + x]) // (w * h) for (x, y, w, h) in r]
         tests.append([c, *r[0], *r[1], px, py]); want.append(m[0] - m[1])
     assert np.array_equal(crf.Context(None, 0).stage_eval_tests(planes, tests), np.array(want, np.int32))
+
+
+def test_multi_gpu_single_caller(crf, O, gpu, synth_models):
+    """crf_multi_*: shards behind one caller.  On a one-GPU box the same device is listed three times, which exercises the
+    sharding, the threads and the frame-boundary cuts exactly as three GPUs would; results must equal the single-context ones."""
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, _ = synth_models
+    ndev = crf.lib().crf_device_count()
+    devices = list(range(ndev)) if ndev >= 2 else [0, 0, 0]
+    mc = crf.MultiContext(gm, devices)
+    assert mc.n_devices == len(devices)
+    one = crf.Context(gm, 0)
+    crops, _ = wl.make_crops(37, seed=12)
+    assert mc.analyze_crops(crops).tobytes() == one.analyze_crops(crops).tobytes()
+    assert mc.analyze_crops(crops[:2]).tobytes() == one.analyze_crops(crops[:2]).tobytes()      # fewer faces than shards
+    assert mc.analyze_crops(crops, headpose_only=True).tobytes() == one.analyze_crops(crops, headpose_only=True).tobytes()
+    frames, boxes, iob, _ = wl.make_frames(5, rows=360, cols=480, faces_per_frame=3, seed=3, wmin=64, wmax=110)
+    assert mc.analyze_batch(frames, boxes, iob).tobytes() == one.analyze_batch(frames, boxes, iob).tobytes()
+    bad = boxes.copy(); bad[len(bad) - 1] = (470, 10, 100, 100)   # the last shard's last box leaves its frame: the error names the shard
+    with pytest.raises(crf.CrfError) as e:
+        mc.analyze_batch(frames, bad, iob)
+    assert e.value.code == -1 and "shard" in str(e.value)
+    assert crf.MultiContext(gm).n_devices == ndev

@@ -3,6 +3,8 @@
 
   staged/model.crfb200   packed binary image of data/trees_headpose + data/trees_ffd (crf_model_save_packed)
   staged/imgs/           the 20 LFW jpgs + index_random_subset.txt (fixtures for C1 and the synthetic generators)
+  staged/trees_headpose, staged/trees_ffd   the 115 Boost text archives themselves (282 MB): what the REAL reference code
+                         (oracle/_ref/libcrf_ref.so, bench.py's cpu_baseline kind "reference") loads on the GPU box
 
 /root/reference does not exist on the GPU box; nothing at run time reads it.
 """
@@ -32,6 +34,9 @@ def main() -> int:
     for p in sorted((REF / "imgs").iterdir()):
         shutil.copy(p, out / "imgs" / p.name)
     shutil.copy(REF / "haarcascade_frontalface_alt.xml", out / "haarcascade_frontalface_alt.xml")
+    for d in ("trees_headpose", "trees_ffd"):
+        if not (out / d).exists():
+            shutil.copytree(REF / d, out / d)
     print("staged", len(list((out / "imgs").iterdir())), "files under staged/imgs + the Haar cascade (host-side detectFace)")
     return 0
 
