@@ -4,7 +4,7 @@ it counts live (bench.py cannot run under ncu).  For each window-traversal launc
 wavefronts per node test and per LDS instruction, issue rate, share of warp samples stalled on the long scoreboard; for the
 other kernels: DRAM bytes per launch and duration under ncu.
 
-usage: ncu_counters.py <report.ncu-rep> <faces_per_launch> <bench.json with work_per_step at the same faces_per_launch>
+usage: ncu_counters.py <report.ncu-rep> <faces_per_launch> <bench.json with work_per_step at the same faces_per_launch> [git head of the captured build]
 """
 import csv
 import json
@@ -40,7 +40,7 @@ def main():
 
     work = bench["work_per_step"]
     bench_faces = bench["config"]["faces_per_gpu"]
-    out = {"git_head": subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip(),
+    out = {"git_head": sys.argv[4] if len(sys.argv) > 4 else subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip(),
            "report": Path(rep).name, "faces_per_launch": faces, "kernels": []}
     trav = 0
     for r in rows[2:]:
@@ -61,17 +61,19 @@ def main():
             tests = work["hp_node_tests" if trav == 0 else "ffd_node_tests"] * faces / bench_faces
             trav += 1
             wf = get(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum")
-            lds = get(r, "smsp__inst_executed_op_shared_ld.sum") or get(r, "sm__inst_executed_op_shared_ld.sum")
-            samples = get(r, "smsp__pcsamp_sample_buffer_full.sum")
+            # requests of the shared-memory loads = wavefronts - bank conflicts (one wavefront per conflict-free request)
+            confl = get(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum")
+            lds = wf - confl if (wf and confl is not None) else None
             stall = None
-            tot = sum(v for v in (get(r, h) for h in hdr if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued.sum")) if v)
-            lsb = get(r, "smsp__pcsamp_warps_issue_stalled_long_scoreboard.sum")
+            tot = sum(v for v in (get(r, h) for h in hdr if h.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in h) if v)
+            lsb = get(r, "smsp__pcsamp_warps_issue_stalled_long_scoreboard")
             if tot and lsb is not None:
                 stall = 100.0 * lsb / tot
             out[key] = {"kernel": name, "dram_bytes_per_face": dram / faces, "node_tests_per_launch": tests,
                         "lds_wavefronts_per_node_test": wf / tests if wf else None, "lds_wavefronts_per_load": wf / lds if (wf and lds) else None,
+                        "lds_pipe_pct": get(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed"),
+                        "tex_pipe_pct": get(r, "l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed"),
                         "issue_active_pct": rec["issue_active_pct"], "long_scoreboard_stall_pct": stall, "duration_ms_under_ncu": rec["duration_ms_under_ncu"]}
-            (samples)
     (ROOT / "profiles" / "r2_counters.json").write_text(json.dumps(out, indent=1))
     print(json.dumps({k: v for k, v in out.items() if k != "kernels"}, indent=1))
 
