@@ -66,6 +66,7 @@ EXPORTS = [
     "crf_stage_compose", "crf_stage_compose_batch", "crf_stage_votes_meanshift", "crf_stage_meanshift",
     "crf_model_load_forest", "crf_model_set_features", "crf_model_get_features", "crf_model_leaf_dump", "crf_stage_feature_channels",
     "crf_stage_eval_patches", "crf_stage_eval_tests", "crf_model_load_tree", "crf_stage_meanshift_opt", "crf_stage_area_under_curve",
+    "crf_cascade_load", "crf_cascade_free", "crf_cascade_info", "crf_detect_faces",
     "crf_multi_create", "crf_multi_destroy", "crf_multi_device_count", "crf_multi_ctx", "crf_multi_analyze_batch", "crf_multi_analyze_crops",
 ]
 
@@ -74,7 +75,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """Compile libcrf_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    srcs = [CSRC / n for n in ("engine.cu", "kernels.cuh", "device_forest.h", "model.h", "model.cc", "pack.cc", "Makefile")] + \
+    srcs = [CSRC / n for n in ("engine.cu", "kernels.cuh", "haar.cuh", "device_forest.h", "model.h", "model.cc", "pack.cc", "Makefile")] + \
            [_PKG.parent / "include" / "crf_b200.h"]
     if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return LIB_PATH
@@ -141,6 +142,11 @@ def lib() -> C.CDLL:
     L.crf_model_load_tree.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.crf_stage_meanshift_opt.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, C.c_float, f32p, i32p, i32p]
     L.crf_stage_area_under_curve.argtypes = [vp, C.c_float, C.c_float, C.c_double, C.c_double, f32p]
+    L.crf_cascade_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.crf_cascade_free.argtypes = [vp]
+    L.crf_cascade_free.restype = None
+    L.crf_cascade_info.argtypes = [vp, i32p, i32p, i32p, i32p]
+    L.crf_detect_faces.argtypes = [vp, vp, u8p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.POINTER(Rect), C.c_int]
     L.crf_multi_create.argtypes = [vp, i32p, C.c_int, C.POINTER(Options), C.POINTER(vp)]
     L.crf_multi_destroy.argtypes = [vp]
     L.crf_multi_destroy.restype = None

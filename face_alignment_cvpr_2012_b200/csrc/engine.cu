@@ -188,6 +188,9 @@ struct crf_ctx {
   int ms_variant = 3;   // resident MeanShift CTAs per SM the kernel is compiled for (register cap); CRF_MS_VARIANT overrides
   size_t work_budget = (size_t)64 << 30;  // bytes of work buffers a launch may use (min(64 GB, half of the free memory at creation))
   StageTimer timer;
+  // face-box source (haar.cuh): device image of the last cascade used + pyramid-level buffers
+  const struct crf_cascade* haar_cached = nullptr;
+  Buf d_haar_stages, d_haar_weak, d_haar_feats, d_haar_level, d_haar_S, d_haar_Q, d_haar_flags;
 };
 
 namespace crf {
@@ -717,10 +720,103 @@ static int analyze_host(crf_ctx* c, const uint8_t* const* images, int n_images, 
 
 }  // namespace crf
 
+#include "haar.cuh"
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
 extern "C" {
+
+// ---- FaceForest::detectFace's box source (src/FaceForest.cpp:136-146): cv::CascadeClassifier::load + detectMultiScale
+int crf_cascade_load(const char* path, crf_cascade** out) {
+  if (!path || !out) return fail(CRF_ERR_ARG, "null argument");
+  *out = nullptr;
+  std::unique_ptr<crf_cascade> c(new crf_cascade());
+  std::string err;
+  const int rc = load_cascade(path, c->c, err);
+  if (rc) return fail(rc, err);
+  *out = c.release();
+  return CRF_OK;
+}
+void crf_cascade_free(crf_cascade* c) { delete c; }
+
+int crf_cascade_info(const crf_cascade* c, int* win_w, int* win_h, int* nstages, int* nweak) {
+  if (!c) return fail(CRF_ERR_ARG, "null argument");
+  if (win_w) *win_w = c->c.win_w;
+  if (win_h) *win_h = c->c.win_h;
+  if (nstages) *nstages = (int)c->c.stages.size();
+  if (nweak) *nweak = (int)c->c.weak.size();
+  return CRF_OK;
+}
+
+int crf_detect_faces(crf_ctx* c, const crf_cascade* cas, const uint8_t* bgr, int rows, int cols, size_t step, double scale_factor, int min_neighbors, int min_size,
+                     crf_rect_t* out, int cap) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (!cas || !bgr || rows < 1 || cols < 1 || step < (size_t)cols * 3 || !(scale_factor > 1.0) || cap < 0 || (cap > 0 && !out)) return fail(CRF_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->w->stream;
+  int rc;
+  const Cascade& K = cas->c;
+  if (c->haar_cached != cas) {
+    if ((rc = upload(c->d_haar_stages, K.stages, s)) || (rc = upload(c->d_haar_weak, K.weak, s)) || (rc = upload(c->d_haar_feats, K.features, s))) return rc;
+    c->haar_cached = cas;
+  }
+  if ((rc = c->d_imgs[0].reserve((size_t)rows * step))) return rc;
+  CU(cudaMemcpyAsync(c->d_imgs[0].p, bgr, (size_t)rows * step, cudaMemcpyHostToDevice, s));
+  c->cnt.h2d_bytes += (size_t)rows * step;
+  // the scales of CascadeClassifierImpl::detectMultiScale (flags 0, no maxSize)
+  struct Level { double factor; int win_w, win_h, sw, sh, ystep, nx, ny; size_t flag_off; };
+  std::vector<Level> levels;
+  size_t flag_bytes = 0;
+  for (double factor = 1;; factor *= scale_factor) {
+    Level L;
+    L.factor = factor;
+    L.win_w = (int)std::lrint(K.win_w * factor); L.win_h = (int)std::lrint(K.win_h * factor);
+    L.sw = (int)std::lrint(cols / factor); L.sh = (int)std::lrint(rows / factor);
+    if (L.win_w > cols || L.win_h > rows || L.sw < K.win_w || L.sh < K.win_h) break;
+    if (L.win_w < min_size || L.win_h < min_size) continue;
+    L.ystep = factor > 2. ? 1 : 2;
+    L.nx = (L.sw - K.win_w + 1 + L.ystep - 1) / L.ystep; L.ny = (L.sh - K.win_h + 1 + L.ystep - 1) / L.ystep;
+    L.flag_off = flag_bytes;
+    flag_bytes += (size_t)L.nx * L.ny;
+    levels.push_back(L);
+  }
+  std::vector<crf_rect_t> cand;
+  if (!levels.empty()) {
+    const Level& L0 = levels[0];
+    const size_t npx = (size_t)(L0.sw + 1) * (L0.sh + 1);
+    if ((rc = c->d_haar_level.reserve((size_t)L0.sw * L0.sh)) || (rc = c->d_haar_S.reserve(npx * 4)) || (rc = c->d_haar_Q.reserve(npx * 4)) || (rc = c->d_haar_flags.reserve(flag_bytes))) return rc;
+    for (const Level& L : levels) {
+      k_haar_level<<<dim3((L.sw + 127) / 128, L.sh), 128, 0, s>>>(c->d_imgs[0].as<uint8_t>(), rows, cols, step, c->d_haar_level.as<uint8_t>(), L.sh, L.sw,
+                                                                   1. / ((double)L.sw / cols), 1. / ((double)L.sh / rows));
+      k_haar_rowscan<<<(L.sh + 7) / 8, 256, 0, s>>>(c->d_haar_level.as<uint8_t>(), L.sh, L.sw, c->d_haar_S.as<uint32_t>(), c->d_haar_Q.as<uint32_t>());
+      k_haar_colscan<<<(L.sw + 1 + 127) / 128, 128, 0, s>>>(L.sh, L.sw, c->d_haar_S.as<uint32_t>(), c->d_haar_Q.as<uint32_t>());
+      k_haar_eval<<<dim3((L.nx + 127) / 128, L.ny), 128, 0, s>>>(c->d_haar_S.as<uint32_t>(), c->d_haar_Q.as<uint32_t>(), L.sw, L.sh, K.win_w, K.win_h, L.ystep, L.nx, L.ny,
+                                                                 c->d_haar_stages.as<HaarStage>(), (int)K.stages.size(), c->d_haar_weak.as<HaarWeak>(), c->d_haar_feats.as<HaarFeature>(),
+                                                                 c->d_haar_flags.as<uint8_t>() + L.flag_off);
+      KCHECK(); count_launch(c, CRF_STAGE_RESIZE, 4);
+    }
+    std::vector<uint8_t> flags(flag_bytes);
+    CU(cudaMemcpyAsync(flags.data(), c->d_haar_flags.p, flag_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    c->cnt.d2h_bytes += flag_bytes;
+    // CascadeClassifierInvoker's scan: windows in raster order, one extra step after a window the first stage rejected
+    for (const Level& L : levels) {
+      const uint8_t* f = flags.data() + L.flag_off;
+      for (int iy = 0; iy < L.ny; iy++)
+        for (int ix = 0; ix < L.nx; ix++) {
+          const uint8_t v = f[(size_t)iy * L.nx + ix];
+          if (v & 1) cand.push_back(crf_rect_t{(int)std::lrint(ix * L.ystep * L.factor), (int)std::lrint(iy * L.ystep * L.factor), L.win_w, L.win_h});
+          if (v & 2) ix++;
+        }
+    }
+  } else {
+    CU(cudaStreamSynchronize(s));
+  }
+  group_rectangles(cand, min_neighbors, 0.2);
+  for (int i = 0; i < (int)cand.size() && i < cap; i++) out[i] = cand[(size_t)i];
+  return (int)cand.size();
+}
 
 const char* crf_last_error(void) { return g_last_error.c_str(); }
 const char* crf_version(void) { return "crf_b200 0.1 (sm_100a)"; }
@@ -942,7 +1038,8 @@ void crf_ctx_destroy(crf_ctx* c) {
   if (c->tex_hp_wide) cudaDestroyTextureObject(c->tex_hp_wide);
   if (c->tex_mp_wide) cudaDestroyTextureObject(c->tex_mp_wide);
   Buf* all[] = {&c->d_hp_slotsw, &c->d_mp_slotsw, &c->d_hp_slots16, &c->d_mp_slots16, &c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
-                &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_coef_sep[1], &c->d_coef_sep[2], &c->d_coef_sep[3], &c->d_coef_sep[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc};
+                &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_coef_sep[1], &c->d_coef_sep[2], &c->d_coef_sep[3], &c->d_coef_sep[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc,
+                &c->d_haar_stages, &c->d_haar_weak, &c->d_haar_feats, &c->d_haar_level, &c->d_haar_S, &c->d_haar_Q, &c->d_haar_flags};
   for (Buf* b : all) b->release();
   for (auto& w : c->ws) {
     for (Buf* b : w.all) b->release();

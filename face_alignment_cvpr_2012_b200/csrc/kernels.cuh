@@ -939,11 +939,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int
             if (la && lb) break;
             const int ca = win_step(colA, rowA, a0, a1, la ? 0u : 1u), cb = win_step(colB, rowA, b0, b1, lb ? 0u : 1u);
             if (COUNT) tests += (vA && !la ? 1 : 0) + (vB && !lb ? 1 : 0);
+            // both walks moved to the same node: one fetch serves both.  The second walk's own fetch (lanes that split) is issued
+            // BEFORE the register copy, which has to wait for the first fetch to land
+            const bool same = !la && !lb && cb == ca;
             if (!la) fetch(ca, a0, a1);
-            if (!lb) {
-              if (!la && cb == ca) { b0 = a0; b1 = a1; }   // both walks moved to the same node: one fetch serves both
-              else fetch(cb, b0, b1);
-            }
+            if (!lb && !same) fetch(cb, b0, b1);
+            if (same) { b0 = a0; b1 = a1; }
           }
           int va = (int)a1.y, vb = (int)b1.y;
           if (a.leaf_value) { va = __float_as_int(__ldg(a.leaf_value + va)); vb = __float_as_int(__ldg(a.leaf_value + vb)); }

@@ -425,6 +425,48 @@ class Context:
         return mean, rnd, it.value
 
 
+class CascadeClassifier:
+    """cv::CascadeClassifier for the reference's face cascade (src/FaceForest.cpp:23): load() parses the XML on the host,
+    detectMultiScale evaluates it on the GPU (crf_detect_faces)."""
+
+    def __init__(self, path: str | None = None):
+        self.h = None
+        if path:
+            self.load(path)
+
+    def load(self, path: str) -> bool:
+        h = C.c_void_p()
+        if capi.lib().crf_cascade_load(str(path).encode(), C.byref(h)) != 0:
+            return False
+        self.close()
+        self.h = h
+        return True
+
+    def empty(self) -> bool:
+        return self.h is None
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            capi.lib().crf_cascade_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def detectMultiScale(self, ctx: "Context", img: np.ndarray, scaleFactor: float = 1.1, minNeighbors: int = 3, minSize=(0, 0)) -> list:
+        img = np.ascontiguousarray(img, np.uint8)
+        rows, cols = img.shape[:2]
+        cap = 1024
+        out = (Rect * cap)()
+        n = capi.lib().crf_detect_faces(ctx.h, self.h, capi.ptr(img, C.c_uint8), rows, cols, cols * 3, float(scaleFactor), int(minNeighbors), int(max(minSize)), out, cap)
+        if n < 0:
+            capi.check(n)
+        return [(r.x, r.y, r.width, r.height) for r in out[: min(n, cap)]]
+
+
 class MultiContext:
     """Several GPUs behind one caller (crf_multi_*): one context and one host thread per GPU inside the library, contiguous
     shards of the faces, records written straight into one array.  devices=None: every visible GPU."""
@@ -489,9 +531,8 @@ class FaceForest:
             self.model = model
             self.ctx = Context(model, self.option.device, _options(self.option))
             self.m_face_cascade = None
-            if self.option.fd_option.path_face_cascade:   # src/FaceForest.cpp:23-28; the cascade itself stays on the CPU
-                import cv2
-                self.m_face_cascade = cv2.CascadeClassifier(self.option.fd_option.path_face_cascade)
+            if self.option.fd_option.path_face_cascade:   # src/FaceForest.cpp:23-28
+                self.m_face_cascade = CascadeClassifier(self.option.fd_option.path_face_cascade)
                 if self.m_face_cascade.empty():
                     import sys
                     print(f"(!) Error loading face detection model: {self.option.fd_option.path_face_cascade}", file=sys.stderr)
@@ -517,16 +558,15 @@ class FaceForest:
             return face
         return f
 
-    @staticmethod
-    def detectFace(img: np.ndarray, face_cascade, fd_option: FaceDetectionOption) -> list:
-        """src/FaceForest.cpp:136-159: cv::CascadeClassifier::detectMultiScale on the host (OpenCV, as in the reference) +
-        the box enlargement.  Not part of the GPU hot path: its boxes feed analyzeFace."""
+    def detectFace(self, img: np.ndarray, face_cascade: CascadeClassifier, fd_option: FaceDetectionOption) -> list:
+        """src/FaceForest.cpp:136-159: detectMultiScale(img, boxes, search_scale_factor, min_neighbors, 0, Size(min_feature_size))
+        with the cascade evaluated on the GPU + the reference's box enlargement."""
         mfs = (fd_option.min_feature_size, fd_option.min_feature_size)
-        det = face_cascade.detectMultiScale(img, scaleFactor=fd_option.search_scale_factor, minNeighbors=fd_option.min_neighbors, flags=0, minSize=mfs)
-        return enlarge_detections([tuple(int(v) for v in b) for b in det], img.shape[0], img.shape[1])
+        det = face_cascade.detectMultiScale(self.ctx, img, scaleFactor=fd_option.search_scale_factor, minNeighbors=fd_option.min_neighbors, minSize=mfs)
+        return enlarge_detections(det, img.shape[0], img.shape[1])
 
     def analyzeImage(self, img: np.ndarray, faces_bboxes=None, faces: list | None = None) -> list:
-        """src/FaceForest.cpp:161-181.  With faces_bboxes=None the Haar cascade of fd_option runs first (host), as in the
+        """src/FaceForest.cpp:161-181.  With faces_bboxes=None the Haar cascade of fd_option runs first (on the GPU), as in the
         reference; otherwise the caller's boxes are used.  All faces of the frame go through the GPU in one launch."""
         if not self.is_inizialized:
             raise AssertionError("CV_Assert(is_inizialized)")  # src/FaceForest.cpp:167

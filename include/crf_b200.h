@@ -175,6 +175,18 @@ int crf_headpose_crops(crf_ctx* ctx, const uint8_t* bgr_batch, int n, int rows, 
  * on crf_ctx_stream(); used to measure the kernel path without PCIe. */
 int crf_analyze_crops_device(crf_ctx* ctx, const uint8_t* d_bgr_batch, int n, int rows, int cols, crf_face_t* d_out, int headpose_only);
 
+/* ---- FaceForest::detectFace's box source (src/FaceForest.cpp:136-146): cv::CascadeClassifier::load on the reference's
+ * data/haarcascade_frontalface_alt.xml (new-format stump-based HAAR cascade) and detectMultiScale(img, boxes, search_scale_factor,
+ * min_neighbors, 0, Size(min_feature_size, min_feature_size)) with the cascade evaluated on the GPU.  The boxes are the RAW detections:
+ * the enlargement of src/FaceForest.cpp:147-157 is the caller's (crf_b200::FaceForest::detectFace does both).
+ * Returns the number of boxes (the first `cap` are written) or a negative status. */
+typedef struct crf_cascade crf_cascade;
+int crf_cascade_load(const char* path, crf_cascade** out);
+void crf_cascade_free(crf_cascade* c);
+int crf_cascade_info(const crf_cascade* c, int* win_w, int* win_h, int* nstages, int* nweak);
+int crf_detect_faces(crf_ctx* ctx, const crf_cascade* c, const uint8_t* bgr, int rows, int cols, size_t step, double scale_factor,
+                     int min_neighbors, int min_size, crf_rect_t* out, int cap);
+
 /* ---- several GPUs behind one caller: one context + one host thread per GPU, contiguous shards of the faces (cut at frame
  * boundaries when the boxes are grouped by frame), a forest replica per GPU, records written straight into `out`.  No collective:
  * faces are independent (FaceForest::analyzeImage's loop over faces, src/FaceForest.cpp:174-180).  devices NULL / n_devices 0 = every

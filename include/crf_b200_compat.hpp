@@ -14,9 +14,12 @@
 // otherwise layout-compatible stand-ins in namespace cvlite (the image this was built in has no OpenCV C++; tests/cpp compiles the
 // OpenCV branch against a stub <opencv2/core/core.hpp> so that it cannot rot).
 //
-// Deviations, all forced by "boxes are given"  and by the GPU context:
-//   * FaceForest::analyzeImage(img, faces) runs cv::CascadeClassifier only in the OpenCV build; analyzeImage(img, bboxes, faces)
-//     takes the boxes (the library analyses all faces of the frame in one launch).
+// Deviations:
+//   * FaceForest's constructor loads the face cascade only if fd_option.path_face_cascade is set (the reference requires it,
+//     src/FaceForest.cpp:23-28); without it analyzeImage(img, bboxes, faces) takes the boxes from the caller.  Either way all
+//     faces of a frame are analysed in one launch.
+//   * crf_b200::CascadeClassifier stands for cv::CascadeClassifier (load + detectMultiScale, evaluated on the GPU); it reads the
+//     new-format stump-based HAAR cascades, which is what the reference ships.
 //   * FaceForestOptions carries three extra members at its end (device, ms_mode, mean_shift_option).
 #ifndef CRF_B200_COMPAT_HPP
 #define CRF_B200_COMPAT_HPP
@@ -549,6 +552,39 @@ class MeanShift {
   }
 };
 
+// ------------------------------------------------------------------------------------------------ CascadeClassifier
+// cv::CascadeClassifier as FaceForest uses it (src/FaceForest.cpp:23, :145): load() + detectMultiScale(), the cascade evaluated on the GPU
+class CascadeClassifier {
+ public:
+  CascadeClassifier() {}
+  explicit CascadeClassifier(const std::string& filename) { load(filename); }
+  ~CascadeClassifier() { if (c_) crf_cascade_free(c_); }
+  CascadeClassifier(const CascadeClassifier&) = delete;
+  CascadeClassifier& operator=(const CascadeClassifier&) = delete;
+  bool empty() const { return c_ == nullptr; }
+  bool load(const std::string& filename) {
+    crf_cascade* n = nullptr;
+    if (crf_cascade_load(filename.c_str(), &n) != CRF_OK) return false;
+    if (c_) crf_cascade_free(c_);
+    c_ = n;
+    return true;
+  }
+  // min_size: cv::Size(min, min) of the reference's call
+  void detectMultiScale(const cvlite::Mat& image, std::vector<cvlite::Rect>& objects, double scaleFactor = 1.1, int minNeighbors = 3, int flags = 0, int min_size = 0) {
+    (void)flags;
+    if (!c_) throw std::logic_error("CascadeClassifier::detectMultiScale on an empty classifier");
+    if (image.channels() != 3) throw std::invalid_argument("detectMultiScale expects an 8-bit BGR image");
+    std::vector<crf_rect_t> r(256);
+    int n = crf_detect_faces(detail::plain_context(), c_, image.data, image.rows, image.cols, image.step, scaleFactor, minNeighbors, min_size, r.data(), (int)r.size());
+    check(n);
+    if (n > (int)r.size()) { r.resize((size_t)n); n = crf_detect_faces(detail::plain_context(), c_, image.data, image.rows, image.cols, image.step, scaleFactor, minNeighbors, min_size, r.data(), n); check(n); }
+    objects.clear();
+    for (int i = 0; i < n; i++) objects.push_back(cvlite::Rect(r[(size_t)i].x, r[(size_t)i].y, r[(size_t)i].width, r[(size_t)i].height));
+  }
+ private:
+  crf_cascade* c_ = nullptr;
+};
+
 // ------------------------------------------------------------------------------------------------ FaceForest
 // include/FaceForest.hpp:81-157, src/FaceForest.cpp
 class FaceForest {
@@ -564,6 +600,10 @@ class FaceForest {
   bool load(const FaceForestOptions& o) {
     is_inizialized = false;
     m_options = o;
+    if (!o.fd_option.path_face_cascade.empty()) {   // src/FaceForest.cpp:21-28
+      std::puts("Loading face cascade classifier");
+      if (!m_face_cascade.load(o.fd_option.path_face_cascade)) { std::fprintf(stderr, "(!) Error loading cascade classifier\n"); return false; }
+    }
     loaded_.reset(new detail::Loaded());
     loaded_->device = o.device;
     m_hp_forest = Forest<HeadPoseSample>(); m_mp_forest = Forest<MPSample>(); m_mp_jungle.clear();
@@ -637,7 +677,22 @@ class FaceForest {
     }
   }
 
-  // src/FaceForest.cpp:161-181 with the face boxes supplied by the caller: one launch for all faces of the frame
+  // include/FaceForest.hpp:118-126, src/FaceForest.cpp:136-159
+  static void detectFace(const cvlite::Mat& img, CascadeClassifier& face_cascade, FaceDetectionOption fd_option, std::vector<cvlite::Rect>& faces_bboxes) {
+    face_cascade.detectMultiScale(img, faces_bboxes, fd_option.search_scale_factor, fd_option.min_neighbors, 0, fd_option.min_feature_size);
+    enlargeDetections(img, faces_bboxes);   // the face detection boxes are too tight for us
+  }
+
+  // include/FaceForest.hpp:128-133, src/FaceForest.cpp:161-181: detect, then analyse every face (appended to `faces`)
+  void analyzeImage(cvlite::Mat img, std::vector<Face>& faces) {
+    require_init();
+    if (m_face_cascade.empty()) throw std::logic_error("analyzeImage(img, faces) needs fd_option.path_face_cascade; pass the boxes otherwise");
+    std::vector<cvlite::Rect> faces_bboxes;
+    detectFace(img, m_face_cascade, m_options.fd_option, faces_bboxes);
+    analyze(img, faces_bboxes, faces, true);
+  }
+
+  // the same with the face boxes supplied by the caller: one launch for all faces of the frame
   void analyzeImage(cvlite::Mat img, const std::vector<cvlite::Rect>& faces_bboxes, std::vector<Face>& faces) {
     require_init();
     analyze(img, faces_bboxes, faces, true);
@@ -695,6 +750,7 @@ class FaceForest {
     }
   }
   FaceForestOptions m_options;
+  CascadeClassifier m_face_cascade;
   std::shared_ptr<detail::Loaded> loaded_;
   Forest<HeadPoseSample> m_hp_forest;
   Forest<MPSample> m_mp_forest;

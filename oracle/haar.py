@@ -116,7 +116,7 @@ def detect_candidates(c: Cascade, gray: np.ndarray, scale_factor: float = 1.3, m
                 while ix < len(xs):
                     if alive[iy, ix]:
                         out.append((int(round(xs[ix] * factor)), int(round(ys[iy] * factor)), win[0], win[1]))
-                    if first_fail[iy, ix] or not ok[iy, ix]:
+                    if first_fail[iy, ix]:   # runAt() == 0 (rejected by the first stage): x += ystep once more; an invalid window returns -1
                         ix += 1
                     ix += 1
         factor *= scale_factor

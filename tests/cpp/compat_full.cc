@@ -156,6 +156,29 @@ int main(int argc, char** argv) {
   bool same = many.size() == 4 && many[0].headpose == face.headpose && many[3].headpose == face.headpose;
   for (size_t i = 0; same && i < 10; i++) same = many[0].ffd_cordinates[i].x == face.ffd_cordinates[i].x && many[3].ffd_cordinates[i].y == face.ffd_cordinates[i].y;
   std::printf("\nmulti.same %d\n", (int)same);
+  if (argc >= 5) {   // <cascade.xml> <image.ppm>: FaceForest::analyzeImage(img, faces) as the reference's demo calls it (detectFace + analyzeFace)
+    FILE* fp = std::fopen(argv[4], "rb");
+    int pw = 0, ph = 0, maxv = 0;
+    if (!fp || std::fscanf(fp, "P6 %d %d %d", &pw, &ph, &maxv) != 3) { std::puts("FAIL ppm"); return 1; }
+    std::fgetc(fp);
+    std::vector<unsigned char> rgb((size_t)pw * ph * 3), bgr((size_t)pw * ph * 3);
+    if (std::fread(rgb.data(), 1, rgb.size(), fp) != rgb.size()) { std::puts("FAIL ppm data"); return 1; }
+    std::fclose(fp);
+    for (size_t i = 0; i < rgb.size(); i += 3) { bgr[i] = rgb[i + 2]; bgr[i + 1] = rgb[i + 1]; bgr[i + 2] = rgb[i]; }
+    FaceForestOptions with_fd = ff_options;
+    with_fd.fd_option.path_face_cascade = argv[3];
+    FaceForest ffd(with_fd);
+    if (!ffd.is_inizialized) { std::puts("FAIL cascade init"); return 1; }
+    std::vector<Face> found;
+    ffd.analyzeImage(cvlite::Mat(ph, pw, CV_8UC3, bgr.data()), found);
+    std::printf("detect.faces %d", (int)found.size());
+    for (const Face& f : found) std::printf(" %d %d %d %d %.9g %d %d", f.bbox.x, f.bbox.y, f.bbox.width, f.bbox.height, f.headpose, f.ffd_cordinates[0].x, f.ffd_cordinates[0].y);
+    std::printf("\n");
+    FaceForestOptions bad_fd = ff_options;
+    bad_fd.fd_option.path_face_cascade = "/nonexistent/cascade.xml";
+    FaceForest ffb(bad_fd);
+    std::printf("detect.badcascade %d\n", (int)ffb.is_inizialized);
+  }
   std::printf("compat_full ok\n");
   return 0;
 }

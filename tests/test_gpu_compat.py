@@ -28,7 +28,15 @@ def test_reference_interface_in_cpp(crf, O, synth_dirs, synth_models, tmp_path, 
     subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", *flags, "-I", str(ROOT / "include"), str(ROOT / "tests" / "cpp" / "compat_full.cc"), "-o", str(exe),
                     "-L", str(capi.LIB_PATH.parent), "-lcrf_b200", f"-Wl,-rpath,{capi.LIB_PATH.parent}"], check=True)
     hp, ffd = synth_dirs
-    r = subprocess.run([str(exe), hp, ffd], capture_output=True, text=True)
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    extra = []
+    xml = wl.STAGED / "haarcascade_frontalface_alt.xml"
+    lfw = wl.load_lfw()
+    if xml.exists() and lfw:
+        import cv2
+        cv2.imwrite(str(tmp_path / "face.ppm"), lfw[0]["img"])
+        extra = [str(xml), str(tmp_path / "face.ppm")]
+    r = subprocess.run([str(exe), hp, ffd, *extra], capture_output=True, text=True)
     assert r.returncode == 0 and "compat_full ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     out = {}
     for line in r.stdout.split("\n"):
@@ -101,4 +109,13 @@ def test_reference_interface_in_cpp(crf, O, synth_dirs, synth_models, tmp_path, 
     ids = ef["leaf_ids"][33 * ny1 + 41]
     assert [int(v) for v in out["mp_forest.evaluateMT"]] == [int(_leaf(om, int(fi[k]), int(ti[k]), ids[k])[1]) for k in range(len(fi))]
     assert out["multi.same"] == ["1"]
+    if extra:   # analyzeImage(img, faces): GPU cascade -> enlarged box -> analyzeFace, against the oracle on the same box
+        from oracle import haar as H
+        d = out["detect.faces"]
+        assert d[0] == "1" and out["detect.badcascade"] == ["0"]
+        box = tuple(int(v) for v in d[1:5])
+        want_box = H.enlarge(H.detect_multi_scale(H.Cascade(str(xml)), lfw[0]["img"]), *lfw[0]["img"].shape[:2])[0]
+        assert box == want_box
+        w2 = om.analyze_face(lfw[0]["img"], box)
+        assert np.float32(d[5]) == w2["headpose"] and (int(d[6]), int(d[7])) == tuple(w2["ffd"][0])
     s.close()

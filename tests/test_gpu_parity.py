@@ -557,8 +557,8 @@ def test_cpp_eval_ffd_driver(crf, staged_models, lfw_faces, lfw_golden, gpu, tmp
         assert abs(float(pred) - float(lfw_golden["recs"][names.index(f["name"])]["headpose"])) < 1e-5
 
 
-def test_analyze_image_with_host_haar_detector(crf, staged_models, lfw_faces, gpu):
-    """FaceForest::analyzeImage as the reference runs it: Haar cascade on the host (cv2), enlarged boxes, GPU pipeline."""
+def test_analyze_image_with_the_cascade_detector(crf, staged_models, lfw_faces, gpu):
+    """FaceForest::analyzeImage as the reference runs it: Haar cascade (evaluated on the GPU), enlarged boxes, GPU pipeline."""
     from face_alignment_cvpr_2012_b200 import workloads as wl
     xml = wl.STAGED / "haarcascade_frontalface_alt.xml"
     if not xml.exists():
