@@ -165,9 +165,10 @@ struct crf_ctx {
   // units (fp32 issue for the Gabor bank, L1/L2 gathers for the forests, latency for the sequential folds) overlap
   struct WorkSet {
     cudaStream_t stream = nullptr;
+    Buf d_gabor_scratch, d_gabor_counters;
     Buf d_scaled, d_stacks, d_mag, d_minmax, d_hp_leaf, d_ffd_leaf, d_face_roots, d_face_ntrees, d_votes, d_vote_counts, d_vote_base, d_seg_counts, d_u8planes, d_int32;
     size_t scaled_fs = 0, stack_fs = 0, plane_stride = 0, mag_fs = 0, mag_ps = 0, hp_leaf_fs = 0, ffd_leaf_fs = 0, vote_cap = 0, u8_fs = 0;
-    Buf* all[14] = {&d_scaled, &d_stacks, &d_mag, &d_minmax, &d_hp_leaf, &d_ffd_leaf, &d_face_roots, &d_face_ntrees, &d_votes, &d_vote_counts, &d_vote_base,
+    Buf* all[16] = {&d_gabor_scratch, &d_gabor_counters, &d_scaled, &d_stacks, &d_mag, &d_minmax, &d_hp_leaf, &d_ffd_leaf, &d_face_roots, &d_face_ntrees, &d_votes, &d_vote_counts, &d_vote_base,
                     &d_seg_counts, &d_u8planes, &d_int32};
   };
   WorkSet ws[2];
@@ -184,6 +185,11 @@ struct crf_ctx {
   // 1 = consecutive chunks run back to back on one stream (default: measured faster — co-resident Gabor CTAs shrink the L1
   // the gathers live on, and two chunks' stacks thrash L2); 2 = alternate chunks between two streams / work sets
   int nstreams = 1;
+  // CRF_GABOR_FUSED=1: the fused per-scale Gabor kernels (k_gabor_fused: rolling row pass, magnitudes in an L2-resident scratch, quantisation in
+  // the same kernel).  Bit-identical and MEASURED SLOWER on B200 (30.4 vs 22.3 ms per 4096 faces: the serial phases of a CTA that owns a whole
+  // plane cost more than the 27 % of multiply-adds and the 18 GB of DRAM traffic it saves), so the banded kernels stay the default.
+  int gabor_fused = 0;
+  int gabor_quant_old = 0;   // CRF_GABOR_QUANT_OLD=1: k_gabor_quant_integral (one column per thread) instead of k_gabor_quant_band
   int ms_mode = CRF_MS_FAST;   // resolved from crf_options_t::ms_mode / CRF_MS_MODE at creation
   int ms_variant = 3;   // resident MeanShift CTAs per SM the kernel is compiled for (register cap); CRF_MS_VARIANT overrides
   size_t work_budget = (size_t)64 << 30;  // bytes of work buffers a launch may use (min(64 GB, half of the free memory at creation))
@@ -249,7 +255,7 @@ static int ensure(crf_ctx* c, const Plan& p) {
   if ((rc = c->w->d_scaled.reserve(n * c->w->scaled_fs))) return rc;
   if ((rc = c->w->d_stacks.reserve(n * c->w->stack_fs * sizeof(stack_t)))) return rc;
   if (p.want_u8 && (rc = c->w->d_int32.reserve(n * c->w->stack_fs * 4))) return rc;
-  if (p.need_gabor) {
+  if (p.need_gabor && !c->gabor_fused) {   // the fused kernels keep their magnitudes in a per-CTA scratch (launch_channels)
     if ((rc = c->w->d_mag.reserve(n * c->w->mag_fs * 4))) return rc;
     if ((rc = c->w->d_minmax.reserve(n * 35 * 2 * 4))) return rc;
   }
@@ -323,10 +329,31 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, cons
   }
   if (L.gabor_first < 0) return CRF_OK;
   Span s(c, CRF_STAGE_GABOR);
+  const uint8_t* sc = c->w->d_scaled.as<uint8_t>();
+  if (c->gabor_fused) {
+    // one persistent launch per scale: (face) items from a counter, magnitudes through a per-CTA scratch slot that stays in L2
+    const int grid = std::min(n, c->sm_count * 3);
+    const size_t plane = (size_t)Hmax * 128;
+    int rc;
+    if ((rc = c->w->d_gabor_scratch.reserve((size_t)c->sm_count * 3 * 2 * plane * 4)) || (rc = c->w->d_gabor_counters.reserve(8 * 4))) return rc;
+    CU(cudaMemsetAsync(c->w->d_gabor_counters.p, 0, 8 * 4, c->w->stream));
+    GaborFusedArgs g{};
+    g.fd = fd; g.nfaces = n; g.scaled = sc; g.scaled_face_stride = c->w->scaled_fs;
+    g.scratch = c->w->d_gabor_scratch.as<float>(); g.scratch_plane_stride = plane;
+    g.stacks = c->w->d_stacks.as<stack_t>(); g.stack_face_stride = c->w->stack_fs; g.plane_stride = c->w->plane_stride; g.first_plane = L.gabor_first;
+    g.u8planes = u8; g.u8_face_stride = c->w->u8_fs; g.dbg32 = dbg32;
+    int* cnt = c->w->d_gabor_counters.as<int>();
+    g.counter = cnt + 4; k_gabor_fused<25><<<grid, 256, GaborSepSmem<25>::bytes, c->w->stream>>>(g, c->d_coef_sep[4].as<float>(), 4); KCHECK();
+    g.counter = cnt + 3; k_gabor_fused<19><<<grid, 256, GaborSepSmem<19>::bytes, c->w->stream>>>(g, c->d_coef_sep[3].as<float>(), 3); KCHECK();
+    g.counter = cnt + 2; k_gabor_fused<13><<<grid, 256, GaborSepSmem<13>::bytes, c->w->stream>>>(g, c->d_coef_sep[2].as<float>(), 2); KCHECK();
+    g.counter = cnt + 1; k_gabor_fused<9><<<grid, 256, GaborSepSmem<9>::bytes, c->w->stream>>>(g, c->d_coef_sep[1].as<float>(), 1); KCHECK();
+    g.counter = cnt + 0; k_gabor_fused7<<<std::min(n, c->sm_count * 2), 256, 0, c->w->stream>>>(g, c->d_coef[0].as<float2>()); KCHECK();
+    count_launch(c, CRF_STAGE_GABOR, 5);
+    return CRF_OK;
+  }
   k_init_minmax<<<(n * 70 + 255) / 256, 256, 0, c->w->stream>>>(c->w->d_minmax.as<uint32_t>(), n * 70);
   KCHECK();
   const dim3 grid((Hmax + 15) / 16, 7, n);
-  const uint8_t* sc = c->w->d_scaled.as<uint8_t>();
   float* mag = c->w->d_mag.as<float>();
   uint32_t* mm = c->w->d_minmax.as<uint32_t>();
   const dim3 gsym((Hmax + 15) / 16, n);
@@ -336,8 +363,17 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, cons
   k_gabor_sep<13><<<gsym, 256, GaborSepSmem<13>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[2].as<float>(), 2, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
   k_gabor_sep<9><<<gsym, 256, GaborSepSmem<9>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[1].as<float>(), 1, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
   k_gabor_mag<7><<<grid, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef[0].as<float2>(), 0, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
-  k_gabor_quant_integral<<<dim3(35, n), 128, 0, c->w->stream>>>(fd, mag, c->w->mag_fs, c->w->mag_ps, mm, c->w->d_stacks.as<stack_t>(), c->w->stack_fs, c->w->plane_stride, L.gabor_first,
-                                                             u8, c->w->u8_fs, dbg32);
+  {
+    GaborFusedArgs g{};
+    g.fd = fd; g.nfaces = n;
+    g.stacks = c->w->d_stacks.as<stack_t>(); g.stack_face_stride = c->w->stack_fs; g.plane_stride = c->w->plane_stride; g.first_plane = L.gabor_first;
+    g.u8planes = u8; g.u8_face_stride = c->w->u8_fs; g.dbg32 = dbg32;
+    if (c->gabor_quant_old)
+      k_gabor_quant_integral<<<dim3(35, n), 128, 0, c->w->stream>>>(fd, mag, c->w->mag_fs, c->w->mag_ps, mm, c->w->d_stacks.as<stack_t>(), c->w->stack_fs, c->w->plane_stride, L.gabor_first,
+                                                                 u8, c->w->u8_fs, dbg32);
+    else
+      k_gabor_quant_band<<<dim3(35, n), 256, 0, c->w->stream>>>(g, mag, c->w->mag_fs, c->w->mag_ps, mm);
+  }
   KCHECK(); count_launch(c, CRF_STAGE_GABOR, 7);
   return CRF_OK;
 }
@@ -514,7 +550,7 @@ static int pick_chunk(const crf_ctx* c, int Hmax, bool headpose_only) {
   const size_t np_ffd = headpose_only ? 0 : (size_t)patches_1d(125, c->opt.ffd_stride) * patches_1d(Hmax, c->opt.ffd_stride);
   // the same terms ensure() reserves per face
   const size_t per_face = (size_t)Hmax * 128 + (size_t)(Hmax + 1) * kRowStride * sizeof(stack_t) * c->layout.nplanes +
-                          (c->layout.gabor_first >= 0 ? (size_t)Hmax * 128 * 4 * 35 + 35 * 2 * 4 : 0) + np_hp * c->hp_ntrees * 4 +
+                          (c->layout.gabor_first >= 0 && !c->gabor_fused ? (size_t)Hmax * 128 * 4 * 35 + 35 * 2 * 4 : 0) + np_hp * c->hp_ntrees * 4 +
                           np_ffd * c->mp_ntrees_cfg * (4 + 3 * sizeof(DevVote)) + (size_t)kMaxList * 4 + 4 +
                           (headpose_only ? 0 : (size_t)kVoteSegs * kParts * 4 + 2 * kParts * 4) + sizeof(FaceDesc) + sizeof(crf_face_t);
   const size_t budget = c->work_budget / c->nstreams;
@@ -1077,6 +1113,8 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if (const char* v = std::getenv("CRF_WIN_TEX")) c->win_tex = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_WIN_HP")) c->win_hp = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_WIN_FFD")) c->win_ffd = (int)std::strtol(v, nullptr, 0);
+  if (const char* v = std::getenv("CRF_GABOR_FUSED")) c->gabor_fused = (int)std::strtol(v, nullptr, 0);
+  if (const char* v = std::getenv("CRF_GABOR_QUANT_OLD")) c->gabor_quant_old = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_MS_VARIANT")) c->ms_variant = (int)std::strtol(v, nullptr, 0);
   c->ms_mode = c->opt.ms_mode == CRF_MS_EXACT ? CRF_MS_EXACT : CRF_MS_FAST;
   if (c->opt.ms_mode == CRF_MS_DEFAULT)
@@ -1179,6 +1217,10 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   CU(cudaFuncSetAttribute(k_gabor_sep<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<19>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_sep<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<13>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_sep<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<9>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_fused<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<25>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_fused<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<19>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_fused<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<13>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_fused<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<9>::bytes));
   if (const char* v = std::getenv("CRF_CARVEOUT")) {   // experiment: shared-memory carveout (percent) of the traversal kernels
     const int pct = (int)std::strtol(v, nullptr, 0);
     CU(cudaFuncSetAttribute(k_traverse16<10, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));

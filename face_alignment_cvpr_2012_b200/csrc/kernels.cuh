@@ -76,15 +76,20 @@ __global__ void __launch_bounds__(128) k_gray_resize(const FaceDesc* __restrict_
 // stack_t (device_forest.h).  out: (H+1) rows x kRowStride elements.  u8out (optional): dense H x W copy of the
 // 8-bit plane; out32 (optional): the full 32-bit integral, same pitch (stage API / parity tests).
 // ---------------------------------------------------------------------------------------------
-template <class PixFn>
-__device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, stack_t* __restrict__ out, uint8_t* __restrict__ u8out, uint32_t* __restrict__ out32) {
-  __shared__ __align__(16) uint32_t band[32][kRowStride];
+// NT = threads of the CTA (a multiple of 128): the first 128 own the columns, every warp takes part in the row scans.
+template <int NT, class PixFn>
+__device__ __forceinline__ void integral_plane_in(uint32_t (*band)[kRowStride] /* shared memory, 32 rows */, PixFn pix, int W, int H, stack_t* __restrict__ out,
+                                                  uint8_t* __restrict__ u8out, uint32_t* __restrict__ out32) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  out[tid] = 0;  // row 0
-  if (out32) out32[tid] = 0;
+  const bool col = tid < kRowStride;
+  if (col) {
+    out[tid] = 0;  // row 0
+    if (out32) out32[tid] = 0;
+  }
   uint32_t run = 0;
   for (int r0 = 0; r0 < H; r0 += 32) {
     const int nr = min(32, H - r0);
+    if (col)
     for (int r = 0; r < nr; r++) {
       uint32_t p = 0;
       if (tid < W) {
@@ -95,7 +100,7 @@ __device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, stack_t*
       band[r][tid] = run;
     }
     __syncthreads();
-    for (int r = warp; r < nr; r += 4) {
+    for (int r = warp; r < nr; r += NT / 32) {
       uint4 v = *reinterpret_cast<uint4*>(&band[r][lane * 4]);
       v.y += v.x; v.z += v.y; v.w += v.z;
       uint32_t incl = v.w;
@@ -109,13 +114,19 @@ __device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, stack_t*
       *reinterpret_cast<uint4*>(&band[r][lane * 4]) = v;
     }
     __syncthreads();
-    for (int r = 0; r < nr; r++) {  // I[y+1][x+1] = sum; column 0 stays zero
-      const uint32_t v = tid == 0 ? 0u : band[r][tid - 1];
-      out[(size_t)(r0 + r + 1) * kRowStride + tid] = (stack_t)v;   // truncates only in the 16-bit layout (device_forest.h)
-      if (out32) out32[(size_t)(r0 + r + 1) * kRowStride + tid] = v;
+    for (int i = tid; i < nr * kRowStride; i += NT) {  // I[y+1][x+1] = sum; column 0 stays zero
+      const int r = i / kRowStride, c = i - r * kRowStride;
+      const uint32_t v = c == 0 ? 0u : band[r][c - 1];
+      out[(size_t)(r0 + r + 1) * kRowStride + c] = (stack_t)v;   // truncates only in the 16-bit layout (device_forest.h)
+      if (out32) out32[(size_t)(r0 + r + 1) * kRowStride + c] = v;
     }
     __syncthreads();
   }
+}
+template <int NT = 128, class PixFn>
+__device__ __forceinline__ void integral_plane(PixFn pix, int W, int H, stack_t* __restrict__ out, uint8_t* __restrict__ u8out, uint32_t* __restrict__ out32) {
+  __shared__ __align__(16) uint32_t band[32][kRowStride];
+  integral_plane_in<NT>(band, pix, W, H, out, u8out, out32);
 }
 
 // a5 + a7 (+ a7b): FC_GRAY, FC_SOBEL (d/dy then d/dx, 8U-saturated), FC_MIN_MAX
@@ -554,6 +565,410 @@ __global__ void __launch_bounds__(128) k_gabor_quant_integral(const FaceDesc* __
     const int iv = __float2int_rn(__fmul_rn(v, 255.f));
     return (uint32_t)min(max(iv, 0), 255);
   }, d.W, d.H, out, u8o, o32);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a6, whole: one scale of the Gabor bank for one face per work item, fused with normalize / convertTo / integral
+// (FeatureChannelFactory.hpp:253-283).  Same arithmetic, bit for bit, as k_gabor_sep / k_gabor_mag<7> + k_gabor_quant_integral
+// (every output is the same sequence of fmaf over the same operands), re-organised around three facts:
+//   * the row pass of a padded row does not depend on the band that needs it: bands of 16 output rows are walked top to bottom and
+//     only the 16 new rows are filtered, the K - 1 rows a band shares with the previous one are kept (moved to the top of the ring).
+//     Row-pass work drops from 8 x (16 + K - 1) to H + K - 1 rows per plane (-27 % of all multiply-adds of the separable scales);
+//   * a magnitude plane is consumed by its own CTA as soon as its minimum and maximum are known, so it never needs to reach DRAM:
+//     it is written to a per-CTA scratch slot (2 planes per resident CTA, ~57 MB for the whole GPU, L2-resident and overwritten
+//     plane after plane) and read back for the quantisation, instead of an 18 GB round trip through a per-face scratch;
+//   * min / max are CTA-local: no atomics, no initialisation kernel.
+// Persistent CTAs fetch (face) items from a global counter.  grid = min(items, SMs x 3), 256 threads.
+// scratch: [gridDim.x][2][Hcap][128] f32 (plane 0: Gaussian term of the scale, plane 1: magnitudes of the current orientation).
+// ---------------------------------------------------------------------------------------------
+struct GaborFusedArgs {
+  const FaceDesc* fd; int nfaces;
+  const uint8_t* scaled; size_t scaled_face_stride;
+  float* scratch; size_t scratch_plane_stride;   // Hcap * 128
+  stack_t* stacks; size_t stack_face_stride, plane_stride; int first_plane;
+  uint8_t* u8planes; size_t u8_face_stride; uint32_t* dbg32;
+  int* counter;
+};
+
+// min / max of the CTA's valid magnitudes -> the scale and shift of cv::normalize(NORM_MINMAX, 0, 1) (as k_gabor_quant_integral)
+__device__ __forceinline__ void gabor_minmax_to_affine(float vmin, float vmax, float& a, float& b) {
+  __shared__ uint32_t s_mn[8], s_mx[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t umin = __reduce_min_sync(0xffffffffu, __float_as_uint(vmin)), umax = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+  __syncthreads();   // the previous plane's readers are done with s_mn / s_mx
+  if (lane == 0) { s_mn[warp] = umin; s_mx[warp] = umax; }
+  __syncthreads();
+  uint32_t mn = s_mn[0], mx = s_mx[0];
+#pragma unroll
+  for (int j = 1; j < 8; j++) { mn = min(mn, s_mn[j]); mx = max(mx, s_mx[j]); }
+  const double smin = (double)__uint_as_float(mn), smax = (double)__uint_as_float(mx);
+  const double dscale = (smax - smin) > 2.220446049250313e-16 ? 1. / (smax - smin) : 0.;
+  const double dshift = 0.0 - smin * dscale;
+  a = (float)dscale; b = (float)dshift;
+}
+
+// cv::normalize + convertTo(8U, x255) + cv::integral of a magnitude plane held in the CTA's scratch slot, by all 256 threads:
+// a 32-row band is quantised cooperatively (independent float4 loads: the scratch sits in L2, and a per-column loop over dependent
+// loads would serialise on its latency), then 128 threads run the column sums out of shared memory, the warps scan the rows, and
+// the band is written with coalesced rows.  band: 16 KB of shared memory the caller does not need meanwhile (its filter ring).
+__device__ __forceinline__ void gabor_quantise_plane(const GaborFusedArgs& g, int f, const FaceDesc& d, int gp, const float* __restrict__ mplane, float a, float b,
+                                                     uint32_t (*band)[kRowStride]) {
+  const int plane = g.first_plane + gp;
+  stack_t* __restrict__ out = g.stacks + f * g.stack_face_stride + (size_t)plane * g.plane_stride;
+  uint8_t* __restrict__ u8o = g.u8planes ? g.u8planes + f * g.u8_face_stride + (size_t)plane * d.W * d.H : nullptr;
+  uint32_t* __restrict__ o32 = g.dbg32 ? g.dbg32 + f * g.stack_face_stride + (size_t)plane * g.plane_stride : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = d.W, H = d.H;
+  if (tid < kRowStride) { out[tid] = 0; if (o32) o32[tid] = 0; }   // row 0
+  uint32_t run = 0;
+  for (int r0 = 0; r0 < H; r0 += 32) {
+    const int nr = min(32, H - r0);
+    for (int i = tid; i < nr * 32; i += 256) {
+      const int r = i >> 5, c = (i & 31) * 4;
+      const float4 m = *reinterpret_cast<const float4*>(&mplane[(size_t)(r0 + r) * 128 + c]);   // this CTA's own stores: coherent load
+      const float mv[4] = {m.x, m.y, m.z, m.w};
+      uint32_t q[4];
+#pragma unroll
+      for (int o = 0; o < 4; o++) {
+        const int iv = __float2int_rn(__fmul_rn(__fmaf_rn(mv[o], a, b), 255.f));
+        q[o] = c + o < W ? (uint32_t)min(max(iv, 0), 255) : 0u;
+        if (u8o && c + o < W) u8o[(size_t)(r0 + r) * W + c + o] = (uint8_t)q[o];
+      }
+      *reinterpret_cast<uint4*>(&band[r][c]) = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+    __syncthreads();
+    if (tid < kRowStride) {
+#pragma unroll 8
+      for (int r = 0; r < nr; r++) { run += band[r][tid]; band[r][tid] = run; }
+    }
+    __syncthreads();
+    for (int r = warp; r < nr; r += 8) {
+      uint4 v = *reinterpret_cast<uint4*>(&band[r][lane * 4]);
+      v.y += v.x; v.z += v.y; v.w += v.z;
+      uint32_t incl = v.w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      const uint32_t excl = incl - v.w;
+      v.x += excl; v.y += excl; v.z += excl; v.w += excl;
+      *reinterpret_cast<uint4*>(&band[r][lane * 4]) = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < nr * kRowStride; i += 256) {   // I[y+1][x+1] = sum; column 0 stays zero
+      const int r = i / kRowStride, c = i - r * kRowStride;
+      const uint32_t v = c == 0 ? 0u : band[r][c - 1];
+      out[(size_t)(r0 + r + 1) * kRowStride + c] = (stack_t)v;
+      if (o32) o32[(size_t)(r0 + r + 1) * kRowStride + c] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// a6, second half for the banded kernels (k_gabor_sep / k_gabor_mag<7>): the per-plane minimum and maximum they reduced with atomics
+// give the affine map of cv::normalize; quantisation and integral as above.  Replaces k_gabor_quant_integral, whose one-column-per-
+// thread loop over dependent magnitude loads ran at the DRAM latency (4.2 ms for 143 360 planes; this one is bandwidth-bound).
+// grid = (35, faces), 256 threads.
+__global__ void __launch_bounds__(256) k_gabor_quant_band(GaborFusedArgs g, const float* __restrict__ mag, size_t mag_face_stride, size_t mag_plane_stride,
+                                                          const uint32_t* __restrict__ minmax) {
+  __shared__ __align__(16) uint32_t s_band[32][kRowStride];
+  const int f = blockIdx.y, gp = blockIdx.x;
+  const FaceDesc d = g.fd[f];
+  const uint32_t* mm = minmax + ((size_t)f * 35 + gp) * 2;
+  const double smin = (double)__uint_as_float(mm[0]), smax = (double)__uint_as_float(mm[1]);
+  const double dscale = (smax - smin) > 2.220446049250313e-16 ? 1. / (smax - smin) : 0.;
+  const double dshift = 0.0 - smin * dscale;
+  gabor_quantise_plane(g, f, d, gp, mag + f * mag_face_stride + (size_t)gp * mag_plane_stride, (float)dscale, (float)dshift, s_band);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, 3) k_gabor_fused(GaborFusedArgs g, const float* __restrict__ coef, int nu) {
+  using G = GaborGeom<K>;
+  constexpr int R = K / 2, TH = G::TH, PITCH = G::PITCH, NEW = G::BAND;   // TH = 16 + K - 1 is even
+  extern __shared__ __align__(16) float s_gs[];
+  float (*tile)[PITCH] = reinterpret_cast<float (*)[PITCH]>(s_gs);
+  float (*rre)[128] = reinterpret_cast<float (*)[128]>(s_gs + TH * PITCH);
+  float (*rim)[128] = rre + TH;
+  float* cf = s_gs + TH * PITCH + 2 * TH * 128;
+  const float2* hx = reinterpret_cast<const float2*>(cf);      // [7][K]
+  const float2* hy = hx + 7 * K;                               // [7][K]
+  const float* g1 = cf + 7 * K * 4;                            // [K]
+  __shared__ int s_item;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < GaborSepSmem<K>::NCOEF; i += 256) cf[i] = coef[i];
+  __syncthreads();
+  const float dc = cf[7 * K * 4 + K];
+  const int x0 = (tid & 31) * 4, q2 = (tid >> 5) * 2;
+  float* gplane = g.scratch + (size_t)blockIdx.x * 2 * g.scratch_plane_stride;
+  float* mplane = gplane + g.scratch_plane_stride;
+
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(g.counter, 1);
+    __syncthreads();
+    const int f = s_item;
+    if (f >= g.nfaces) break;
+    const FaceDesc d = g.fd[f];
+    const int W = d.W, H = d.H;
+    const uint8_t* __restrict__ gray = g.scaled + f * g.scaled_face_stride;
+    const int nbands = (H + NEW - 1) / NEW;
+
+    // rows [first, first + n) of the ring <- REFLECT_101-padded gray rows starting at padded row p0 (as float, with the halo columns)
+    auto load_tile = [&](int first, int n, int p0) {
+      for (int i = tid; i < n * PITCH; i += 256) {
+        const int ty = i / PITCH, tx = i - ty * PITCH;
+        tile[first + ty][tx] = (float)gray[(size_t)border101(p0 + ty, H) * 128 + border101(tx - R, W)];
+      }
+    };
+    // ================= the Gaussian term of this scale: G plane (shared by the 7 orientations)
+    for (int band = 0; band < nbands; band++) {
+      const int r0 = band * NEW;
+      const int first = band == 0 ? 0 : K - 1, nrows = band == 0 ? TH : NEW;
+      if (band > 0) {
+        // moving rows down by NEW inside one array: sources [NEW, TH) and destinations [0, K - 1) overlap when K - 1 > NEW, so the
+        // move goes through registers with a barrier between all loads and all stores
+        float4 keep[((K - 1) * 32 + 255) / 256];
+#pragma unroll
+        for (int j = 0; j < ((K - 1) * 32 + 255) / 256; j++) { const int i = tid + j * 256; if (i < (K - 1) * 32) keep[j] = *reinterpret_cast<const float4*>(&rre[NEW + (i >> 5)][(i & 31) * 4]); }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ((K - 1) * 32 + 255) / 256; j++) { const int i = tid + j * 256; if (i < (K - 1) * 32) *reinterpret_cast<float4*>(&rre[i >> 5][(i & 31) * 4]) = keep[j]; }
+      }
+      load_tile(first, nrows, r0 - R + first);
+      __syncthreads();
+      // row pass: pairs of rows (r, r + nrows / 2) share every coefficient load
+      for (int it = tid; it < (nrows / 2) * 32; it += 256) {
+        const int r = first + (it >> 5), xs = (it & 31) * 4, hstep = nrows / 2;
+        float px[2][4 * G::NF4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const float4* row = reinterpret_cast<const float4*>(&tile[r + h * hstep][xs]);
+#pragma unroll
+          for (int q = 0; q < G::NF4; q++) { const float4 v = row[q]; px[h][4 * q] = v.x; px[h][4 * q + 1] = v.y; px[h][4 * q + 2] = v.z; px[h][4 * q + 3] = v.w; }
+        }
+        float a[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+          const float c = g1[i];
+#pragma unroll
+          for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int o = 0; o < 4; o++) a[h][o] = __fmaf_rn(px[h][o + i], c, a[h][o]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) *reinterpret_cast<float4*>(&rre[r + h * hstep][xs]) = make_float4(a[h][0], a[h][1], a[h][2], a[h][3]);
+      }
+      __syncthreads();
+      float Gs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      {
+        float cprev = 0.f;
+#pragma unroll 2
+        for (int t = 0; t <= K; t++) {
+          const float4 v = *reinterpret_cast<const float4*>(&rre[q2 + t][x0]);
+          const float c = t < K ? g1[t] : 0.f;
+          if (t < K) { Gs[0][0] = __fmaf_rn(v.x, c, Gs[0][0]); Gs[0][1] = __fmaf_rn(v.y, c, Gs[0][1]); Gs[0][2] = __fmaf_rn(v.z, c, Gs[0][2]); Gs[0][3] = __fmaf_rn(v.w, c, Gs[0][3]); }
+          if (t > 0) { Gs[1][0] = __fmaf_rn(v.x, cprev, Gs[1][0]); Gs[1][1] = __fmaf_rn(v.y, cprev, Gs[1][1]); Gs[1][2] = __fmaf_rn(v.z, cprev, Gs[1][2]); Gs[1][3] = __fmaf_rn(v.w, cprev, Gs[1][3]); }
+          cprev = c;
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int r = r0 + q2 + h;
+        if (r < H) *reinterpret_cast<float4*>(&gplane[(size_t)r * 128 + x0]) = make_float4(Gs[h][0], Gs[h][1], Gs[h][2], Gs[h][3]);
+      }
+      __syncthreads();   // the column pass is done with the ring before the next band moves it
+    }
+
+    // ================= the 7 orientations
+#pragma unroll 1
+    for (int mu = 0; mu < 7; mu++) {
+      const float2* hxm = hx + mu * K;
+      const float2* hym = hy + mu * K;
+      float vmin = __int_as_float(0x7f800000), vmax = 0.f;
+#pragma unroll 1
+      for (int band = 0; band < nbands; band++) {
+        const int r0 = band * NEW;
+        const int first = band == 0 ? 0 : K - 1, nrows = band == 0 ? TH : NEW;
+        if (band > 0) {
+          float4 ka[((K - 1) * 32 + 255) / 256], kb[((K - 1) * 32 + 255) / 256];
+#pragma unroll
+          for (int j = 0; j < ((K - 1) * 32 + 255) / 256; j++) {
+            const int i = tid + j * 256;
+            if (i < (K - 1) * 32) { ka[j] = *reinterpret_cast<const float4*>(&rre[NEW + (i >> 5)][(i & 31) * 4]); kb[j] = *reinterpret_cast<const float4*>(&rim[NEW + (i >> 5)][(i & 31) * 4]); }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < ((K - 1) * 32 + 255) / 256; j++) {
+            const int i = tid + j * 256;
+            if (i < (K - 1) * 32) { *reinterpret_cast<float4*>(&rre[i >> 5][(i & 31) * 4]) = ka[j]; *reinterpret_cast<float4*>(&rim[i >> 5][(i & 31) * 4]) = kb[j]; }
+          }
+        }
+        load_tile(first, nrows, r0 - R + first);
+        __syncthreads();
+#pragma unroll 1
+        for (int it = tid; it < (nrows / 2) * 32; it += 256) {
+          const int r = first + (it >> 5), xs = (it & 31) * 4, hstep = nrows / 2;
+          float px[2][4 * G::NF4];
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const float4* row = reinterpret_cast<const float4*>(&tile[r + h * hstep][xs]);
+#pragma unroll
+            for (int q = 0; q < G::NF4; q++) { const float4 v = row[q]; px[h][4 * q] = v.x; px[h][4 * q + 1] = v.y; px[h][4 * q + 2] = v.z; px[h][4 * q + 3] = v.w; }
+          }
+          float a[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, b[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+          for (int i = 0; i < K; i++) {
+            const float2 c = hxm[i];
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+              for (int o = 0; o < 4; o++) { a[h][o] = __fmaf_rn(px[h][o + i], c.x, a[h][o]); b[h][o] = __fmaf_rn(px[h][o + i], c.y, b[h][o]); }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            *reinterpret_cast<float4*>(&rre[r + h * hstep][xs]) = make_float4(a[h][0], a[h][1], a[h][2], a[h][3]);
+            *reinterpret_cast<float4*>(&rim[r + h * hstep][xs]) = make_float4(b[h][0], b[h][1], b[h][2], b[h][3]);
+          }
+        }
+        __syncthreads();
+        float re[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, im[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        {
+          float2 cprev = make_float2(0.f, 0.f);
+#pragma unroll 2
+          for (int t = 0; t <= K; t++) {
+            const float4 a = *reinterpret_cast<const float4*>(&rre[q2 + t][x0]);
+            const float4 b = *reinterpret_cast<const float4*>(&rim[q2 + t][x0]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            const float2 c = t < K ? hym[t] : make_float2(0.f, 0.f);
+            if (t < K) {
+#pragma unroll
+              for (int o = 0; o < 4; o++) {
+                re[0][o] = __fmaf_rn(av[o], c.x, re[0][o]); re[0][o] = __fmaf_rn(-bv[o], c.y, re[0][o]);
+                im[0][o] = __fmaf_rn(av[o], c.y, im[0][o]); im[0][o] = __fmaf_rn(bv[o], c.x, im[0][o]);
+              }
+            }
+            if (t > 0) {
+#pragma unroll
+              for (int o = 0; o < 4; o++) {
+                re[1][o] = __fmaf_rn(av[o], cprev.x, re[1][o]); re[1][o] = __fmaf_rn(-bv[o], cprev.y, re[1][o]);
+                im[1][o] = __fmaf_rn(av[o], cprev.y, im[1][o]); im[1][o] = __fmaf_rn(bv[o], cprev.x, im[1][o]);
+              }
+            }
+            cprev = c;
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int r = r0 + q2 + h;
+          if (r < H) {
+            const float4 gq = *reinterpret_cast<const float4*>(&gplane[(size_t)r * 128 + x0]);   // this CTA's own earlier stores
+            const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+            float m[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+              const float rr = __fmaf_rn(-dc, gv[o], re[h][o]);
+              m[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[h][o], im[h][o]), __fmul_rn(rr, rr)));
+              if (x0 + o < W) { vmin = fminf(vmin, m[o]); vmax = fmaxf(vmax, m[o]); }
+            }
+            *reinterpret_cast<float4*>(&mplane[(size_t)r * 128 + x0]) = make_float4(m[0], m[1], m[2], m[3]);
+          }
+        }
+        __syncthreads();   // ring free for the next band; the magnitudes of this band are visible to the CTA
+      }
+      float a, b;
+      gabor_minmax_to_affine(vmin, vmax, a, b);
+      static_assert(((size_t)TH * PITCH + 2 * (size_t)TH * 128) * sizeof(float) >= 32 * kRowStride * sizeof(uint32_t), "tile + ring (not the coefficients behind them) are lent to the integral scan");
+      gabor_quantise_plane(g, f, d, nu * 7 + mu, mplane, a, b, reinterpret_cast<uint32_t (*)[kRowStride]>(s_gs));
+    }
+  }
+}
+
+// The 7 x 7 scale the same way: the direct raster sum of k_gabor_mag<7> (== cv2's filter2D), magnitudes to the CTA's scratch
+// slot, CTA-local min / max, quantise + integral.  One item = one face; 256 threads, 16-row bands.
+__global__ void __launch_bounds__(256, 2) k_gabor_fused7(GaborFusedArgs g, const float2* __restrict__ coef /* [7][49] (re, im) raster order */) {
+  constexpr int K = 7, KP = K + 1;
+  using G = GaborGeom<K>;
+  __shared__ __align__(16) float tile[G::TH][G::PITCH];
+  __shared__ __align__(16) float2 cf[K][KP];
+  __shared__ __align__(16) uint32_t s_band[32][kRowStride];
+  __shared__ int s_item;
+  const int tid = threadIdx.x;
+  float* mplane = g.scratch + ((size_t)blockIdx.x * 2 + 1) * g.scratch_plane_stride;
+  const int x0 = (tid & 31) * 4, rA = tid >> 5;
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(g.counter, 1);
+    __syncthreads();
+    const int f = s_item;
+    if (f >= g.nfaces) break;
+    const FaceDesc d = g.fd[f];
+    const int W = d.W, H = d.H;
+    const uint8_t* __restrict__ gray = g.scaled + f * g.scaled_face_stride;
+#pragma unroll 1
+    for (int mu = 0; mu < 7; mu++) {
+      __syncthreads();   // cf / tile of the previous plane are no longer read
+      for (int i = tid; i < K * KP; i += 256) {
+        const int jj = i / KP, ii = i - jj * KP;
+        cf[jj][ii] = ii < K ? coef[mu * K * K + jj * K + ii] : make_float2(0.f, 0.f);
+      }
+      float vmin = __int_as_float(0x7f800000), vmax = 0.f;
+#pragma unroll 1
+      for (int r0 = 0; r0 < H; r0 += G::BAND) {
+        __syncthreads();
+        for (int i = tid; i < G::TH * G::PITCH; i += 256) {
+          const int ty = i / G::PITCH, tx = i - ty * G::PITCH;
+          tile[ty][tx] = (float)gray[(size_t)border101(r0 + ty - G::R, H) * 128 + border101(tx - G::R, W)];
+        }
+        __syncthreads();
+        float re[2][4], im[2][4];
+#pragma unroll
+        for (int o = 0; o < 4; o++) { re[0][o] = re[1][o] = 0.f; im[0][o] = im[1][o] = 0.f; }
+#pragma unroll 1
+        for (int j = 0; j < K; j++) {
+          float px[2][4 * G::NF4];
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const float4* row = reinterpret_cast<const float4*>(&tile[rA + 8 * h + j][x0]);
+#pragma unroll
+            for (int q = 0; q < G::NF4; q++) { const float4 v = row[q]; px[h][4 * q] = v.x; px[h][4 * q + 1] = v.y; px[h][4 * q + 2] = v.z; px[h][4 * q + 3] = v.w; }
+          }
+          const float4* crow = reinterpret_cast<const float4*>(&cf[j][0]);
+#pragma unroll
+          for (int i2 = 0; i2 < KP / 2; i2++) {
+            const float4 c2 = crow[i2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int i = 2 * i2 + e;
+              if (i < K) {
+                const float cr = e ? c2.z : c2.x, ci = e ? c2.w : c2.y;
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                  for (int o = 0; o < 4; o++) {   // product and sum rounded separately == cv2's filter2D bit for bit
+                    re[h][o] = __fadd_rn(re[h][o], __fmul_rn(px[h][o + i], cr));
+                    im[h][o] = __fadd_rn(im[h][o], __fmul_rn(px[h][o + i], ci));
+                  }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int r = r0 + rA + 8 * h;
+          if (r < H) {
+            float m[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+              m[o] = __fsqrt_rn(__fadd_rn(__fmul_rn(im[h][o], im[h][o]), __fmul_rn(re[h][o], re[h][o])));
+              if (x0 + o < W) { vmin = fminf(vmin, m[o]); vmax = fmaxf(vmax, m[o]); }
+            }
+            *reinterpret_cast<float4*>(&mplane[(size_t)r * 128 + x0]) = make_float4(m[0], m[1], m[2], m[3]);
+          }
+        }
+      }
+      float a, b;
+      gabor_minmax_to_affine(vmin, vmax, a, b);   // its barriers also publish the magnitudes to the CTA
+      gabor_quantise_plane(g, f, d, mu, mplane, a, b, s_band);
+    }
+  }
 }
 
 __global__ void k_init_minmax(uint32_t* mm, int n) {

@@ -128,3 +128,34 @@ def test_multi_gpu_single_caller(crf, O, gpu, synth_models):
         mc.analyze_batch(frames, bad, iob)
     assert e.value.code == -1 and "shard" in str(e.value)
     assert crf.MultiContext(gm).n_devices == ndev
+
+
+def test_fused_and_banded_gabor_kernels_agree(crf, O, gpu, synth_models, monkeypatch):
+    """The fused per-scale Gabor kernels (CRF_GABOR_FUSED=1: rolling row pass, magnitudes in an L2-resident per-CTA scratch,
+    quantisation in the same kernel; measured slower, kept as a variant) and both quantisation kernels against the default banded path and the oracle:
+    identical planes on ragged heights (1 .. 33 bands, partial last band, W = 124 / 125) and identical records in a batch."""
+    import cv2
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, _ = synth_models
+    rng = np.random.default_rng(0)
+    imgs = [cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), 1.3) for H, W in [(125, 125), (148, 124), (32, 125), (47, 125), (48, 125), (49, 124), (521, 125), (200, 125)]]
+    imgs.append(np.zeros((125, 125), np.uint8)); imgs.append(rng.integers(0, 256, (125, 125), dtype=np.uint8))
+    banded = crf.Context(None, 0)
+    monkeypatch.setenv("CRF_GABOR_FUSED", "1")
+    fused = crf.Context(None, 0)
+    monkeypatch.delenv("CRF_GABOR_FUSED")
+    monkeypatch.setenv("CRF_GABOR_QUANT_OLD", "1")
+    old_quant = crf.Context(None, 0)
+    monkeypatch.delenv("CRF_GABOR_QUANT_OLD")
+    for img in imgs:
+        pf, jf = fused.stage_channels(img)
+        pb, jb = banded.stage_channels(img)
+        pq, jq = old_quant.stage_channels(img)
+        assert np.array_equal(pf, pb) and np.array_equal(jf, jb) and np.array_equal(pq, pb) and np.array_equal(jq, jb), img.shape
+        op, oi = O.channels(img)
+        assert np.array_equal(pf, op) and np.array_equal(jf, oi.astype(np.uint32)), img.shape
+    crops, _ = wl.make_crops(700, seed=8)     # more faces than resident CTAs: every persistent CTA takes several items
+    a = crf.Context(gm, 0).analyze_crops(crops)
+    monkeypatch.setenv("CRF_GABOR_FUSED", "1")
+    b = crf.Context(gm, 0).analyze_crops(crops)
+    assert a.tobytes() == b.tobytes()
