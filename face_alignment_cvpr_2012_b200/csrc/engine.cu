@@ -293,7 +293,7 @@ static bool is_pinned_host(const void* p) {
 
 // src/FaceForest.cpp:199-204 (scale, scaled size) + the argument checks of the path.
 static int make_desc(const crf_ctx* c, int rows, int cols, size_t step, size_t img_off, const crf_rect_t& b, FaceDesc& d) {
-  if (b.x < 0 || b.y < 0 || b.width <= 0 || b.height <= 0 || b.x + b.width > cols || b.y + b.height > rows)
+  if (b.x < 0 || b.y < 0 || b.width <= 0 || b.height <= 0 || (long long)b.x + b.width > cols || (long long)b.y + b.height > rows)
     return fail(CRF_ERR_ARG, "bbox outside image");
   const float scale = static_cast<float>(125) / static_cast<float>(b.width);
   const int sw = (int)(b.width * scale), sh = (int)(b.height * scale);

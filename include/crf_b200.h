@@ -161,7 +161,11 @@ int crf_host_alloc(void** p, size_t bytes);
 void crf_host_free(void* p);
 
 /* ---- FaceForest::analyzeFace (src/FaceForest.cpp:183-258) for n boxes of one BGR frame
- * (analyzeImage with the Haar boxes given, :161-181). */
+ * (analyzeImage with the Haar boxes given, :161-181).
+ * Argument checking is all-or-nothing: every box is validated before any work starts (inside the image; scaled face larger than a
+ * 31-px patch, at most 125 wide and CRF_MAX_SCALED_H tall) and ONE bad box fails the whole call with CRF_ERR_ARG, leaving `out`
+ * untouched — the reference would throw out of cv::Mat::operator() for that face in the middle of its loop.  Callers that take boxes
+ * from a detector should clip them first (crf_b200::FaceForest::detectFace does, as src/FaceForest.cpp:152-157). */
 int crf_analyze_faces(crf_ctx* ctx, const uint8_t* bgr, int rows, int cols, size_t step,
                       const crf_rect_t* boxes, int n, crf_face_t* out);
 /* n boxes spread over n_images equal-size frames; image_of_box[i] selects the frame of box i. */
