@@ -76,6 +76,22 @@ struct alignas(32) DevSlotW {
 };
 static_assert(sizeof(DevSlotW) == 32, "window slot is one 32-byte sector");
 
+// Internal-nodes-only window form (k_traverse_win2).  Leaves have no record at all: a child is either the index of another
+// DevSlotN (>= 0) or ~(forest-global leaf index) (< 0), so a walk knows that it has arrived — and where — from its PARENT's
+// record.  That (a) drops the last record fetch of every walk and halves the array (every second node of a full binary tree is a
+// leaf), and (b) takes the freshly fetched record out of the loop condition, which lets the two walks of a lane run half an
+// iteration apart: the record fetch of one is in flight while the other does its node test (software pipelining inside the warp).
+// Records of a tree are breadth-first, `nroot_of_slot` maps a DevSlot root index to the DevSlotN index (or ~leaf for a one-leaf tree).
+struct alignas(32) DevSlotN {
+  uint32_t pw1, pw2;   // ch * kWinPlaneBytes + x * 4 (18 bits) | (w * 4) << 18
+  uint32_t yh1, yh2;   // y * kWinRowBytes | (h * kWinRowBytes) << 16
+  uint32_t m1, m2;     // magic_for_area
+  int32_t left_thr;    // left child in bits 0..21 (two's complement), threshold in bits 22..31
+  int32_t right;       // right child
+};
+static_assert(sizeof(DevSlotN) == 32, "internal-node slot is one 32-byte sector");
+constexpr int kSlotNChildBits = 22;   // |child| < 2^21: forests of up to 2 M internal nodes / leaves
+
 // MPLeaf (include/MPSample.hpp:137-159) with the vote predicate of src/face_utils.cpp:285-290 folded
 // into `mask` (bit i: part i votes) for the options of the context.
 struct alignas(16) DevMpLeaf {   // 48 bytes: three 128-bit loads
@@ -89,6 +105,8 @@ struct PackedForest {
   std::vector<DevSlot> slots;
   std::vector<DevSlot16> slots16;    // same slots, compact form
   std::vector<DevSlotW> slotsw;      // same slots, window form (valid when max_extent <= kWinExtent)
+  std::vector<DevSlotN> slotsn;      // internal nodes only, children tagged (k_traverse_win2); empty when the forest is too large for the tag
+  std::vector<int32_t> nroot;        // per tree (parallel to `roots`): DevSlotN index of the root, or ~leaf for a one-leaf tree
   int max_extent = 0;                // largest x + w or y + h over all rectangles
   std::vector<int32_t> roots;        // slot of the root of tree t (forest-major for the jungle)
   std::vector<int32_t> forest_base;  // jungle: first tree of pose forest f in `roots`

@@ -158,7 +158,7 @@ struct crf_ctx {
   bool full_model = true; // head-pose forest + 5 pose forests: what analyzeFace needs (a partial model serves Forest<S> alone)
   PackedForest hp, mp;  // host copies (object-id maps for the stage API)
   // device model
-  Buf d_hp_slotsw, d_mp_slotsw, d_hp_slots16, d_mp_slots16, d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5], d_coef_sep[5];
+  Buf d_hp_slotsn, d_mp_slotsn, d_hp_nroot, d_mp_nroot, d_hp_slotsw, d_mp_slotsw, d_hp_slots16, d_mp_slots16, d_hp_slots, d_hp_roots, d_hp_m, d_mp_slots, d_mp_roots, d_mp_mask, d_mp_leaf, d_xs, d_coef[5], d_coef_sep[5];
   int gabor_width[5] = {0, 0, 0, 0, 0};
   ComposeTables ct{};
   // work buffers: two complete sets, so that consecutive chunks run on two streams and kernels bound by different
@@ -181,7 +181,8 @@ struct crf_ctx {
   int win_hp = 0, win_ffd = 0;   // k_traverse_win variants (0 = default)
   bool win_smem_ok = true;       // the device grants a CTA the 231 040 bytes of dynamic shared memory the window needs
   int win_tex = 1;               // node records of k_traverse_win through the texture pipe (CRF_WIN_TEX=0: 256-bit global loads)
-  cudaTextureObject_t tex_hp = 0, tex_mp = 0, tex_hp_wide = 0, tex_mp_wide = 0;
+  cudaTextureObject_t tex_hp = 0, tex_mp = 0, tex_hp_wide = 0, tex_mp_wide = 0, tex_hp_n = 0, tex_mp_n = 0;
+  int win_fmt = 2;               // 2 = k_traverse_win2 on the internal-nodes-only records (default), 1 = k_traverse_win (CRF_WIN_FMT)
   // 1 = consecutive chunks run back to back on one stream (default: measured faster — co-resident Gabor CTAs shrink the L1
   // the gathers live on, and two chunks' stacks thrash L2); 2 = alternate chunks between two streams / work sets
   int nstreams = 1;
@@ -387,11 +388,13 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
   a.stride = stride;
   if (hp) {
     a.slots = c->d_hp_slots.as<DevSlot>(); a.slots16 = c->d_hp_slots16.as<DevSlot16>(); a.slotsw = c->d_hp_slotsw.as<DevSlotW>(); a.slotsw_tex = c->tex_hp; a.slots_tex = c->tex_hp_wide; a.roots = roots; a.ntrees = ntrees;
+    a.slotsn_tex = c->tex_hp_n; a.nroot_of_slot = c->d_hp_nroot.as<int32_t>();
     a.leaf_out = c->w->d_hp_leaf.as<int32_t>(); a.leaf_face_stride = c->w->hp_leaf_fs;
     a.cnt_tests = CNT_HP_TESTS; a.cnt_trav = CNT_HP_TRAV;
     if (hp_values) a.leaf_value = c->d_hp_m.as<float>();
   } else {
     a.slots = c->d_mp_slots.as<DevSlot>(); a.slots16 = c->d_mp_slots16.as<DevSlot16>(); a.slotsw = c->d_mp_slotsw.as<DevSlotW>(); a.slotsw_tex = c->tex_mp; a.slots_tex = c->tex_mp_wide;
+    a.slotsn_tex = c->tex_mp_n; a.nroot_of_slot = c->d_mp_nroot.as<int32_t>();
     a.face_roots = c->w->d_face_roots.as<int32_t>(); a.face_ntrees = c->w->d_face_ntrees.as<int32_t>();
     a.leaf_out = c->w->d_ffd_leaf.as<int32_t>(); a.leaf_face_stride = c->w->ffd_leaf_fs;
     a.cnt_tests = CNT_FFD_TESTS; a.cnt_trav = CNT_FFD_TRAV;
@@ -410,8 +413,20 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
     if (fits && (forced || (c->traverse_variant == 0 && (long long)n * ncols >= 2LL * c->sm_count))) {
       const int nitems = n * ncols, grid = std::min(nitems, c->sm_count);
       // (warps per CTA) | (walks per lane) << 8; CRF_WIN_HP / CRF_WIN_FFD override for experiments
-      const int wv = hp ? (c->win_hp ? c->win_hp : (30 | 1 << 8)) : (c->win_ffd ? c->win_ffd : (20 | 2 << 8));
+      const bool fmt2 = c->win_fmt == 2 && (hp ? c->tex_hp_n : c->tex_mp_n) != 0;
+      // defaults measured on B200 (tools/win2_variants.py): head pose 32 warps x 1 walk (30 x 1 for k_traverse_win), FFD 20 warps x 2 walks
+      const int wv = hp ? (c->win_hp ? c->win_hp : ((fmt2 ? 32 : 30) | 1 << 8)) : (c->win_ffd ? c->win_ffd : (20 | 2 << 8));
       bool ok = false;
+#define CRF_WIN2(NW_, WK_)                                                                                                  \
+      if (fmt2 && wv == (NW_ | WK_ << 8)) {                                                                                  \
+        auto kf = c->counting ? k_traverse_win2<NW_, WK_, true> : k_traverse_win2<NW_, WK_, false>;                          \
+        CU(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmemBytes));                            \
+        kf<<<grid, NW_ * 32, kWinSmemBytes, c->w->stream>>>(a, nitems, ncols, c->num_channels);                              \
+        ok = true;                                                                                                           \
+      }
+      CRF_WIN2(15, 2) CRF_WIN2(20, 2) CRF_WIN2(24, 2) CRF_WIN2(30, 1) CRF_WIN2(32, 1) CRF_WIN2(20, 1)
+#undef CRF_WIN2
+      if (ok) { KCHECK(); count_launch(c, stage); return CRF_OK; }
 #define CRF_WIN(NW_, WK_)                                                                                                   \
       if (wv == (NW_ | WK_ << 8)) {                                                                                          \
         auto kf = c->counting ? k_traverse_win<NW_, WK_, true> : c->win_tex ? k_traverse_win<NW_, WK_, false, true> : k_traverse_win<NW_, WK_, false>; \
@@ -1051,6 +1066,27 @@ int crf_model_check_packing(const crf_model* m, int* max_extent_hp, int* max_ext
       checked++;
     }
     if (ext != pf.max_extent) return fail(CRF_ERR_STATE, "max_extent is not the largest rectangle extent");
+    // internal-nodes-only form: walking it from every root must visit the same tests and end on the same leaves as the wide form
+    if (!pf.nroot.empty()) {
+      if (pf.nroot.size() != pf.roots.size()) return fail(CRF_ERR_STATE, "nroot and roots differ in length");
+      std::vector<std::pair<int32_t, int32_t>> st;
+      for (size_t t = 0; t < pf.roots.size(); t++) {
+        st.assign(1, {pf.roots[t], pf.nroot[t]});
+        while (!st.empty()) {
+          const auto [si, ni] = st.back(); st.pop_back();
+          const DevSlot& a = pf.slots[si];
+          if (a.is_leaf) { if (ni != ~a.child) return fail(CRF_ERR_STATE, "DevSlotN leaf tag mismatch"); continue; }
+          if (ni < 0 || (size_t)ni >= pf.slotsn.size()) return fail(CRF_ERR_STATE, "DevSlotN index out of range");
+          const DevSlotN& r = pf.slotsn[ni]; const DevSlotW& w = pf.slotsw[si];
+          const int32_t left = (int32_t)((uint32_t)r.left_thr << (32 - kSlotNChildBits)) >> (32 - kSlotNChildBits), thr = r.left_thr >> kSlotNChildBits;
+          if ((r.pw1 & 0x3ffffu) != w.px1 || (r.pw2 & 0x3ffffu) != w.px2 || (r.pw1 >> 18) != ((w.tw >> 16) & 0xffu) || (r.pw2 >> 18) != ((w.tw >> 24) & 0x7fu) ||
+              r.yh1 != w.yh1 || r.yh2 != w.yh2 || r.m1 != w.m1 || r.m2 != w.m2 || thr != std::min(255, std::max(-256, (int)a.thr)))
+            return fail(CRF_ERR_STATE, "DevSlotN test mismatch at slot " + std::to_string(si));
+          st.push_back({a.child, left});
+          st.push_back({a.child + 1, r.right});
+        }
+      }
+    }
     if (which == 0 && max_extent_hp) *max_extent_hp = ext;
     if (which == 1 && max_extent_ffd) *max_extent_ffd = ext;
   }
@@ -1071,9 +1107,11 @@ void crf_ctx_destroy(crf_ctx* c) {
   for (auto& w : c->ws) if (w.stream) cudaStreamSynchronize(w.stream);
   if (c->tex_hp) cudaDestroyTextureObject(c->tex_hp);
   if (c->tex_mp) cudaDestroyTextureObject(c->tex_mp);
+  if (c->tex_hp_n) cudaDestroyTextureObject(c->tex_hp_n);
+  if (c->tex_mp_n) cudaDestroyTextureObject(c->tex_mp_n);
   if (c->tex_hp_wide) cudaDestroyTextureObject(c->tex_hp_wide);
   if (c->tex_mp_wide) cudaDestroyTextureObject(c->tex_mp_wide);
-  Buf* all[] = {&c->d_hp_slotsw, &c->d_mp_slotsw, &c->d_hp_slots16, &c->d_mp_slots16, &c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
+  Buf* all[] = {&c->d_hp_slotsn, &c->d_mp_slotsn, &c->d_hp_nroot, &c->d_mp_nroot, &c->d_hp_slotsw, &c->d_mp_slotsw, &c->d_hp_slots16, &c->d_mp_slots16, &c->d_hp_slots, &c->d_hp_roots, &c->d_hp_m, &c->d_mp_slots, &c->d_mp_roots, &c->d_mp_mask, &c->d_mp_leaf, &c->d_xs, &c->d_coef[0], &c->d_coef[1],
                 &c->d_coef[2], &c->d_coef[3], &c->d_coef[4], &c->d_coef_sep[1], &c->d_coef_sep[2], &c->d_coef_sep[3], &c->d_coef_sep[4], &c->d_imgs[0], &c->d_imgs[1], &c->d_fd, &c->d_faces, &c->d_counters, &c->d_misc,
                 &c->d_haar_stages, &c->d_haar_weak, &c->d_haar_feats, &c->d_haar_level, &c->d_haar_S, &c->d_haar_Q, &c->d_haar_flags};
   for (Buf* b : all) b->release();
@@ -1111,6 +1149,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if (c->opt.hp_stride < 1 || c->opt.ffd_stride < 1) return fail(CRF_ERR_ARG, "strides must be >= 1");
   if (const char* v = std::getenv("CRF_TRAVERSE_VARIANT")) c->traverse_variant = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_WIN_TEX")) c->win_tex = (int)std::strtol(v, nullptr, 0);
+  if (const char* v = std::getenv("CRF_WIN_FMT")) c->win_fmt = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_WIN_HP")) c->win_hp = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_WIN_FFD")) c->win_ffd = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_GABOR_FUSED")) c->gabor_fused = (int)std::strtol(v, nullptr, 0);
@@ -1155,11 +1194,23 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
       (rc = upload(c->d_mp_slots, c->mp.slots, c->w->stream)) || (rc = upload(c->d_mp_roots, c->mp.roots, c->w->stream)) ||
       (rc = upload(c->d_mp_mask, c->mp.mp_mask, c->w->stream)) || (rc = upload(c->d_mp_leaf, c->mp.mp_leaf, c->w->stream)))
     return rc;
-  for (int k = 0; k < 4; k++) {   // node records as linear uint4 textures: window form (k < 2) and wide form (k >= 2)
+  // internal-nodes-only records (k_traverse_win2) + the map from a root's DevSlot index to its DevSlotN index
+  for (int k = 0; k < 2; k++) {
+    const PackedForest& pf = k ? c->mp : c->hp;
+    if (pf.slotsn.empty() && pf.nroot.empty()) continue;
+    std::vector<int32_t> map(pf.slots.size(), -1);
+    for (size_t t = 0; t < pf.roots.size(); t++) map[pf.roots[t]] = pf.nroot[t];
+    // a forest of one-leaf trees has no records at all: keep the texture bindable
+    std::vector<DevSlotN> recs = pf.slotsn;
+    if (recs.empty()) recs.emplace_back();
+    if ((rc = upload(k ? c->d_mp_slotsn : c->d_hp_slotsn, recs, c->w->stream)) || (rc = upload(k ? c->d_mp_nroot : c->d_hp_nroot, map, c->w->stream))) return rc;
+  }
+  for (int k = 0; k < 6; k++) {   // node records as linear uint4 textures: window form (k < 2), wide form (2, 3), internal-only form (4, 5)
     cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear;
-    void* ptrs[4] = {c->d_hp_slotsw.p, c->d_mp_slotsw.p, c->d_hp_slots.p, c->d_mp_slots.p};
-    const size_t counts[4] = {c->hp.slotsw.size(), c->mp.slotsw.size(), c->hp.slots.size(), c->mp.slots.size()};
-    cudaTextureObject_t* objs[4] = {&c->tex_hp, &c->tex_mp, &c->tex_hp_wide, &c->tex_mp_wide};
+    void* ptrs[6] = {c->d_hp_slotsw.p, c->d_mp_slotsw.p, c->d_hp_slots.p, c->d_mp_slots.p, c->d_hp_slotsn.p, c->d_mp_slotsn.p};
+    const size_t counts[6] = {c->hp.slotsw.size(), c->mp.slotsw.size(), c->hp.slots.size(), c->mp.slots.size(),
+                              c->d_hp_slotsn.p ? std::max<size_t>(c->hp.slotsn.size(), 1) : 0, c->d_mp_slotsn.p ? std::max<size_t>(c->mp.slotsn.size(), 1) : 0};
+    cudaTextureObject_t* objs[6] = {&c->tex_hp, &c->tex_mp, &c->tex_hp_wide, &c->tex_mp_wide, &c->tex_hp_n, &c->tex_mp_n};
     if (counts[k] == 0) continue;   // a partial model has no records of the other kind
     rd.res.linear.devPtr = ptrs[k];
     rd.res.linear.desc = cudaCreateChannelDesc<uint4>();

@@ -996,6 +996,8 @@ struct TraverseArgs {
   const DevSlotW* slotsw;        // window form of the same slots (k_traverse_win)
   cudaTextureObject_t slotsw_tex;  // the same array as a linear uint4 texture (two texels per record)
   cudaTextureObject_t slots_tex;   // `slots` as a linear uint4 texture (k_traverse with MODE bit 3)
+  cudaTextureObject_t slotsn_tex;  // DevSlotN records (internal nodes only) as a linear uint4 texture (k_traverse_win2)
+  const int32_t* nroot_of_slot;    // DevSlot root index -> DevSlotN index of the same root (or ~leaf)
   const int32_t* roots;        // shared tree list (head pose) or nullptr
   const int32_t* face_roots;   // [face][kMaxList] composed lists (FFD) or nullptr
   const int32_t* face_ntrees;  // [face] or nullptr
@@ -1406,6 +1408,172 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win(TraverseArgs a, int
           }
           int va = (int)a1.y;
           if (a.leaf_value) va = __float_as_int(__ldg(a.leaf_value + va));
+          if (vA) out[((size_t)(x0 + lx) * ny + (y0 + py)) * nt + t] = va;
+        }
+      }
+      if (COUNT && threadIdx.x == 0) trav += (unsigned long long)min(kWinTile, nx - x0) * min(kWinTile, ny - y0) * nt;
+    }
+  }
+  if (COUNT) {
+    tests = __reduce_add_sync(0xffffffffu, tests);
+    if (lane == 0 && tests) atomicAdd(&a.counters[a.cnt_tests], (unsigned long long)tests);
+    if (threadIdx.x == 0 && trav) atomicAdd(&a.counters[a.cnt_trav], trav);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_traverse_win2: the same window, ring and item order as k_traverse_win, on the internal-nodes-only records (DevSlotN,
+// device_forest.h).  What changes is the walk loop:
+//  * a walk's position is one int: >= 0 a record index, < 0 ~leaf.  Whether the next node is a leaf is known from the parent's
+//    record, so no leaf record is ever fetched (one fetch less per walk, half the record array in L1/L2) ...
+//  * ... and the loop condition no longer depends on a fetch in flight.  With two walks per lane the loop body is
+//    [test A, fetch A', test B, fetch B']: A's fetch has the ~60 instructions of B's test to land in, and vice versa, where
+//    k_traverse_win issued both fetches at the end of the body and then waited for both (long-scoreboard stalls, 39-45 % of its
+//    warp samples).
+//  * lanes whose patch lies outside the grid start parked (they used to walk on whatever the window held).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int win2_step(uint32_t col, uint32_t row, const uint4 q0, const uint4 q1, uint32_t live) {
+  constexpr uint32_t kRing = kWinPlaneBytes;
+  uint32_t ra1 = row + (q0.z & 0xffffu); ra1 = min(ra1, ra1 - kRing);
+  uint32_t rc1 = ra1 + (q0.z >> 16);     rc1 = min(rc1, rc1 - kRing);
+  uint32_t ra2 = row + (q0.w & 0xffffu); ra2 = min(ra2, ra2 - kRing);
+  uint32_t rc2 = ra2 + (q0.w >> 16);     rc2 = min(rc2, rc2 - kRing);
+  const uint32_t ca1 = col + (q0.x & 0x3ffffu), cb1 = ca1 + (q0.x >> 18);
+  const uint32_t ca2 = col + (q0.y & 0x3ffffu), cb2 = ca2 + (q0.y >> 18);
+  const uint32_t A1 = lds_u32(ca1 + ra1, live), B1 = lds_u32(cb1 + ra1, live), C1 = lds_u32(ca1 + rc1, live), D1 = lds_u32(cb1 + rc1, live);
+  const uint32_t A2 = lds_u32(ca2 + ra2, live), B2 = lds_u32(cb2 + ra2, live), C2 = lds_u32(ca2 + rc2, live), D2 = lds_u32(cb2 + rc2, live);
+  const int m1 = (int)__umulhi((D1 - B1 - C1 + A1) << 1, q1.x), m2 = (int)__umulhi((D2 - B2 - C2 + A2) << 1, q1.y);
+  const int thr = (int)q1.z >> kSlotNChildBits;
+  const int left = ((int)q1.z << (32 - kSlotNChildBits)) >> (32 - kSlotNChildBits);
+  return (m1 - m2) > thr ? (int)q1.w : left;   // go left iff mean1 - mean2 <= threshold
+}
+
+// Record fetch of a walk: two texel fetches, UNCONDITIONAL (a parked walk re-reads record 0, a broadcast hit) and volatile, so that
+// (a) ptxas counts the fetches in flight on its scoreboard and waits for exactly the older walk's pair while the younger one's stays
+// in flight, and (b) the order [gathers of A, fetch A', gathers of B, fetch B'] survives instruction scheduling.
+__device__ __forceinline__ void fetch_slotn(cudaTextureObject_t tex, int slot, uint4& q0, uint4& q1) {
+  const int s2 = 2 * max(slot, 0);
+  asm volatile("tex.1d.v4.u32.s32 {%0,%1,%2,%3}, [%4, {%5}];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "l"(tex), "r"(s2));
+  asm volatile("tex.1d.v4.u32.s32 {%0,%1,%2,%3}, [%4, {%5}];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(tex), "r"(s2 + 1));
+}
+
+template <int NW, int WALKS, bool COUNT>
+__global__ void __launch_bounds__(NW * 32, 1) k_traverse_win2(TraverseArgs a, int nitems, int ncols, int nplanes) {
+  static_assert(WALKS == 1 || WALKS == 2, "one or two walks per lane");
+  auto fetch = [&](int slot, uint4& q0, uint4& q1) { fetch_slotn(a.slotsn_tex, slot, q0, q1); };
+  extern __shared__ __align__(16) uint8_t s_win[];
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_win);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lx = lane & 7, ly = lane >> 3;
+  unsigned tests = 0;
+  unsigned long long trav = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int f = item / ncols, ixb = item - f * ncols;
+    const FaceDesc d = a.fd[f];
+    const int nx = d.W - kPatch, ny = d.H - kPatch;   // stride 1
+    const int x0 = ixb * kWinTile;
+    if (nx <= 0 || ny <= 0 || x0 >= nx) continue;
+    const int nrows = d.H + 1;
+    const stack_t* __restrict__ src = a.stacks + f * a.stack_face_stride + x0;
+    const int nt = a.face_ntrees ? a.face_ntrees[f] : a.ntrees;
+    const int32_t* roots = a.face_roots ? a.face_roots + (size_t)f * kMaxList : a.roots;
+    int32_t* out = a.leaf_out + f * a.leaf_face_stride;
+    const bool vx = x0 + lx < nx;
+    const int ntile_y = (ny + kWinTile - 1) / kWinTile;
+    for (int iyb = 0; iyb < ntile_y; iyb++) {
+      const int y0 = iyb * kWinTile;
+      const int rbeg = iyb == 0 ? 0 : y0 + kWinExtent, rend = min(y0 + kWinRows, nrows);
+      const int nvec = max(rend - rbeg, 0) * nplanes * (kWinCols / 4);
+      __syncthreads();   // every walk of the previous tile is done with the rows about to be replaced
+#pragma unroll 4
+      for (int i = threadIdx.x; i < nvec; i += NW * 32) {
+        const int c = i % (kWinCols / 4), pr = i / (kWinCols / 4);
+        const int p = pr % nplanes, r = rbeg + pr / nplanes;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)p * a.plane_stride + (size_t)r * kRowStride) + c);
+        const uint32_t dst = s_base + p * kWinPlaneBytes + (r % kWinRows) * kWinRowBytes + c * 16;
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+      __syncthreads();
+      if (WIN_PREFETCH) {
+        // The stacks of a launch (2.4 MB per face) do not stay in L2: pull the rows of the next tile step (or the first window of the
+        // next item) towards L2 while this tile's walks run.  The warps share the planes: one bulk prefetch (UBLKPF, warp-uniform operands) per plane and
+        // group of up to 8 FULL rows (4 KB contiguous): the other tile columns of the face, walked by the neighbouring CTAs at the same
+        // time, want the rest of those rows anyway.  (A prefetch per 32-byte sector of the 160-byte row pieces, as k_traverse_win does,
+        // costs 5 % of the kernel's instructions.)
+        const stack_t* psrc = a.stacks + f * a.stack_face_stride;
+        int pbeg = y0 + kWinTile + kWinExtent, pend = min(y0 + kWinTile + kWinRows, nrows);
+        if (iyb + 1 >= ntile_y) {
+          const int nitem = item + gridDim.x;
+          pbeg = pend = 0;
+          if (nitem < nitems) {
+            const int nf = nitem / ncols;
+            psrc = a.stacks + nf * a.stack_face_stride;
+            pend = min(kWinRows, a.fd[nf].H + 1);
+          }
+        }
+        for (int rb = pbeg; rb < pend; rb += 8) {
+          const uint32_t bytes = (uint32_t)(min(pend - rb, 8) * kRowStride * sizeof(stack_t));
+          for (int p = warp; p < nplanes; p += NW)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(psrc + (size_t)p * a.plane_stride + (size_t)rb * kRowStride), "r"(bytes));
+        }
+      }
+      const int r0 = y0 % kWinRows;
+      const uint32_t col = s_base + lx * 4;
+      if (WALKS == 2) {
+        int ra = r0 + ly, rb = r0 + ly + 4;
+        ra -= ra >= kWinRows ? kWinRows : 0;
+        rb -= rb >= kWinRows ? kWinRows : 0;
+        const uint32_t rowA = ra * kWinRowBytes, rowB = rb * kWinRowBytes;
+        const bool vA = vx && y0 + ly < ny, vB = vx && y0 + ly + 4 < ny;
+        for (int t = warp; t < nt; t += NW) {
+          const int root = __ldg(a.nroot_of_slot + roots[t]);
+          int ca = vA ? root : -1, cb = vB ? root : -1;   // lanes outside the grid start parked; their result is never stored
+          uint4 a0, a1, b0, b1;
+          fetch(ca, a0, a1);
+          for (;;) {
+            // Steady state: test A_k, fetch A_k+1, test B_k, fetch B_k+1, ... — one walk's fetch is in flight while the other walk is
+            // tested.  The body starts at "fetch B" so that the fetches in flight are in the same order on every path into a test
+            // (ptxas waits by counting them).  The warp-uniform branches skip a walk whose 32 lanes are all parked, and they are also
+            // what keeps ptxas from merging the halves (it would sink A's fetch below B's gathers and lose the overlap).
+            fetch(cb, b0, b1);
+            const bool la = ca >= 0;
+            if (__any_sync(0xffffffffu, la)) {
+              const int na = win2_step(col, rowA, a0, a1, la ? 1u : 0u);
+              ca = la ? na : ca;
+              if (COUNT) tests += la ? 1 : 0;
+            }
+            fetch(ca, a0, a1);
+            const bool lb = cb >= 0;
+            if (__any_sync(0xffffffffu, lb)) {
+              const int nb = win2_step(col, rowB, b0, b1, lb ? 1u : 0u);
+              cb = lb ? nb : cb;
+              if (COUNT) tests += lb ? 1 : 0;
+            }
+            if (!__any_sync(0xffffffffu, (ca & cb) >= 0)) break;   // no walk of the warp sits on a record any more
+          }
+          int va = ~ca, vb = ~cb;
+          if (a.leaf_value) { if (vA) va = __float_as_int(__ldg(a.leaf_value + va)); if (vB) vb = __float_as_int(__ldg(a.leaf_value + vb)); }
+          if (vA) out[((size_t)(x0 + lx) * ny + (y0 + ly)) * nt + t] = va;
+          if (vB) out[((size_t)(x0 + lx) * ny + (y0 + ly + 4)) * nt + t] = vb;
+        }
+      } else {
+        for (int k = warp; k < 2 * nt; k += NW) {
+          const int t = k >> 1, py = ly + 4 * (k & 1);
+          int ra = r0 + py;
+          ra -= ra >= kWinRows ? kWinRows : 0;
+          const uint32_t rowA = ra * kWinRowBytes;
+          const bool vA = vx && y0 + py < ny;
+          int ca = vA ? __ldg(a.nroot_of_slot + roots[t]) : -1;
+          uint4 a0, a1;
+          while (__any_sync(0xffffffffu, ca >= 0)) {
+            const bool la = ca >= 0;
+            fetch(ca, a0, a1);
+            const int n = win2_step(col, rowA, a0, a1, la ? 1u : 0u);
+            ca = la ? n : ca;
+            if (COUNT) tests += la ? 1 : 0;
+          }
+          int va = ~ca;
+          if (a.leaf_value && vA) va = __float_as_int(__ldg(a.leaf_value + va));
           if (vA) out[((size_t)(x0 + lx) * ny + (y0 + py)) * nt + t] = va;
         }
       }

@@ -65,6 +65,14 @@ int pack_forests(const std::vector<const FlatForest*>& forests, ForestKind kind,
       const int32_t base = (int32_t)out.slots.size();
       out.roots.push_back(base);
       std::vector<int32_t> slot_of(t.nodes.size(), -1);
+      // DevSlotN index of every internal node, ~(global leaf) of every leaf
+      std::vector<int32_t> n_of(t.nodes.size(), 0);
+      auto tag = [&](int32_t ni) {
+        if (t.nodes[ni].leaf >= 0) n_of[ni] = ~(leaf_base + t.nodes[ni].leaf);
+        else { n_of[ni] = (int32_t)out.slotsn.size(); out.slotsn.emplace_back(); }
+      };
+      tag(0);
+      out.nroot.push_back(n_of[0]);
       std::deque<int32_t> q;
       out.slots.emplace_back();
       slot_of[0] = base;
@@ -86,6 +94,8 @@ int pack_forests(const std::vector<const FlatForest*>& forests, ForestKind kind,
           slot_of[n.right] = pair + 1;
           q.push_back(n.left);
           q.push_back(n.right);
+          tag(n.left);
+          tag(n.right);
           const uint32_t area1 = (uint32_t)n.r1[2] * n.r1[3], area2 = (uint32_t)n.r2[2] * n.r2[3];
           if (area1 == 0 || area2 == 0) { err = "empty rectangle"; return CRF_ERR_UNSUPPORTED; }
           if (n.r1[0] + n.r1[2] > kPatch || n.r1[1] + n.r1[3] > kPatch || n.r2[0] + n.r2[2] > kPatch || n.r2[1] + n.r2[3] > kPatch) { err = "rectangle leaves the patch"; return CRF_ERR_UNSUPPORTED; }
@@ -136,9 +146,21 @@ int pack_forests(const std::vector<const FlatForest*>& forests, ForestKind kind,
         }
         if (out.slotsw.size() < out.slots.size()) out.slotsw.resize(out.slots.size());
         out.slotsw[slot_of[ni]] = w;
+        if (n.leaf < 0) {
+          DevSlotN r{};
+          r.pw1 = w.px1 | (n.r1[2] * 4u) << 18;
+          r.pw2 = w.px2 | (n.r2[2] * 4u) << 18;
+          r.yh1 = w.yh1; r.yh2 = w.yh2; r.m1 = s.m1; r.m2 = s.m2;
+          const int32_t thr = std::min(255, std::max(-256, (int)n.threshold));   // |mean1 - mean2| <= 255: the clamp preserves the test
+          r.left_thr = (int32_t)(((uint32_t)n_of[n.left] & ((1u << kSlotNChildBits) - 1)) | (uint32_t)thr << kSlotNChildBits);
+          r.right = n_of[n.right];
+          out.slotsn[n_of[ni]] = r;
+        }
       }
     }
   }
+  // the child tag of DevSlotN holds 21 bits + sign; larger forests simply do not get the form (k_traverse_win stays in use)
+  if (out.slotsn.size() >= (1u << (kSlotNChildBits - 1)) || out.leaf_oid.size() >= (1u << (kSlotNChildBits - 1))) { out.slotsn.clear(); out.nroot.clear(); }
   return CRF_OK;
 }
 

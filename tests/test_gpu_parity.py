@@ -133,7 +133,7 @@ def test_forest_leaf_ids_synthetic_model(O, sctx, synth_models, stride, H, W):
     s.close()
 
 
-@pytest.mark.parametrize("win", ["default", "rows", "pairx"])
+@pytest.mark.parametrize("win", ["default", "rows", "pairx", "fmt1", "win2_15x2"])
 @pytest.mark.parametrize("H,W,nt", [(125, 125, 20), (148, 124, 20), (33, 125, 7), (40, 125, 23), (200, 125, 20), (32, 125, 20), (70, 124, 41)])
 def test_window_traversal_forced(O, crf, gpu, synth_models, monkeypatch, H, W, nt, win):
     """k_traverse_win (shared-memory window, ring rows, two walks per lane) on one ragged face: partial tiles right and
@@ -146,6 +146,10 @@ def test_window_traversal_forced(O, crf, gpu, synth_models, monkeypatch, H, W, n
         monkeypatch.setenv("CRF_WIN_HP", str(30 | 1 << 8)); monkeypatch.setenv("CRF_WIN_FFD", str(20 | 2 << 8))
     elif win == "pairx":
         monkeypatch.setenv("CRF_WIN_HP", str(15 | 2 << 8 | 1 << 12)); monkeypatch.setenv("CRF_WIN_FFD", str(20 | 2 << 8 | 1 << 12))
+    elif win == "fmt1":   # k_traverse_win on the records that keep leaf slots (the default is k_traverse_win2 on DevSlotN)
+        monkeypatch.setenv("CRF_WIN_FMT", "1")
+    elif win == "win2_15x2":   # k_traverse_win2 with the pipelined two-walk loop for both forests
+        monkeypatch.setenv("CRF_WIN_HP", str(15 | 2 << 8)); monkeypatch.setenv("CRF_WIN_FFD", str(24 | 2 << 8))
     ctx = crf.Context(gm, 0)
     ctx.set_profiling(False, True)
     rng = np.random.default_rng(H * 7 + nt)
