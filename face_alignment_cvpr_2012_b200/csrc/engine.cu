@@ -357,7 +357,8 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, cons
   const dim3 grid((Hmax + 15) / 16, 7, n);
   float* mag = c->w->d_mag.as<float>();
   uint32_t* mm = c->w->d_minmax.as<uint32_t>();
-  const dim3 gsym((Hmax + 15) / 16, n);
+  // small batches (single faces, one video frame): one CTA per (band, face, orientation) instead of a loop over the orientations
+  const dim3 gsym((Hmax + 15) / 16, n, 2LL * n * ((Hmax + 15) / 16) <= c->sm_count ? 7 : 1);
   // 9x9 .. 25x25 in separable form (heaviest first), 7x7 as the direct raster sum that equals cv2 bit for bit
   k_gabor_sep<25><<<gsym, 256, GaborSepSmem<25>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[4].as<float>(), 4, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
   k_gabor_sep<19><<<gsym, 256, GaborSepSmem<19>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[3].as<float>(), 3, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();

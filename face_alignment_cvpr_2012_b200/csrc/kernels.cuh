@@ -457,9 +457,11 @@ __global__ void __launch_bounds__(256, 3) k_gabor_sep(const FaceDesc* __restrict
     }
   }
   __syncthreads();
-  // ---- the 7 orientations
+  // ---- the 7 orientations (all of them, or the one blockIdx.z names: small batches spread the orientations over CTAs for latency,
+  //      each recomputing the Gaussian pair above)
+  const int mu_begin = gridDim.z == 7 ? blockIdx.z : 0, mu_end = gridDim.z == 7 ? mu_begin + 1 : 7;
 #pragma unroll 1
-  for (int mu = 0; mu < 7; mu++) {
+  for (int mu = mu_begin; mu < mu_end; mu++) {
     const float2* hxm = hx + mu * K;
     const float2* hym = hy + mu * K;
 #pragma unroll 1
