@@ -12,7 +12,7 @@ reduction are the only torch.distributed calls.
            the library's stream, max over ranks.
 `e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers (crf_analyze_crops):
            pinned host crops -> H2D -> path -> D2H of the crf_face_t results, every step.
-`roofline`: the dominant kernel (FFD forest traversal, k_traverse_win).  achieved / peak / frac are the contract's
+`roofline`: the dominant kernel (FFD forest traversal, k_traverse_win2).  achieved / peak / frac are the contract's
            HBM-EQUIVALENT figure: algorithmic bytes (48 B per node test + 4 B per leaf written) / the kernel's
            CUDA-event duration inside the timed region, against the measured HBM copy peak.  The gathers are served from a
            shared-memory window, so this is NOT a DRAM roofline (it exceeds 1); `roofline.physical` holds what bounds the
@@ -502,7 +502,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             wf = k["lds_wavefronts_per_node_test"] * tests            # shared-memory wavefronts of the launch
             peak_wf = n_sm * sm_clock * 1e6                            # one wavefront per SM and clock
             dram = k["dram_bytes_per_face"] * F
-            return {"bound": "l1/shared data pipe (LSU wavefronts) + node-record latency; not HBM",
+            return {"bound": "l1/shared data pipe (LSU wavefronts: 63 % of them bank conflicts between diverged lanes) + texture pipe (node records); not HBM",
                     "lds_wavefronts_per_s": wf / (t_ms * 1e-3), "peak_wavefronts_per_s": peak_wf, "frac": wf / (t_ms * 1e-3) / peak_wf,
                     "lds_wavefronts_per_load": k.get("lds_wavefronts_per_load"), "issue_active_pct": k.get("issue_active_pct"),
                     "long_scoreboard_stall_pct": k.get("long_scoreboard_stall_pct"),
@@ -521,14 +521,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_traverse_win<20,2> (FFD forest, stride 1, shared-memory window)", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "roofline": {"kernel": "k_traverse_win2<20,2> (FFD forest, stride 1, shared-memory window, pipelined two-walk loop)", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": phys["dram_bytes_per_launch"] / launches_ffd if phys else None, "peak_kind": peak_kind,
                          "label": "HBM-EQUIVALENT of the SURVEY 8(d) algorithmic bytes (48 B per node test + 4 B per leaf), not a DRAM roofline: the gathers are served "
                                   "from a shared-memory window, so it exceeds 1; see `physical`",
                          "alg_bytes_per_launch": alg_bytes / launches_ffd, "launches_per_step": launches_ffd, "ms_per_step": ffd_ms, "physical": phys},
             "stages_ms_per_step": per_step,
             "kernels": [
-                {"kernel": "k_traverse_win<30,1> (head-pose forest)", "ms_per_step": hp_ms,
+                {"kernel": "k_traverse_win2<32,1> (head-pose forest)", "ms_per_step": hp_ms,
                  "hbm_equivalent_gbs": (48 * work["hp_node_tests"] + 4 * work["hp_traversals"]) / (hp_ms * 1e-3) / 1e9 if hp_ms > 0 else 0.0,
                  "physical": physical("k_traverse_win_hp", work["hp_node_tests"], hp_ms)},
                 {"kernel": "k_gabor_sep<9..25> + k_gabor_mag<7> + quantise/integral", "bound": "fp32 issue (non-tensor FFMA) + shared-memory operands", "ms_per_step": gabor_ms,
