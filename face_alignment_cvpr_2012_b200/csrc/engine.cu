@@ -1388,13 +1388,22 @@ int crf_analyze_crops_device(crf_ctx* c, const uint8_t* d_bgr_batch, int n, int 
   c->w = &c->ws[0];
   if (!headpose_only) {
     // faces whose composition or vote count exceeded the batched capacities: fetch the flags, re-run those faces wide
-    std::vector<crf_face_t> tmp((size_t)n);
-    CU(cudaMemcpyAsync(tmp.data(), d_out, (size_t)n * sizeof(crf_face_t), cudaMemcpyDeviceToHost, s0));
+    // (4 bytes come back, not the records: the flag is counted on the device)
+    int n_wide = 0;
+    CU(cudaMemsetAsync(c->d_misc.p, 0, 4, s0));
+    k_count_wide<<<(n + 255) / 256, 256, 0, s0>>>(d_out, n, c->d_misc.as<int>());
+    KCHECK(); count_launch(c, CRF_STAGE_MEANSHIFT);
+    CU(cudaMemcpyAsync(&n_wide, c->d_misc.p, 4, cudaMemcpyDeviceToHost, s0));
     CU(cudaStreamSynchronize(s0));
-    std::vector<int> wide;
-    for (int i = 0; i < n; i++) if (tmp[(size_t)i].flags & 6) wide.push_back(i);
-    if (!wide.empty() && (rc = rerun_wide(c, c->d_fd.as<FaceDesc>(), descs, d_bgr_batch, d_out, wide))) return rc;
-    CU(cudaStreamSynchronize(s0));
+    if (n_wide > 0) {
+      std::vector<crf_face_t> tmp((size_t)n);
+      CU(cudaMemcpyAsync(tmp.data(), d_out, (size_t)n * sizeof(crf_face_t), cudaMemcpyDeviceToHost, s0));
+      CU(cudaStreamSynchronize(s0));
+      std::vector<int> wide;
+      for (int i = 0; i < n; i++) if (tmp[(size_t)i].flags & 6) wide.push_back(i);
+      if (!wide.empty() && (rc = rerun_wide(c, c->d_fd.as<FaceDesc>(), descs, d_bgr_batch, d_out, wide))) return rc;
+      CU(cudaStreamSynchronize(s0));
+    }
   }
   c->cnt.faces += n;
   c->timer.collect();

@@ -973,6 +973,15 @@ __global__ void __launch_bounds__(256, 2) k_gabor_fused7(GaborFusedArgs g, const
   }
 }
 
+// Number of faces whose record asks for the wide re-run (flags bits 1-2): lets the device-resident entry point fetch 4 bytes instead of
+// every record when, as always with real inputs, no face overflowed the batched capacities.
+__global__ void k_count_wide(const crf_face_t* __restrict__ faces, int n, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool wide = i < n && (faces[i].flags & 6) != 0;
+  const unsigned b = __ballot_sync(0xffffffffu, wide);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
+}
+
 __global__ void k_init_minmax(uint32_t* mm, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) mm[i] = (i & 1) ? 0u : 0x7f800000u;
