@@ -141,8 +141,9 @@ int crf_model_leaf_dump(const crf_model* m, int which, int tree, float* out, int
 /* Pre-order dump of one tree (which = -1 head pose, 0..4 pose forest), 16 ints per node:
  * [is_leaf, depth, ch, r1x,r1y,r1w,r1h, r2x,r2y,r2w,r2h, thr, left_oid, right_oid, nsamples, object_id] */
 int crf_model_tree_dump(const crf_model* m, int which, int tree, int32_t* out, int cap_nodes);
-/* Host-only self-check of the device image of the forests (the three node-record forms the kernels read agree, children are
- * adjacent, window leaves self-loop); returns the number of records checked or a negative status. */
+/* Host-only self-check of the device image of the forests (the node-record forms the kernels read agree: wide, compact, window, and
+ * the internal-nodes-only form walked from every root; children are adjacent, window leaves self-loop); returns the number of records
+ * checked or a negative status. */
 int crf_model_check_packing(const crf_model* m, int* max_extent_hp, int* max_extent_ffd);
 void crf_model_free(crf_model* m);
 
