@@ -190,6 +190,7 @@ struct crf_ctx {
   // the same kernel).  Bit-identical and MEASURED SLOWER on B200 (30.4 vs 22.3 ms per 4096 faces: the serial phases of a CTA that owns a whole
   // plane cost more than the 27 % of multiply-adds and the 18 GB of DRAM traffic it saves), so the banded kernels stay the default.
   int gabor_fused = 0;
+  int gabor_band = 16;       // rows per CTA of k_gabor_sep (CRF_GABOR_BAND = 16 | 32)
   int gabor_quant_old = 0;   // CRF_GABOR_QUANT_OLD=1: k_gabor_quant_integral (one column per thread) instead of k_gabor_quant_band
   int ms_mode = CRF_MS_FAST;   // resolved from crf_options_t::ms_mode / CRF_MS_MODE at creation
   int ms_variant = 3;   // resident MeanShift CTAs per SM the kernel is compiled for (register cap); CRF_MS_VARIANT overrides
@@ -358,12 +359,21 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, cons
   float* mag = c->w->d_mag.as<float>();
   uint32_t* mm = c->w->d_minmax.as<uint32_t>();
   // small batches (single faces, one video frame): one CTA per (band, face, orientation) instead of a loop over the orientations
-  const dim3 gsym((Hmax + 15) / 16, n, 2LL * n * ((Hmax + 15) / 16) <= c->sm_count ? 7 : 1);
   // 9x9 .. 25x25 in separable form (heaviest first), 7x7 as the direct raster sum that equals cv2 bit for bit
-  k_gabor_sep<25><<<gsym, 256, GaborSepSmem<25>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[4].as<float>(), 4, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
-  k_gabor_sep<19><<<gsym, 256, GaborSepSmem<19>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[3].as<float>(), 3, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
-  k_gabor_sep<13><<<gsym, 256, GaborSepSmem<13>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[2].as<float>(), 2, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
-  k_gabor_sep<9><<<gsym, 256, GaborSepSmem<9>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[1].as<float>(), 1, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  if (c->gabor_band == 32) {
+    const int nb = (Hmax + 31) / 32;
+    const dim3 g32(nb, n, 2LL * n * nb <= c->sm_count ? 7 : 1);
+    k_gabor_sep<25, 32><<<g32, 512, GaborSepSmem<25, 32>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[4].as<float>(), 4, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+    k_gabor_sep<19, 32><<<g32, 512, GaborSepSmem<19, 32>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[3].as<float>(), 3, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+    k_gabor_sep<13, 32><<<g32, 512, GaborSepSmem<13, 32>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[2].as<float>(), 2, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+    k_gabor_sep<9, 32><<<g32, 512, GaborSepSmem<9, 32>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[1].as<float>(), 1, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  } else {
+    const dim3 gsym((Hmax + 15) / 16, n, 2LL * n * ((Hmax + 15) / 16) <= c->sm_count ? 7 : 1);
+    k_gabor_sep<25><<<gsym, 256, GaborSepSmem<25>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[4].as<float>(), 4, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+    k_gabor_sep<19><<<gsym, 256, GaborSepSmem<19>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[3].as<float>(), 3, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+    k_gabor_sep<13><<<gsym, 256, GaborSepSmem<13>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[2].as<float>(), 2, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+    k_gabor_sep<9><<<gsym, 256, GaborSepSmem<9>::bytes, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef_sep[1].as<float>(), 1, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
+  }
   k_gabor_mag<7><<<grid, 256, 0, c->w->stream>>>(fd, sc, c->w->scaled_fs, c->d_coef[0].as<float2>(), 0, mag, c->w->mag_fs, c->w->mag_ps, mm); KCHECK();
   {
     GaborFusedArgs g{};
@@ -1155,6 +1165,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if (const char* v = std::getenv("CRF_WIN_FFD")) c->win_ffd = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_GABOR_FUSED")) c->gabor_fused = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_GABOR_QUANT_OLD")) c->gabor_quant_old = (int)std::strtol(v, nullptr, 0);
+  if (const char* v = std::getenv("CRF_GABOR_BAND")) c->gabor_band = std::strtol(v, nullptr, 0) == 32 ? 32 : 16;
   if (const char* v = std::getenv("CRF_MS_VARIANT")) c->ms_variant = (int)std::strtol(v, nullptr, 0);
   c->ms_mode = c->opt.ms_mode == CRF_MS_EXACT ? CRF_MS_EXACT : CRF_MS_FAST;
   if (c->opt.ms_mode == CRF_MS_DEFAULT)
@@ -1269,6 +1280,10 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   CU(cudaFuncSetAttribute(k_gabor_sep<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<19>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_sep<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<13>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_sep<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<9>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_sep<25, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<25, 32>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_sep<19, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<19, 32>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_sep<13, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<13, 32>::bytes));
+  CU(cudaFuncSetAttribute(k_gabor_sep<9, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<9, 32>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_fused<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<25>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_fused<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<19>::bytes));
   CU(cudaFuncSetAttribute(k_gabor_fused<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GaborSepSmem<13>::bytes));

@@ -2,6 +2,8 @@
 ImageSample::evalTest) and contexts on partial models — each against the oracle."""
 from pathlib import Path
 
+import os
+
 import numpy as np
 import pytest
 
@@ -147,11 +149,16 @@ def test_fused_and_banded_gabor_kernels_agree(crf, O, gpu, synth_models, monkeyp
     monkeypatch.setenv("CRF_GABOR_QUANT_OLD", "1")
     old_quant = crf.Context(None, 0)
     monkeypatch.delenv("CRF_GABOR_QUANT_OLD")
+    monkeypatch.setenv("CRF_GABOR_BAND", "32" if os.environ.get("CRF_GABOR_BAND", "") != "32" else "16")   # the band height that is NOT the default
+    other_band = crf.Context(None, 0)
+    monkeypatch.delenv("CRF_GABOR_BAND")
     for img in imgs:
         pf, jf = fused.stage_channels(img)
         pb, jb = banded.stage_channels(img)
         pq, jq = old_quant.stage_channels(img)
+        po, jo = other_band.stage_channels(img)
         assert np.array_equal(pf, pb) and np.array_equal(jf, jb) and np.array_equal(pq, pb) and np.array_equal(jq, jb), img.shape
+        assert np.array_equal(po, pb) and np.array_equal(jo, jb), img.shape
         op, oi = O.channels(img)
         assert np.array_equal(pf, op) and np.array_equal(jf, oi.astype(np.uint32)), img.shape
     crops, _ = wl.make_crops(700, seed=8)     # more faces than resident CTAs: every persistent CTA takes several items
