@@ -281,9 +281,11 @@ def run_reference(args, rank: int, world: int):
 
 
 # FFMA the Gabor kernels execute per output pixel (2 flops each), counted from their loop structure: for a K x K kernel in separable
-# form the row pass does (7 x 2 + 1) K multiply-adds on the (16 + K - 1) rows a 16-row band needs, the column pass (7 x 4 + 1) K;
-# the 7 x 7 scale is the direct sum, 49 taps x 7 orientations x (re, im) with separately rounded multiply and add.
-GABOR_EXECUTED_FLOP_PER_PIXEL = sum(2 * (15 * K * (15 + K) / 16 + 29 * K) for K in (9, 13, 19, 25)) + 2 * 49 * 7 * 2
+# form the row pass does (7 x 2 + 1) K multiply-adds on the (BAND + K - 1) rows a BAND-row band needs (BAND = 32, the library default; the
+# 125-row crops of this workload take 4 bands of 32 rows), the column pass (7 x 4 + 1) K; the 7 x 7 scale is the direct sum, 49 taps x 7
+# orientations x (re, im) with separately rounded multiply and add.
+GABOR_BAND = 32
+GABOR_EXECUTED_FLOP_PER_PIXEL = sum(2 * (15 * K * (GABOR_BAND - 1 + K) / GABOR_BAND + 29 * K) for K in (9, 13, 19, 25)) + 2 * 49 * 7 * 2
 
 
 def other_workloads(crf, wl, torch, gm, om, local_rank, dev, crops, args):
@@ -534,7 +536,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 {"kernel": "k_gabor_sep<9..25> + k_gabor_mag<7> + quantise/integral", "bound": "fp32 issue (non-tensor FFMA) + shared-memory operands", "ms_per_step": gabor_ms,
                  "achieved": GABOR_EXECUTED_FLOP_PER_PIXEL * 125 * 125 * F / (gabor_ms * 1e-3) / 1e12 if gabor_ms > 0 else 0.0,
                  "peak": n_sm * 128 * 2 * sm_clock * 1e6 / 1e12, "unit": "TFLOP/s",
-                 "note": f"EXECUTED flops: {GABOR_EXECUTED_FLOP_PER_PIXEL:.0f} per pixel (separable 9..25 kernels incl. the halo rows of every 16-row band, direct 7x7), "
+                 "note": f"EXECUTED flops: {GABOR_EXECUTED_FLOP_PER_PIXEL:.0f} per pixel (separable 9..25 kernels incl. the halo rows of every 32-row band, direct 7x7), "
                          "not the 35 980 of the direct form"},
                 {"kernel": "k_votes_count / offsets / emit", "bound": "hbm (latency / divergence limited)", "ms_per_step": per_step["votes"],
                  "achieved": (8 * work["ffd_traversals"] + 8 * work["votes"]) / (per_step["votes"] * 1e-3) / 1e9 if per_step["votes"] > 0 else 0.0, "peak": peaks["hbm_gbs"], "unit": "GB/s",

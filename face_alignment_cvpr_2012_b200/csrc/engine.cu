@@ -190,7 +190,7 @@ struct crf_ctx {
   // the same kernel).  Bit-identical and MEASURED SLOWER on B200 (30.4 vs 22.3 ms per 4096 faces: the serial phases of a CTA that owns a whole
   // plane cost more than the 27 % of multiply-adds and the 18 GB of DRAM traffic it saves), so the banded kernels stay the default.
   int gabor_fused = 0;
-  int gabor_band = 16;       // rows per CTA of k_gabor_sep (CRF_GABOR_BAND = 16 | 32)
+  int gabor_band = 32;       // rows per CTA of k_gabor_sep (CRF_GABOR_BAND = 16 | 32): 32 repeats fewer halo rows in the row pass, 21.7 -> 20.1 ms per 4096 faces
   int gabor_quant_old = 0;   // CRF_GABOR_QUANT_OLD=1: k_gabor_quant_integral (one column per thread) instead of k_gabor_quant_band
   int ms_mode = CRF_MS_FAST;   // resolved from crf_options_t::ms_mode / CRF_MS_MODE at creation
   int ms_variant = 3;   // resident MeanShift CTAs per SM the kernel is compiled for (register cap); CRF_MS_VARIANT overrides
@@ -1165,7 +1165,7 @@ int crf_ctx_create(const crf_model* m, int device, const crf_options_t* opt, crf
   if (const char* v = std::getenv("CRF_WIN_FFD")) c->win_ffd = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_GABOR_FUSED")) c->gabor_fused = (int)std::strtol(v, nullptr, 0);
   if (const char* v = std::getenv("CRF_GABOR_QUANT_OLD")) c->gabor_quant_old = (int)std::strtol(v, nullptr, 0);
-  if (const char* v = std::getenv("CRF_GABOR_BAND")) c->gabor_band = std::strtol(v, nullptr, 0) == 32 ? 32 : 16;
+  if (const char* v = std::getenv("CRF_GABOR_BAND")) c->gabor_band = std::strtol(v, nullptr, 0) == 16 ? 16 : 32;
   if (const char* v = std::getenv("CRF_MS_VARIANT")) c->ms_variant = (int)std::strtol(v, nullptr, 0);
   c->ms_mode = c->opt.ms_mode == CRF_MS_EXACT ? CRF_MS_EXACT : CRF_MS_FAST;
   if (c->opt.ms_mode == CRF_MS_DEFAULT)
