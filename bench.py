@@ -403,6 +403,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             dist.barrier()
             torch.cuda.synchronize()
 
+    host_group = dist.new_group(backend="gloo") if dist is not None else None
+
     # ---- work counters of one step (exact, counted on the device; outside the timed region)
     ctx.set_profiling(False, True)
     ctx.reset_counters()
@@ -576,7 +578,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             line["single_caller"] = single_caller(crf, torch, gm, crops, args)
         print_line(json.dumps(line))
     if dist is not None:
-        dist.barrier()
+        # The other ranks wait for rank 0's extra measurements on the HOST (gloo): an NCCL barrier would park a spinning kernel on their
+        # GPUs, and the single-caller pass above runs on every GPU of the box (its persistent traversal CTAs would queue behind it).
+        dist.barrier(group=host_group)
         dist.destroy_process_group()
     return 0
 
