@@ -1915,15 +1915,26 @@ __global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
   int leaf_n = 0;
   unsigned mask_n = 0;
   if (k0 + lane < k1) { leaf_n = ids[k0 + lane]; mask_n = __ldg(a.mp_mask + leaf_n); }
+  // Ranks of a step's votes inside their part lists WITHOUT a ballot + POPC per part (POPC issues at a quarter of the ALU rate and there
+  // were twenty per step): every lane spreads its 10-bit mask into ten 6-bit fields of two words (spread5, as in k_votes_count), an
+  // inclusive scan over the lanes (5 shuffle steps on the two words; a field holds at most 32) gives all ten ranks at once, and lane
+  // 31's words are the step's totals.
+  auto spread5 = [](unsigned x) { return (x * 0x108421u) & 0x01041041u; };
   for (int k = k0 + lane; k - lane < k1; k += 32) {
     const int leaf = leaf_n;
     const unsigned mask = mask_n;
     leaf_n = 0; mask_n = 0;
     if (k + 32 < k1) { leaf_n = ids[k + 32]; mask_n = __ldg(a.mp_mask + leaf_n); }   // next step's gathers overlap this step's emission
-    unsigned bal[kParts];
+    const unsigned own_lo = spread5(mask & 31u), own_hi = spread5(mask >> 5);
+    unsigned lo = own_lo, hi = own_hi;
 #pragma unroll
-    for (int p = 0; p < kParts; p++) bal[p] = __ballot_sync(0xffffffffu, (mask >> p) & 1u);
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned nl = __shfl_up_sync(0xffffffffu, lo, o), nh = __shfl_up_sync(0xffffffffu, hi, o);
+      if (lane >= o) { lo += nl; hi += nh; }
+    }
+    const unsigned tot_lo = __shfl_sync(0xffffffffu, lo, 31), tot_hi = __shfl_sync(0xffffffffu, hi, 31);
     if (mask) {
+      const unsigned ex_lo = lo - own_lo, ex_hi = hi - own_hi;   // votes of the lanes before this one, per part
       const int patch = nt == 1 ? k : (int)__umulhi((unsigned)k, m_nt);
       const int ix = ny == 1 ? patch : (int)__umulhi((unsigned)patch, m_ny), iy = patch - ix * ny;
       const int cx = ix * a.stride + kHalfPatch, cy = iy * a.stride + kHalfPatch;  // patch centre (src/face_utils.cpp:281-282)
@@ -1938,12 +1949,12 @@ __global__ void __launch_bounds__(256) k_votes_emit(VoteArgs a) {
           v.x = (short)(L.off[p][0] + cx);
           v.y = (short)(L.off[p][1] + cy);
           v.w = L.weight;
-          fv[base[p] + __popc(bal[p] & ((1u << lane) - 1u))] = v;
+          fv[base[p] + (int)(((p < 5 ? ex_lo : ex_hi) >> (6 * (p % 5))) & 63u)] = v;
         }
       }
     }
 #pragma unroll
-    for (int p = 0; p < kParts; p++) base[p] += __popc(bal[p]);
+    for (int p = 0; p < kParts; p++) base[p] += (int)(((p < 5 ? tot_lo : tot_hi) >> (6 * (p % 5))) & 63u);
   }
 }
 
