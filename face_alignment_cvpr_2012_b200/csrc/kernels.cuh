@@ -1626,8 +1626,8 @@ __device__ __forceinline__ void compose_face(float headpose, float variance, con
                                              crf_face_t* face, int32_t* list, int32_t* ntrees_out) {
   // areaUnderCurve(x1, x2, mean, std): lanes evaluate exp() of their abscissae, lane 0 folds in order.
   const double mean = (double)headpose, sd = sqrt((double)variance);
-  __shared__ double s_e[9][32];
-  double* e = s_e[(threadIdx.x >> 5) % 9];
+  __shared__ double s_e[10][32];   // one slot per warp of the callers (at most 10 warps: k_hp_reduce_compose)
+  double* e = s_e[(threadIdx.x >> 5) % 10];
   float area[CRF_NUM_POSE_FORESTS];
   for (int j = 0; j < CRF_NUM_POSE_FORESTS; j++) {
     double sum = 0;
@@ -1682,15 +1682,16 @@ constexpr int kFoldChains = 32;
 constexpr int kFoldThreads = 288;  // warp 0 folds, warps 1..8 produce (4 chains each)
 
 constexpr int kHpTile = 256;
-constexpr size_t kHpSmem = (size_t)2 * kHpTile * 33 * sizeof(float);  // dynamic shared memory of k_hp_reduce_compose
+constexpr int kHpPitch = kHpTile + 4;   // chain-major tiles: 260 == 4 (mod 32), so the 8 lanes of a quarter warp reading 16 B each hit 32 different banks
+constexpr size_t kHpSmem = (size_t)2 * kFoldChains * kHpPitch * sizeof(float);  // dynamic shared memory of k_hp_reduce_compose
 
 __global__ void __launch_bounds__(kFoldThreads) k_hp_reduce_compose(const FaceDesc* __restrict__ fd, int nfaces, const float* __restrict__ leaf_m, size_t leaf_face_stride,
                                                                     int ntrees, int stride, ComposeTables ct, int do_compose,
                                                                     crf_face_t* __restrict__ faces, int32_t* __restrict__ face_roots, int32_t* __restrict__ face_ntrees) {
   extern __shared__ __align__(16) float s_hp_dyn[];
-  typedef float HpTile[kHpTile][33];
+  typedef float HpTile[kFoldChains][kHpPitch];   // [chain][element]: producers write coalesced rows, the fold lane reads its row by float4
   HpTile* s_m = reinterpret_cast<HpTile*>(s_hp_dyn);  // [2]
-  __shared__ int s_n[kFoldChains];
+  __shared__ int s_n[kFoldChains], s_cnt[kFoldChains];
   __shared__ float s_mean[kFoldChains], s_var[kFoldChains];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f0 = blockIdx.x * kFoldChains;
@@ -1703,53 +1704,78 @@ __global__ void __launch_bounds__(kFoldThreads) k_hp_reduce_compose(const FaceDe
       n = max(nx, 0) * max(ny, 0) * ntrees;
     }
     s_n[threadIdx.x] = n;
+    s_cnt[threadIdx.x] = 0;
   }
   __syncthreads();
   int maxn = 0;
   for (int j = 0; j < kFoldChains; j++) maxn = max(maxn, s_n[j]);
   const int ntiles = (maxn + kHpTile - 1) / kHpTile;
-  auto produce = [&](int tile) {
-    float(*buf)[33] = s_m[tile & 1];
+  // The producers do everything of the reference's loop body that is not the order-dependent sum (src/face_utils.cpp:222-231): the
+  // fg > min_foreground_probability test is folded into the table at load time (-1 = skip), a skipped vote is stored as +0 (adding +0 is
+  // exact: the sums never hold -0), and the votes are counted as integers (the reference's float count of 1.0s is exact below 2^24).  The
+  // single fold warp is left with load, add, multiply, add per element (a second fold warp for the sum of squares was measured: no gain, the
+  // dependent add chain of the sum is the critical path).  This fold is the latency of a single-face call at stride 1.
+  int valid_count[4] = {0, 0, 0, 0};
+  // A producer keeps the NEXT tile's values in registers across the barrier (loads issued one iteration before they are stored), so the
+  // global-load latency overlaps the fold of a whole tile: with a single live chain the fold is otherwise faster than the load.
+  float pv[4][kHpTile / 32];
+  auto load_tile = [&](int tile) {
 #pragma unroll
     for (int jj = 0; jj < 4; jj++) {
       const int j = (warp - 1) * 4 + jj;
       const int n = s_n[j];
-      if (tile * kHpTile >= n) continue;
       const float* __restrict__ ms = leaf_m + (size_t)(f0 + j) * leaf_face_stride;
-      float v[kHpTile / 32];
 #pragma unroll
       for (int h = 0; h < kHpTile / 32; h++) {
         const int k = tile * kHpTile + h * 32 + lane;
-        v[h] = k < n ? ms[k] : -1.f;
+        pv[jj][h] = k < n ? ms[k] : -1.f;
       }
-#pragma unroll
-      for (int h = 0; h < kHpTile / 32; h++) buf[h * 32 + lane][j] = v[h];
     }
   };
-  float cnt = 0, sum = 0, sum_sq = 0;
-  if (warp > 0 && ntiles > 0) produce(0);
+  auto store_tile = [&](int tile) {
+    float(*buf)[kHpPitch] = s_m[tile & 1];
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int j = (warp - 1) * 4 + jj;
+      if (tile * kHpTile >= s_n[j]) continue;
+#pragma unroll
+      for (int h = 0; h < kHpTile / 32; h++) {
+        const bool valid = !(pv[jj][h] < 0.f);
+        valid_count[jj] += __popc(__ballot_sync(0xffffffffu, valid));
+        buf[j][h * 32 + lane] = valid ? pv[jj][h] : 0.f;
+      }
+    }
+  };
+  float sum = 0, sum_sq = 0;
+  if (warp > 0 && ntiles > 0) { load_tile(0); store_tile(0); if (ntiles > 1) load_tile(1); }
   __syncthreads();
   for (int tile = 0; tile < ntiles; tile++) {
     if (warp == 0) {
-      const float(*buf)[33] = s_m[tile & 1];
-      const int kmax = min(kHpTile, s_n[lane] - tile * kHpTile);
+      const float4* row = reinterpret_cast<const float4*>(s_m[tile & 1][lane]);
+      // the producers stop refreshing the row of a chain that has ended, so its lane adds +0 from here on
+      const bool live = tile * kHpTile < s_n[lane];
 #pragma unroll 8
-      for (int k = 0; k < kHpTile; k++) {
-        // fg > min_foreground_probability is folded into the table at load time (-1 = skip).  Adding +0 is exact
-        // (the sums never hold -0), so the fold is branch-free.
-        const float m = buf[k][lane];
-        const bool valid = k < kmax && !(m < 0.f);
-        const float v = valid ? m : 0.f;
-        sum += v;
-        sum_sq += v * v;
-        cnt += valid ? 1.f : 0.f;
+      for (int k4 = 0; k4 < kHpTile / 4; k4++) {
+        float4 v = row[k4];
+        if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        sum += v.x; sum_sq += v.x * v.x;
+        sum += v.y; sum_sq += v.y * v.y;
+        sum += v.z; sum_sq += v.z * v.z;
+        sum += v.w; sum_sq += v.w * v.w;
       }
     } else if (tile + 1 < ntiles) {
-      produce(tile + 1);
+      store_tile(tile + 1);
+      if (tile + 2 < ntiles) load_tile(tile + 2);
     }
     __syncthreads();
   }
+  if (warp > 0 && lane == 0) {
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) if (valid_count[jj]) atomicAdd(&s_cnt[(warp - 1) * 4 + jj], valid_count[jj]);
+  }
+  __syncthreads();
   if (warp == 0) {
+    const float cnt = (float)s_cnt[lane];
     float mean = sum / cnt;
     float var = (sum_sq / cnt) - (mean * mean);
     mean -= 2;
