@@ -169,6 +169,38 @@ def test_window_traversal_forced(O, crf, gpu, synth_models, monkeypatch, H, W, n
     ctx.close()
 
 
+@pytest.mark.parametrize("depth", [0, 1, 2])
+def test_degenerate_forests_through_every_traversal(O, crf, gpu, tmp_path, monkeypatch, depth):
+    """Forests of one-leaf trees (depth 0: the root is a leaf, so the internal-nodes-only record array of k_traverse_win2 is empty and the
+    root tag is ~leaf), of three-node trees and of depth-2 trees: leaf ids and whole records against the oracle through the window kernels
+    (both record formats) and the global-gather kernels."""
+    from face_alignment_cvpr_2012_b200 import synthetic_model as sm, workloads as wl
+    hp, ffd = sm.write_model(tmp_path / f"d{depth}", seed=40 + depth, hp_depth=depth, ffd_depth=depth)
+    gm, om = crf.Model(hp, ffd, 15, 20), O.Model(hp, ffd, 15, 20)
+    rng = np.random.default_rng(depth)
+    planes = _planes(rng, 38, 125, 125, smooth=True)
+    s = O.Sample(planes=planes)
+    ids_o, _, _, _ = om.eval_hp(s, 1)
+    fi = rng.integers(0, 5, 20); ti = rng.integers(0, 20, 20)
+    e = om.eval_ffd(s, fi, ti, 1)
+    crops, _ = wl.make_crops(48, seed=5)
+    want = [om.analyze_face(c, (0, 0, 100, 100), 1, 1) for c in crops[:3]]
+    for env in ({"CRF_TRAVERSE_VARIANT": "0x100001"}, {"CRF_TRAVERSE_VARIANT": "0x100001", "CRF_WIN_FMT": "1"}, {"CRF_TRAVERSE_VARIANT": hex(32 | (4 << 8) | (10 << 16))}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = crf.Context(gm, 0, crf._options(None, hp_stride=1, ffd_stride=1))
+        assert np.array_equal(ctx.stage_eval_forest(planes, 1), ids_o), env
+        assert np.array_equal(ctx.stage_eval_forest(planes, 1, fi, ti), e["leaf_ids"]), env
+        got = ctx.analyze_crops(crops)
+        for i, w in enumerate(want):
+            assert got[i]["headpose"] == w["headpose"] and (got[i]["n_votes"] == w["n_votes"]).all() and (got[i]["tree_counts"] == w["tree_counts"]).all(), (env, i)
+            assert float(np.nanmax(np.abs(got[i]["ffd_f"] - w["ffd_f"]))) <= 0.5 or not np.isfinite(w["ffd_f"]).all(), (env, i)
+        ctx.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    s.close()
+
+
 def test_window_and_gather_traversals_agree_in_batches(crf, gpu, synth_models, monkeypatch):
     """Whole pipeline at stride 1 on 80 crops: the default (window kernel, persistent CTAs over (face, column) items) against
     the global-gather kernels forced through CRF_TRAVERSE_VARIANT; records must be byte-identical."""
