@@ -355,7 +355,7 @@ static int launch_channels(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, cons
   }
   k_init_minmax<<<(n * 70 + 255) / 256, 256, 0, c->w->stream>>>(c->w->d_minmax.as<uint32_t>(), n * 70);
   KCHECK();
-  const dim3 grid((Hmax + 15) / 16, 7, n);
+  const dim3 grid((Hmax + 15) / 16, 2LL * n * ((Hmax + 15) / 16) <= c->sm_count ? 7 : 1, n);   // k_gabor_mag<7>: orientations in the CTA, or one CTA each for small batches
   float* mag = c->w->d_mag.as<float>();
   uint32_t* mm = c->w->d_minmax.as<uint32_t>();
   // small batches (single faces, one video frame): one CTA per (band, face, orientation) instead of a loop over the orientations

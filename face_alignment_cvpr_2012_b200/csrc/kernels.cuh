@@ -290,22 +290,28 @@ __global__ void __launch_bounds__(256, 2) k_gabor_mag(const FaceDesc* __restrict
   const int W = d.W, H = d.H;
   const int r0 = blockIdx.x * G::BAND;
   if (r0 >= H) return;
-  const int mu = blockIdx.y, plane = nu * 7 + mu;
   const int tid = threadIdx.x;
   const uint8_t* __restrict__ g = scaled + blockIdx.z * scaled_face_stride;
-  for (int i = tid; i < K * KP; i += 256) {
-    const int jj = i / KP, ii = i - jj * KP;
-    cf[jj][ii] = ii < K ? coef[mu * K * K + jj * K + ii] : make_float2(0.f, 0.f);
-  }
   for (int i = tid; i < G::TH * G::PITCH; i += 256) {
     const int ty = i / G::PITCH, tx = i - ty * G::PITCH;
     const int sy = border101(r0 + ty - G::R, H), sx = border101(tx - G::R, W);
     tile[ty][tx] = (float)g[(size_t)sy * 128 + sx];
   }
-  __syncthreads();
   // each thread: two 1 x 4 strips, rows rA and rA + 8 of the band, sharing every coefficient load
   const int x0 = (tid & 31) * 4;
   const int rA = tid >> 5;
+  // the 7 orientations on one tile (the tile load was 20 % of the kernel's instructions when every orientation had its own CTA), or the
+  // one blockIdx.y names: small batches spread the orientations over CTAs for latency
+  const int mu_begin = gridDim.y == 7 ? blockIdx.y : 0, mu_end = gridDim.y == 7 ? mu_begin + 1 : 7;
+#pragma unroll 1
+  for (int mu = mu_begin; mu < mu_end; mu++) {
+  const int plane = nu * 7 + mu;
+  __syncthreads();   // the previous orientation is done with cf (and, the first time, the tile is complete after the next barrier)
+  for (int i = tid; i < K * KP; i += 256) {
+    const int jj = i / KP, ii = i - jj * KP;
+    cf[jj][ii] = ii < K ? coef[mu * K * K + jj * K + ii] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
   float re[2][4], im[2][4];
 #pragma unroll
   for (int o = 0; o < 4; o++) { re[0][o] = re[1][o] = 0.f; im[0][o] = im[1][o] = 0.f; }
@@ -369,6 +375,7 @@ __global__ void __launch_bounds__(256, 2) k_gabor_mag(const FaceDesc* __restrict
     atomicMin(&mm[0], umin);
     atomicMax(&mm[1], umax);
   }
+  }   // orientations
 }
 
 // a6 for the 9x9 .. 25x25 kernels in SEPARABLE form (the canonical arithmetic for these sizes):
