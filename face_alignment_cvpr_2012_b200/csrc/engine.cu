@@ -425,8 +425,8 @@ static int launch_traverse(crf_ctx* c, const FaceDesc* fd, int n, int Hmax, bool
       const int nitems = n * ncols, grid = std::min(nitems, c->sm_count);
       // (warps per CTA) | (walks per lane) << 8; CRF_WIN_HP / CRF_WIN_FFD override for experiments
       const bool fmt2 = c->win_fmt == 2 && (hp ? c->tex_hp_n : c->tex_mp_n) != 0;
-      // defaults measured on B200 (tools/win2_variants.py): head pose 32 warps x 1 walk (30 x 1 for k_traverse_win), FFD 20 warps x 2 walks
-      const int wv = hp ? (c->win_hp ? c->win_hp : ((fmt2 ? 32 : 30) | 1 << 8)) : (c->win_ffd ? c->win_ffd : (20 | 2 << 8));
+      // defaults measured on B200 (tools/win2_variants.py): head pose 15 warps x 2 pipelined walks (30 x 1 for k_traverse_win), FFD 20 warps x 2 walks
+      const int wv = hp ? (c->win_hp ? c->win_hp : (fmt2 ? (15 | 2 << 8) : (30 | 1 << 8))) : (c->win_ffd ? c->win_ffd : (20 | 2 << 8));
       bool ok = false;
 #define CRF_WIN2(NW_, WK_)                                                                                                  \
       if (fmt2 && wv == (NW_ | WK_ << 8)) {                                                                                  \

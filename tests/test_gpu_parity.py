@@ -143,7 +143,7 @@ def test_window_traversal_forced(O, crf, gpu, synth_models, monkeypatch, H, W, n
     gm, om = synth_models
     monkeypatch.setenv("CRF_TRAVERSE_VARIANT", "0x100001")
     if win == "rows":
-        monkeypatch.setenv("CRF_WIN_HP", str(30 | 1 << 8)); monkeypatch.setenv("CRF_WIN_FFD", str(20 | 2 << 8))
+        monkeypatch.setenv("CRF_WIN_HP", str(32 | 1 << 8)); monkeypatch.setenv("CRF_WIN_FFD", str(20 | 2 << 8))
     elif win == "pairx":
         monkeypatch.setenv("CRF_WIN_HP", str(15 | 2 << 8 | 1 << 12)); monkeypatch.setenv("CRF_WIN_FFD", str(20 | 2 << 8 | 1 << 12))
     elif win == "fmt1":   # k_traverse_win on the records that keep leaf slots (the default is k_traverse_win2 on DevSlotN)
