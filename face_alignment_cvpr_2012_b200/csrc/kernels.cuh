@@ -1500,6 +1500,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win2(TraverseArgs a, in
     int32_t* out = a.leaf_out + f * a.leaf_face_stride;
     const bool vx = x0 + lx < nx;
     const int ntile_y = (ny + kWinTile - 1) / kWinTile;
+    // the warp's first tree is the same for every tile of the item: its root index (two dependent global loads) is looked up once here,
+    // not at the start of every tile, where all warps would wait for it together
+    const int task0 = WALKS == 2 ? warp : (warp >> 1);
+    const int root0 = task0 < nt ? __ldg(a.nroot_of_slot + roots[task0]) : -1;
     for (int iyb = 0; iyb < ntile_y; iyb++) {
       const int y0 = iyb * kWinTile;
       const int rbeg = iyb == 0 ? 0 : y0 + kWinExtent, rend = min(y0 + kWinRows, nrows);
@@ -1557,7 +1561,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win2(TraverseArgs a, in
         const uint32_t rowA = ra * kWinRowBytes, rowB = rb * kWinRowBytes;
         const bool vA = vx && y0 + ly < ny, vB = vx && y0 + ly + 4 < ny;
         for (int t = warp; t < nt; t += NW) {
-          const int root = __ldg(a.nroot_of_slot + roots[t]);
+          const int root = t == warp ? root0 : __ldg(a.nroot_of_slot + roots[t]);
           int ca = vA ? root : -1, cb = vB ? root : -1;   // lanes outside the grid start parked; their result is never stored
           uint4 a0, a1, b0, b1;
           fetch(ca, a0, a1);
@@ -1594,7 +1598,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win2(TraverseArgs a, in
           ra -= ra >= kWinRows ? kWinRows : 0;
           const uint32_t rowA = ra * kWinRowBytes;
           const bool vA = vx && y0 + py < ny;
-          int ca = vA ? __ldg(a.nroot_of_slot + roots[t]) : -1;
+          int ca = vA ? (k < NW ? root0 : __ldg(a.nroot_of_slot + roots[t])) : -1;
           uint4 a0, a1;
           while (__any_sync(0xffffffffu, ca >= 0)) {
             const bool la = ca >= 0;
