@@ -532,7 +532,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                          "alg_bytes_per_launch": alg_bytes / launches_ffd, "launches_per_step": launches_ffd, "ms_per_step": ffd_ms, "physical": phys},
             "stages_ms_per_step": per_step,
             "kernels": [
-                {"kernel": "k_traverse_win2<32,1> (head-pose forest)", "ms_per_step": hp_ms,
+                {"kernel": "k_traverse_win2<15,2> (head-pose forest)", "ms_per_step": hp_ms,
                  "hbm_equivalent_gbs": (48 * work["hp_node_tests"] + 4 * work["hp_traversals"]) / (hp_ms * 1e-3) / 1e9 if hp_ms > 0 else 0.0,
                  "physical": physical("k_traverse_win_hp", work["hp_node_tests"], hp_ms)},
                 {"kernel": "k_gabor_sep<9..25> + k_gabor_mag<7> + quantise/integral", "bound": "fp32 issue (non-tensor FFMA) + shared-memory operands", "ms_per_step": gabor_ms,
