@@ -377,6 +377,26 @@ def test_batch_api_and_chunk_independence(crf, O, synth_models, gpu):
     _check_faces(a, want)
 
 
+def test_video_batch_is_cut_in_two_and_stays_identical(crf, O, synth_models, gpu):
+    """A batch that fits one launch but moves >= 64 KB of box pixels per face (faces in video frames) runs as two chunks so that the second
+    half's pack + copy overlaps the first half's kernels (analyze_host): 36 frames 1080p x 16 faces of 150..220 px, against the same call with an
+    explicit max_chunk (which switches the automatic cut off), pinned and pageable sources, and the oracle on a few faces."""
+    import torch
+    from face_alignment_cvpr_2012_b200 import workloads as wl
+    gm, om = synth_models
+    frames, boxes, iob, _ = wl.make_frames(36, 1080, 1920, 16, seed=12, wmin=150, wmax=220)
+    assert len(boxes) >= 512 and int((boxes[:, 2].astype(np.int64) * boxes[:, 3] * 3).mean()) >= 64 * 1024
+    auto_ctx = crf.Context(gm, 0)
+    auto = auto_ctx.analyze_batch(frames, boxes, iob)
+    one = crf.Context(gm, 0, crf._options(None, max_chunk=4096)).analyze_batch(frames, boxes, iob)
+    assert auto.tobytes() == one.tobytes()
+    pinned = torch.from_numpy(frames).pin_memory().numpy()
+    assert auto_ctx.analyze_batch(pinned, boxes, iob).tobytes() == one.tobytes()
+    idx = [0, len(boxes) // 2 - 1, len(boxes) // 2, len(boxes) - 1]
+    want = np.array([om.analyze_face(frames[iob[i]], boxes[i]) for i in idx])
+    _check_faces(auto[idx], want)
+
+
 def test_mixed_resolution_images(crf, O, synth_models, gpu):
     """BASELINE config 5 shape: images from 480p to 4K, 1-8 boxes each, face boxes from 64 px to >1000 px wide
     (heavy down-scaling in cv::resize, tall scaled faces), each image through crf_analyze_faces."""
