@@ -1504,6 +1504,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win2(TraverseArgs a, in
     // not at the start of every tile, where all warps would wait for it together
     const int task0 = WALKS == 2 ? warp : (warp >> 1);
     const int root0 = task0 < nt ? __ldg(a.nroot_of_slot + roots[task0]) : -1;
+    // ... and so is that tree's root RECORD: kept in registers for the item, so the first test of every tile starts without a fetch
+    uint4 rr0, rr1;
+    fetch(root0, rr0, rr1);
     for (int iyb = 0; iyb < ntile_y; iyb++) {
       const int y0 = iyb * kWinTile;
       const int rbeg = iyb == 0 ? 0 : y0 + kWinExtent, rend = min(y0 + kWinRows, nrows);
@@ -1564,7 +1567,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_traverse_win2(TraverseArgs a, in
           const int root = t == warp ? root0 : __ldg(a.nroot_of_slot + roots[t]);
           int ca = vA ? root : -1, cb = vB ? root : -1;   // lanes outside the grid start parked; their result is never stored
           uint4 a0, a1, b0, b1;
-          fetch(ca, a0, a1);
+          if (t == warp) { a0 = rr0; a1 = rr1; } else fetch(ca, a0, a1);
           for (;;) {
             // Steady state: test A_k, fetch A_k+1, test B_k, fetch B_k+1, ... — one walk's fetch is in flight while the other walk is
             // tested.  The body starts at "fetch B" so that the fetches in flight are in the same order on every path into a test
