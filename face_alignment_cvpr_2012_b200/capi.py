@@ -65,7 +65,7 @@ EXPORTS = [
     "crf_stage_gray_resize", "crf_stage_channels", "crf_stage_minmax", "crf_stage_norm", "crf_stage_canny", "crf_stage_eval_forest", "crf_stage_headpose",
     "crf_stage_compose", "crf_stage_compose_batch", "crf_stage_votes_meanshift", "crf_stage_meanshift",
     "crf_model_load_forest", "crf_model_set_features", "crf_model_get_features", "crf_model_leaf_dump", "crf_stage_feature_channels",
-    "crf_stage_eval_patches", "crf_stage_eval_tests", "crf_model_load_tree", "crf_stage_meanshift_opt", "crf_stage_area_under_curve",
+    "crf_stage_eval_patches", "crf_stage_eval_tests", "crf_stage_eval_tests_sum", "crf_model_load_tree", "crf_stage_meanshift_opt", "crf_stage_area_under_curve",
     "crf_cascade_load", "crf_cascade_free", "crf_cascade_info", "crf_detect_faces",
     "crf_multi_create", "crf_multi_destroy", "crf_multi_device_count", "crf_multi_ctx", "crf_multi_analyze_batch", "crf_multi_analyze_crops",
 ]
@@ -139,6 +139,7 @@ def lib() -> C.CDLL:
     L.crf_stage_feature_channels.argtypes = [vp, u8p, C.c_int, C.c_int, i32p, C.c_int, u8p, C.POINTER(C.c_uint32)]
     L.crf_stage_eval_patches.argtypes = [vp, C.c_int, i32p, i32p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i32p]
     L.crf_stage_eval_tests.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i32p]
+    L.crf_stage_eval_tests_sum.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i32p]
     L.crf_model_load_tree.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.crf_stage_meanshift_opt.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, C.c_float, f32p, i32p, i32p]
     L.crf_stage_area_under_curve.argtypes = [vp, C.c_float, C.c_float, C.c_double, C.c_double, f32p]

@@ -1718,6 +1718,33 @@ int crf_stage_eval_tests(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int
   return CRF_OK;
 }
 
+int crf_stage_eval_tests_sum(crf_ctx* c, const uint8_t* planes_u8, int C, int W, int H, const int* tests, int n, int* out) {
+  if (!c) return fail(CRF_ERR_STATE, "context is not initialised");
+  if (n < 0 || C < 1 || W < 1 || H < 1 || !planes_u8 || (n > 0 && (!tests || !out))) return fail(CRF_ERR_ARG, "bad argument");
+  if (n == 0) return CRF_OK;
+  for (int i = 0; i < n; i++) {
+    const int* t = tests + (size_t)i * 11;
+    if (t[0] < 0 || t[0] >= C) return fail(CRF_ERR_ARG, "test reads a channel the planes do not provide");
+    for (int k = 0; k < 2; k++) {
+      const int x = t[9] + t[1 + 4 * k], y = t[10] + t[2 + 4 * k], w = t[3 + 4 * k], h = t[4 + 4 * k];
+      if (w < 1 || h < 1 || x < 0 || y < 0 || x + w > W || y + h > H) return fail(CRF_ERR_ARG, "test rectangle outside the face");
+    }
+  }
+  CU(cudaSetDevice(c->device));
+  Buf d_p, d_t, d_o;
+  struct Free { Buf* b[3]; ~Free() { for (Buf* x : b) x->release(); } } fr{{&d_p, &d_t, &d_o}};
+  int rc;
+  const size_t pbytes = (size_t)C * W * H;
+  if ((rc = d_p.reserve(pbytes)) || (rc = d_t.reserve((size_t)n * 44)) || (rc = d_o.reserve((size_t)n * 4))) return rc;
+  CU(cudaMemcpyAsync(d_p.p, planes_u8, pbytes, cudaMemcpyHostToDevice, c->w->stream));
+  CU(cudaMemcpyAsync(d_t.p, tests, (size_t)n * 44, cudaMemcpyHostToDevice, c->w->stream));
+  k_eval_tests_sum<<<(n + 127) / 128, 128, 0, c->w->stream>>>(d_p.as<uint8_t>(), W, H, d_t.as<int>(), n, d_o.as<int>());
+  KCHECK(); count_launch(c, CRF_STAGE_PLAIN);
+  CU(cudaMemcpyAsync(out, d_o.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->w->stream));
+  CU(cudaStreamSynchronize(c->w->stream));
+  return CRF_OK;
+}
+
 static void fill_list_out(crf_ctx* c, const std::vector<int32_t>& list, int n, int* tree_forest, int* tree_index) {
   for (int i = 0; i < n; i++) {
     const auto it = std::upper_bound(c->mp.roots.begin(), c->mp.roots.end(), list[i]);  // roots ascend with the tree number

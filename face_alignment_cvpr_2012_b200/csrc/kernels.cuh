@@ -1174,6 +1174,26 @@ __global__ void k_eval_tests(const stack_t* __restrict__ stack, size_t plane_str
   out[i] = mean[0] - mean[1];
 }
 
+// The same test on the 8-bit planes themselves: the !m_use_integral branch of ImageSample::evalTest (src/ImageSample.cpp:40-47), cv::sum over
+// the two rectangles.  planes: [C][H][W] u8, dense.  cv::sum is exact (double), the quotient by float(area) truncates to the same integer as the
+// integral branch (sums < 2^24), so the integer division below is both branches' result; what differs is where the sum comes from.
+__global__ void k_eval_tests_sum(const uint8_t* __restrict__ planes, int W, int H, const int* __restrict__ tests, int n, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int* t = tests + (size_t)i * 11;
+  const uint8_t* __restrict__ pl = planes + (size_t)t[0] * W * H;
+  int mean[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int x = t[9] + t[1 + 4 * k], y = t[10] + t[2 + 4 * k], w = t[3 + 4 * k], h = t[4 + 4 * k];
+    uint32_t s = 0;
+    for (int r = 0; r < h; r++)
+      for (int c = 0; c < w; c++) s += pl[(size_t)(y + r) * W + x + c];
+    mean[k] = (int)(s / (uint32_t)(w * h));
+  }
+  out[i] = mean[0] - mean[1];
+}
+
 // Exact floor(s / area) for s <= 255 * area < 2^18 without a stored reciprocal: float estimate, then a +-1 fix-up.
 __device__ __forceinline__ int mean_exact(uint32_t s, uint32_t area) {
   int q = (int)(__uint2float_rn(s) * __frcp_rn(__uint2float_rn(area)));

@@ -354,13 +354,15 @@ class Context:
                                                      capi.ptr(xy, C.c_int32), len(xy), capi.ptr(ids, C.c_int32)))
         return ids
 
-    def stage_eval_tests(self, planes: np.ndarray, tests) -> np.ndarray:
-        """ImageSample::evalTest for n tests {channel, r1(x,y,w,h), r2(x,y,w,h), patch_x, patch_y}."""
+    def stage_eval_tests(self, planes: np.ndarray, tests, use_integral: bool = True) -> np.ndarray:
+        """ImageSample::evalTest for n tests {channel, r1(x,y,w,h), r2(x,y,w,h), patch_x, patch_y}; use_integral selects the branch of
+        src/ImageSample.cpp:40-63 (integral corners, or cv::sum over the 8-bit rectangles)."""
         planes = np.ascontiguousarray(planes, np.uint8)
         Cn, H, W = planes.shape
         t = np.ascontiguousarray(tests, np.int32).reshape(-1, 11)
         out = np.zeros(len(t), np.int32)
-        capi.check(capi.lib().crf_stage_eval_tests(self.h, capi.ptr(planes, C.c_uint8), Cn, W, H, capi.ptr(t, C.c_int32), len(t), capi.ptr(out, C.c_int32)))
+        fn = capi.lib().crf_stage_eval_tests if use_integral else capi.lib().crf_stage_eval_tests_sum
+        capi.check(fn(self.h, capi.ptr(planes, C.c_uint8), Cn, W, H, capi.ptr(t, C.c_int32), len(t), capi.ptr(out, C.c_int32)))
         return out
 
     def stage_eval_forest(self, planes: np.ndarray, stride: int, forest_idx=None, tree_idx=None) -> np.ndarray:

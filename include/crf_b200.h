@@ -237,6 +237,9 @@ int crf_stage_eval_patches(crf_ctx* ctx, int which, const int* tree_forest, cons
 /* ImageSample::evalTest(SimplePatchFeature, Rect) (src/ImageSample.cpp:30-64) for n tests:
  * tests = n x {channel, x1, y1, w1, h1, x2, y2, w2, h2, patch_x, patch_y}; out[i] = mean(rect1) - mean(rect2). */
 int crf_stage_eval_tests(crf_ctx* ctx, const uint8_t* planes_u8, int C, int W, int H, const int* tests, int n, int* out);
+/* The same tests by the branch the reference takes when ImageSample was built with use_integral = false (src/ImageSample.cpp:40-47):
+ * cv::sum over the two rectangles of the 8-bit plane itself.  Same arguments, same results (both branches truncate exact sums). */
+int crf_stage_eval_tests_sum(crf_ctx* ctx, const uint8_t* planes_u8, int C, int W, int H, const int* tests, int n, int* out);
 /* getHeadPoseVotesMT reduce + areaUnderCurve + composition (src/face_utils.cpp:219-241, :304-323;
  * src/FaceForest.cpp:215-250) from planes: returns headpose, variance, counts, dominant and the composed list. */
 int crf_stage_headpose(crf_ctx* ctx, const uint8_t* planes_u8, int C, int W, int H, int stride,

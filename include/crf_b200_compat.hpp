@@ -206,7 +206,9 @@ class ImageSample {
     const int t[11] = {test.feature_channel, test.rect1.x, test.rect1.y, test.rect1.width, test.rect1.height,
                        test.rect2.x, test.rect2.y, test.rect2.width, test.rect2.height, rect.x, rect.y};
     int out = 0;
-    check(crf_stage_eval_tests(detail::plain_context(), planes_.data(), C_, W_, H_, t, 1, &out));
+    // the branch the reference takes follows m_use_integral: integral corners, or cv::sum over the 8-bit rectangles
+    check(m_use_integral ? crf_stage_eval_tests(detail::plain_context(), planes_.data(), C_, W_, H_, t, 1, &out)
+                         : crf_stage_eval_tests_sum(detail::plain_context(), planes_.data(), C_, W_, H_, t, 1, &out));
     return out;
   }
 

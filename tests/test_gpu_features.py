@@ -107,6 +107,8 @@ def test_evaluate_on_explicit_patches_and_eval_test(O, crf, gpu, synth_models, s
         m = [int(integ[c, py + y + h, px + x + w] - integ[c, py + y, px + x + w] - integ[c, py + y + h, px + x] + integ[c, py + y, px + x]) // (w * h) for (x, y, w, h) in r]
         tests.append([c, *r[0], *r[1], px, py]); want.append(m[0] - m[1])
     assert np.array_equal(crf.Context(None, 0).stage_eval_tests(planes, tests), np.array(want, np.int32))
+    # the !m_use_integral branch (cv::sum over the 8-bit rectangles, src/ImageSample.cpp:40-47) gives the same integers
+    assert np.array_equal(crf.Context(None, 0).stage_eval_tests(planes, tests, use_integral=False), np.array(want, np.int32))
 
 
 def test_multi_gpu_single_caller(crf, O, gpu, synth_models):
