@@ -52,6 +52,12 @@ int main(int argc, char** argv) {
   SimplePatchFeature test;
   test.feature_channel = 9; test.rect1 = cvlite::Rect(3, 4, 10, 7); test.rect2 = cvlite::Rect(12, 15, 5, 13);
   std::printf("sample.evalTest %d\n", sample.evalTest(test, cvlite::Rect(20, 30, 31, 31)));
+  {
+    // the !m_use_integral branch (src/ImageSample.cpp:40-47): 8-bit feature channels, cv::sum over the rectangles
+    ImageSample plain(img_scaled, hp_param.features, false);
+    std::printf("plain.type8u %d\n", (int)(plain.m_feature_channels[9].type() == CV_8UC1));
+    std::printf("plain.evalTest %d\n", plain.evalTest(test, cvlite::Rect(20, 30, 31, 31)));
+  }
 
   Forest<HeadPoseSample> hp_forest;
   if (!hp_forest.load(hp_dir, hp_param)) { std::puts("FAIL hp load"); return 1; }

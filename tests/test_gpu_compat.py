@@ -65,6 +65,7 @@ def test_reference_interface_in_cpp(crf, O, synth_dirs, synth_models, tmp_path, 
     def mean(c, px_, py_, rx, ry, rw, rh):
         return int(I[c, py_ + ry + rh, px_ + rx + rw] - I[c, py_ + ry, px_ + rx + rw] - I[c, py_ + ry + rh, px_ + rx] + I[c, py_ + ry, px_ + rx]) // (rw * rh)
     assert int(out["sample.evalTest"][0]) == mean(9, 20, 30, 3, 4, 10, 7) - mean(9, 20, 30, 12, 15, 5, 13)
+    assert int(out["plain.type8u"][0]) == 1 and int(out["plain.evalTest"][0]) == int(out["sample.evalTest"][0])
     # Forest<HeadPoseSample>::load / evaluateMT, Tree::evaluateMT, TreeNode
     s = O.Sample(planes=planes)
     ny1 = sh - 31
