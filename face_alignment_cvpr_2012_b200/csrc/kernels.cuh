@@ -2261,7 +2261,9 @@ __global__ void __launch_bounds__(BLOCK) k_meanshift_fast(const FaceDesc* __rest
 #pragma unroll 4
     for (int k = tid; k < cnt; k += BLOCK) {
       const int2 q = __ldg(v + k);
-      const float x = (float)(short)(q.x & 0xffff), y = (float)(q.x >> 16);
+      // int16 -> float through the mantissa (1.5 * 2^23 + i is exact for |i| < 2^22): an integer add and a float subtract instead of I2F, which
+      // issues on the quarter-rate XU pipe — with two I2F, a reciprocal square root and an exp2 per vote and pass this kernel was XU-bound
+      const float x = __int_as_float(0x4B400000 + (int)(short)(q.x & 0xffff)) - 12582912.f, y = __int_as_float(0x4B400000 + (q.x >> 16)) - 12582912.f;
       float w = __int_as_float(q.y);
       if (pass > 0) {
         const float dx = mx - x, dy = my - y;
