@@ -20,8 +20,8 @@ reduction are the only torch.distributed calls.
            the committed ncu capture of this build x the node tests counted live), the DRAM fraction, and the issue rate.
 `kernels`: the other kernel groups, each against the unit that bounds it (executed FFMA for the Gabor bank, bytes for
            votes / MeanShift).
-`other_workloads`: C2 at the reference's default strides and C3 (64 frames 1080p x 16 faces, crf_analyze_batch with host
-           frames), each with its own CPU sample; `strong`: 32 768 C2 crops split over the ranks, records gathered on
+`other_workloads`: C2 at the reference's default strides, C3 (64 frames 1080p x 16 faces, crf_analyze_batch with host frames), C4 (head-pose
+           forest only, 65 536 crops) and C5 (64 mixed-resolution images up to 4K, one call per image), each with its own CPU sample; `strong`: 32 768 C2 crops split over the ranks, records gathered on
            rank 0 inside the timed region; `single_caller`: crf_multi_* (one process, one host thread per GPU).
 `cpu_baseline` / `--impl reference`: the reference's ThreadPool CPU path on the box's host cores, on a bounded sample of
            the same workload: oracle/_ref (the reference's own sources compiled against type stand-ins, `kind` "reference")
@@ -150,7 +150,7 @@ def load_models(need_gpu: bool, need_oracle: bool):
     return gm, om, tag
 
 
-def cpu_sample(om, items, hp_stride: int, ffd_stride: int, budget_s: float, max_faces: int):
+def cpu_sample(om, items, hp_stride: int, ffd_stride: int, budget_s: float, max_faces: int, headpose_only: bool = False):
     """Reference-shaped CPU path of the oracle port (per-face ThreadPool over patches / Gabor filters) on all host cores.
     items: list of (bgr image, box)."""
     from oracle import oracle as O
@@ -158,7 +158,7 @@ def cpu_sample(om, items, hp_stride: int, ffd_stride: int, budget_s: float, max_
     n, t0, ms = 0, time.perf_counter(), []
     while n < min(max_faces, len(items)) and (time.perf_counter() - t0) < budget_s:
         t1 = time.perf_counter()
-        om.analyze_face(items[n][0], items[n][1], hp_stride, ffd_stride, threads=cores)
+        om.analyze_face(items[n][0], items[n][1], hp_stride, ffd_stride, threads=cores, headpose_only=headpose_only)
         ms.append((time.perf_counter() - t1) * 1e3); n += 1
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "faces": n, "p50_ms_per_face": float(np.median(ms))}
@@ -232,10 +232,11 @@ def cv2_channel_ms(items, n: int = 3):
         return {"error": str(e)}
 
 
-def cpu_baseline(om, items, hp_stride: int, ffd_stride: int, budget_s: float, max_faces: int, what: str):
-    """Port and (when staged) the real reference on the same sample; the faster one is the headline."""
-    port = cpu_sample(om, items, hp_stride, ffd_stride, budget_s, max_faces)
-    ref = ref_sample(items, hp_stride, ffd_stride, budget_s, max_faces)
+def cpu_baseline(om, items, hp_stride: int, ffd_stride: int, budget_s: float, max_faces: int, what: str, headpose_only: bool = False):
+    """Port and (when staged) the real reference on the same sample; the faster one is the headline.  headpose_only (C4): the port only —
+    the reference's analyzeFace has no way to stop after getHeadPoseVotesMT."""
+    port = cpu_sample(om, items, hp_stride, ffd_stride, budget_s, max_faces, headpose_only)
+    ref = None if headpose_only else ref_sample(items, hp_stride, ffd_stride, budget_s, max_faces)
     best = dict(ref if (ref and ref["value"] > port["value"]) else port)
     best["sample"] = f"first {best['faces']} faces of {what} (strides {hp_stride}/{ffd_stride}), one face at a time, ThreadPool over {best['cores']} host threads per face"
     best["port"] = {k: port[k] for k in ("value", "faces", "p50_ms_per_face")}
@@ -330,6 +331,33 @@ def other_workloads(crf, wl, torch, gm, om, local_rank, dev, crops, args):
         if om is not None:
             out["C3"]["cpu_baseline"] = cpu_baseline(om, [(frames[i], tuple(int(v) for v in b)) for b, i in zip(boxes, iob)], 4, 3, 5.0, 64, "the same frames")
         del one
+        # C4: head-pose forest only on 65 536 crops at the reference's stride 4 (stops after getHeadPoseVotesMT): 16 calls on this rank's pinned
+        # 4096-crop block, so that the host memory of the default run stays small; the path's cost does not depend on the content
+        hp_rec = np.zeros(F, crf.FACE_DTYPE)
+        ctx.analyze_crops_ptr(h.data_ptr(), F, CROP, CROP, hp_rec, headpose_only=True)
+        ncall = max(1, 65536 // F)
+        t0 = time.perf_counter()
+        for _ in range(ncall):
+            ctx.analyze_crops_ptr(h.data_ptr(), F, CROP, CROP, hp_rec, headpose_only=True)
+        dt = time.perf_counter() - t0
+        out["C4"] = {"workload": f"head-pose forest only, {ncall * F} crops 100x100 as {ncall} crf_headpose_crops calls of {F} pinned host crops, stride 4", "value": ncall * F / dt,
+                     "unit": UNIT, "ms_per_call": 1e3 * dt / ncall}
+        if om is not None:
+            out["C4"]["cpu_baseline"] = cpu_baseline(om, [(c, (0, 0, CROP, CROP)) for c in crops[:64]], 4, 3, 3.0, 64, "the same crops, head pose only", headpose_only=True)
+        # C5: 64 mixed-resolution images (480p .. 4K, 1-8 boxes each, widths 64..1500), one crf_analyze_faces call per image, pageable host frames
+        imgs, tag5 = wl.make_mixed(args.c5_images, seed=2015)
+        nfaces5 = sum(len(bx) for _, bx in imgs)
+        for fr5, bx5 in imgs[:5]:
+            ctx.analyze_faces(fr5, bx5)
+        t0 = time.perf_counter()
+        for fr5, bx5 in imgs:
+            ctx.analyze_faces(fr5, bx5)
+        dt = time.perf_counter() - t0
+        out["C5"] = {"workload": f"{len(imgs)} mixed-resolution images (480p .. 4K) with {nfaces5} faces in all, one crf_analyze_faces call per image, pageable host frames, reference default strides",
+                     "value": nfaces5 / dt, "unit": UNIT, "images_per_s": len(imgs) / dt, "ms_per_image": 1e3 * dt / len(imgs), "data": tag5}
+        if om is not None:
+            items5 = [(fr5, tuple(int(v) for v in b)) for fr5, bx5 in imgs for b in bx5]
+            out["C5"]["cpu_baseline"] = cpu_baseline(om, items5, 4, 3, 3.0, 32, "the same images")
         ctx.close()
     except Exception as e:  # noqa: BLE001
         out["error"] = str(e)
@@ -598,6 +626,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip other_workloads / single_caller")
     ap.add_argument("--strong-faces", type=int, default=32768, help="total crops of the strong-scaling pass (0 = skip)")
     ap.add_argument("--c3-frames", type=int, default=64)
+    ap.add_argument("--c5-images", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     # stdout carries exactly one JSON line: library banners written to fd 1 meanwhile (NCCL prints its version there) go to stderr
