@@ -1,7 +1,7 @@
 """GPU: the CUDA path (through the C ABI) against the CPU oracle on the same inputs, stage by stage and end to end.
 Bit-exact for every integer / byte / index result (scaled pixels, 8-bit planes, integrals, leaf ids, vote lists,
-head pose and its variance, forest composition); MeanShift means within the 0.5 px of the north star (observed
-<= 1e-4: the only non-identical operation is exp())."""
+head pose and its variance, forest composition); MeanShift means within the 0.5 px of the north star (observed: 0.0 px in the
+exact mode, <= 0.024 px in the default tolerance mode on a 3543-face campaign)."""
 import zlib
 from pathlib import Path
 
